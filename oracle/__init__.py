@@ -1,0 +1,5 @@
+"""CPU oracle -- TEST INFRASTRUCTURE ONLY (see oracle/tabletop_oracle.c header).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import
+this package.  The product package `earl_benchmark_b200` never does.
+"""
