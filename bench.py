@@ -1,0 +1,292 @@
+#!/usr/bin/env python
+"""bench.py -- batched env-steps/sec of the tabletop_manipulation hot path on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--num-envs E]
+
+Workload (BASELINE.json configs[1]): tabletop_manipulation, sparse reward, reset-free train horizon
+200,000, 1,048,576 envs per GPU (weak scaling), random actions pre-generated on the device
+(torch.rand, seed 1234+rank) in a ring of 64 batches (768 MB > L2), observations / rewards / dones
+written to a ring of 16 output slots (848 MB > L2).  One "step" = one launch of the fused step kernel
+over the whole batch (env.step + PersistentStateWrapper bookkeeping).
+
+One JSON line on stdout (rank 0):
+  value        whole-job env-steps/s, inputs resident in HBM, CUDA-event timed, max over ranks
+  e2e          same metric through the public API with HOST (pinned) buffers: H2D of the actions and D2H of
+               obs/reward/done/success inside the timed region, every step
+  roofline     HBM roofline of the step kernel: 113 algorithmic bytes per env-step
+  cpu_baseline the CPU oracle (C port of the reference arithmetic, OpenMP, all host threads) on a bounded
+               sample of the same workload (rank 0, N=1 only)
+`--impl reference` times that CPU port alone on the same config (the reference itself is Python over
+mujoco-py and cannot run on the GPU box).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+ALG_BYTES_PER_ENV_STEP = 113  # read 36 B, write 77 B
+METRIC = "batched env-steps/sec (tabletop_manipulation, sparse, reset-free)"
+UNIT = "env-steps/s"
+ACTION_RING, OUT_RING = 64, 16
+TRAIN_HORIZON = 200000
+
+
+def measured_peak_gbs():
+    p = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 100 ms while the benchmark runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,utilization.gpu,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
+
+    def stop(self, t0=None, t1=None):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for ts, r in self.rows if (t0 is None or ts >= t0 - 0.1) and (t1 is None or ts <= t1 + 0.1)]
+        if not rows:
+            rows = [r for _, r in self.rows]
+        sm, mx, reasons = [], None, set()
+        for r in rows:
+            try:
+                clk, mxc, util = float(r[0]), float(r[1]), float(r[3])
+            except Exception:
+                continue
+            mx = mxc
+            if util >= 10:
+                sm.append(clk)
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            sm = [float(r[0]) for r in rows if r[0].replace(".", "").isdigit()]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(rows)}
+
+
+# ----------------------------------------------------------------------------------------------- CPU arm
+
+def cpu_port_rate(num_envs, steps, threads, budget_s=20.0):
+    """env-steps/s of the CPU oracle (step-major: all envs advance one step at a time, like a vector env).
+    The sample is bounded to about `budget_s` seconds: fewer envs per step if needed, never fewer steps."""
+    import numpy as np
+    os.environ["OMP_NUM_THREADS"] = str(threads)
+    from oracle import loader
+    L = loader.lib()
+    ring = 4
+
+    def run(n, k):
+        rs = np.random.RandomState(1234)
+        acts = rs.uniform(-1, 1, (ring, n, 3)).astype(np.float32)
+        qpos = np.tile(np.array([0.0, 0.0, 2.5, 0.0]), (n, 1))
+        att = np.zeros(n, np.int32)
+        goal = np.tile(loader.INITIAL_STATE, (n, 1))
+        goal[:, 2:4] = loader.GOAL_STATES[rs.randint(0, 4, n), 2:4]
+        total, since = np.zeros(n, np.int64), np.zeros(n, np.int64)
+        obs, rew, done = np.zeros((n, 12), np.float32), np.zeros(n), np.zeros(n, np.uint8)
+        t0 = time.perf_counter()
+        L.earl_oracle_tt_rollout_stepmajor(n, k, ring, qpos, att, goal, acts, 0, 0, 1, total, since, TRAIN_HORIZON,
+                                           obs, rew, done)
+        return time.perf_counter() - t0
+
+    n = min(num_envs, 1 << 16)
+    run(n, 2)                      # touch pages, spin up threads
+    t = run(n, 8) / 8              # seconds per step at the calibration size
+    per_env_step = t / n
+    n_sample = num_envs
+    if per_env_step * num_envs * steps > budget_s:
+        n_sample = max(1 << 14, int(budget_s / (per_env_step * steps)))
+        n_sample = min(num_envs, n_sample)
+    el = run(n_sample, steps)
+    return n_sample * steps / el, n_sample, el
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    threads = os.cpu_count() or 1
+    n_total = args.num_envs * args.gpus
+    cpu_port_rate(1 << 14, max(1, args.warmup), threads, budget_s=2.0)
+    rate, n_sample, el = cpu_port_rate(n_total, args.steps, threads, budget_s=90.0)
+    sample = (f"{n_sample} of {n_total} envs x {args.steps} steps, step-major, OpenMP {threads} threads, "
+              f"{el:.2f} s; C port of reference tabletop step + PersistentStateWrapper (the reference itself is Python "
+              "over mujoco-py and cannot run here)")
+    line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * n_total / rate, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": config_dict(args, n_total),
+            "cpu_baseline": {"value": rate, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def config_dict(args, n_total):
+    return {"workload": "tabletop_manipulation sparse reward, reset-free train horizon 200000, random actions "
+                        "(BASELINE.json configs[1])",
+            "envs_per_gpu": args.num_envs, "total_envs": n_total, "state_dtype": "float32",
+            "action_ring": ACTION_RING, "out_ring": OUT_RING,
+            "l2": "inputs larger than L2: action ring 64 x 12.6 MB, output ring 16 x 55.6 MB; per-env state "
+                  "(25 MB) is deliberately left L2-resident between steps",
+            "parallelism": f"env-sharded x{args.gpus}, no collective on the step path"}
+
+
+# ----------------------------------------------------------------------------------------------- GPU arm
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import earl_benchmark_b200 as eb
+    from earl_benchmark_b200.distributed import init_from_env, max_over_ranks
+
+    rank, world, local = init_from_env()
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    n = args.num_envs
+    n_total = n * world
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    loader = eb.EARLEnvs("tabletop_manipulation", reward_type="sparse", num_envs=n_total, rank=rank, world_size=world,
+                         device=dev, seed=0, train_horizon=TRAIN_HORIZON, goal_stream_rows=2)
+    train, _ = loader.get_envs()
+    train.reset()
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(1234 + rank)
+    actions = torch.rand((ACTION_RING, n, 3), generator=gen, device=dev, dtype=torch.float32) * 2 - 1
+    obs = torch.empty((OUT_RING, n, 12), device=dev, dtype=torch.float32)
+    rew = torch.empty((OUT_RING, n), device=dev, dtype=torch.float32)
+    done = torch.empty((OUT_RING, n), device=dev, dtype=torch.uint8)
+    env = train.env
+    sampler = ClockSampler(local) if rank == 0 else None
+
+    # warm-up: W steps as asked, then keep the GPU busy for >= 1 s so clocks are sampled under load
+    env.rollout_into(actions, max(args.warmup, 3), obs, rew, done)
+    torch.cuda.synchronize()
+    t_w = time.perf_counter()
+    while time.perf_counter() - t_w < 1.0:
+        env.rollout_into(actions, 256, obs, rew, done)
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing: exactly K steps, CUDA events on the launching stream
+    launches0 = env.launch_count
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_region0 = time.perf_counter()
+    e0.record()
+    env.rollout_into(actions, args.steps, obs, rew, done)
+    e1.record()
+    barrier()
+    t_region1 = time.perf_counter()
+    ms = max_over_ranks(e0.elapsed_time(e1), dev)
+    launches = env.launch_count - launches0
+    value = n_total * args.steps / (ms * 1e-3)
+
+    # ---- end to end through the public API with host buffers
+    e2e_steps = args.steps if args.e2e_steps is None else args.e2e_steps
+    host_actions = [(torch.rand((n, 3), dtype=torch.float32) * 2 - 1).pin_memory() for _ in range(4)]
+    for k in range(3):
+        train.step(host_actions[k % 4])
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(e2e_steps):
+        ho, hr, hd, hinfo = train.step(host_actions[k % 4])   # numpy views of pinned result buffers
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0, dev)
+    e2e_value = n_total * e2e_steps / e2e_s
+    h2d = n * 3 * 4
+    d2h = n * (12 * 4 + 4 + 1 + 1)
+    clocks = sampler.stop(t_region0, t_region1) if sampler else None
+
+    if rank == 0:
+        peak, peak_src = measured_peak_gbs()
+        per_launch_s = ms * 1e-3 / args.steps
+        achieved = ALG_BYTES_PER_ENV_STEP * n / per_launch_s / 1e9
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config_dict(args, n_total),
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d * world,
+                        "d2h_bytes_per_step": d2h * world, "steps": e2e_steps,
+                        "api": "PersistentStateWrapper.step(pinned host actions) -> host obs/reward/done/success"},
+                "gpu_launches": launches,
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                             "traffic": args.traffic_bytes, "peak_source": peak_src,
+                             "kernel": "earl::tabletop_step_kernel<false,true>",
+                             "algorithmic_bytes_per_launch": ALG_BYTES_PER_ENV_STEP * n,
+                             "avg_launch_us": per_launch_s * 1e6},
+                "clocks": clocks}
+        if world == 1 and not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            rate, n_sample, el = cpu_port_rate(n, min(args.steps, 200), threads, budget_s=15.0)
+            line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+                                    "sample": f"{n_sample} envs x {min(args.steps, 200)} steps of the same workload, "
+                                              f"step-major C oracle, OpenMP {threads} threads, {el:.2f} s"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=100)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--num-envs", type=int, default=1 << 20, help="envs per GPU")
+    ap.add_argument("--e2e-steps", type=int, default=None)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--traffic-bytes", type=float, default=None,
+                    help="dram bytes per launch from the committed ncu capture (profiles/), else null")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    if args.gpus > 1 and "WORLD_SIZE" not in os.environ:
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", "29577", os.path.abspath(__file__)] + sys.argv[1:]
+        return subprocess.call(cmd)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

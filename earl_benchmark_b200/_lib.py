@@ -1,0 +1,101 @@
+"""ctypes binding of libearl_b200.so (the C ABI declared in include/earl_b200.h).
+
+There is no CPU fallback: if the CUDA library is missing this module raises at import of the first
+symbol, and every compute entry point fails without a CUDA device.
+"""
+import ctypes as C
+import os
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libearl_b200.so")
+
+# mirror of include/earl_b200.h ------------------------------------------------------------------
+EARL_ABI_VERSION = 1
+ENV_TABLETOP, ENV_SAWYER_DOOR, ENV_SAWYER_PEG, ENV_KITCHEN = 0, 1, 2, 3
+FLAG_DENSE_REWARD = 0x01
+FLAG_WIDE_INIT = 0x02
+FLAG_STATE_F64 = 0x04
+FLAG_LIFELONG = 0x08
+FLAG_AUTO_RESET = 0x10
+FLAG_RESET_AT_GOAL = 0x20
+FLAG_EVAL_STATS = 0x40
+TABLETOP_MAGIC = 0x54544142
+
+
+class EarlConfig(C.Structure):
+    _fields_ = [("env_kind", C.c_int32), ("num_envs", C.c_int32), ("device", C.c_int32), ("flags", C.c_uint32),
+                ("episode_horizon", C.c_int64), ("goal_change_frequency", C.c_int64),
+                ("goal_stream_rows", C.c_int32), ("reserved", C.c_int32)]
+
+
+class TabletopModel(C.Structure):
+    _fields_ = [("magic", C.c_uint32), ("num_goals", C.c_int32), ("threshold", C.c_double),
+                ("move_distance", C.c_double), ("clip", C.c_double), ("success_radius", C.c_double),
+                ("initial_state", C.c_double * 6), ("goal_table", (C.c_double * 6) * 256)]
+
+
+# (name, restype, argtypes) for EVERY symbol the header declares; tests/test_abi.py checks the list
+# against the header text and the built library.
+_VP, _I32, _I64, _U32, _SZ = C.c_void_p, C.c_int32, C.c_int64, C.c_uint32, C.c_size_t
+SIGNATURES = [
+    ("earl_abi_version", C.c_int, []),
+    ("earl_last_error", C.c_char_p, []),
+    ("earl_create", C.c_int, [C.POINTER(EarlConfig), _VP, _SZ, C.POINTER(_VP)]),
+    ("earl_destroy", C.c_int, [_VP]),
+    ("earl_num_envs", C.c_int, [_VP]),
+    ("earl_obs_dim", C.c_int, [_VP]),
+    ("earl_action_dim", C.c_int, [_VP]),
+    ("earl_set_goal_stream", C.c_int, [_VP, _VP, _I32]),
+    ("earl_reset", C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP]),
+    ("earl_set_goal", C.c_int, [_VP, _VP, _VP, _VP]),
+    ("earl_set_goal_table", C.c_int, [_VP, _VP, _I32, _I32]),
+    ("earl_step", C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP, _VP]),
+    ("earl_rollout", C.c_int, [_VP, _VP, _I32, _I32, _VP, _VP, _VP, _VP, _I32, _VP]),
+    ("earl_step_host", C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP]),
+    ("earl_get_obs", C.c_int, [_VP, _VP, _VP]),
+    ("earl_compute_reward", C.c_int, [_VP, _VP, _I64, _VP, _VP, _VP]),
+    ("earl_counters", C.c_int, [_VP, C.POINTER(_I64), _VP, _VP, _VP, _VP]),
+    ("earl_eval_stats", C.c_int, [_VP, _VP, _VP]),
+    ("earl_state_nbytes", _SZ, [_VP]),
+    ("earl_get_state", C.c_int, [_VP, _VP, _SZ]),
+    ("earl_set_state", C.c_int, [_VP, _VP, _SZ]),
+    ("earl_launch_count", _I64, [_VP]),
+    ("earl_rng_create", _VP, [_I32, _VP, _I32]),
+    ("earl_rng_destroy", None, [_VP]),
+    ("earl_rng_next_u32", _U32, [_VP]),
+    ("earl_rng_py_randbelow", None, [_VP, _U32, _I64, _VP]),
+    ("earl_rng_tabletop_goal_rows", None, [_VP, _VP, _U32, _I64, _VP]),
+    ("earl_rng_np_randint", None, [_VP, _U32, _I64, _VP]),
+    ("earl_rng_np_uniform", None, [_VP, C.c_double, C.c_double, _I64, _VP]),
+]
+
+_lib = None
+
+
+class EarlError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"libearl_b200 error {code}: {msg}")
+        self.code = code
+
+
+def lib():
+    """Load the CUDA library.  Fails loudly when it has not been built (no fallback path exists)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} is missing: build it with `python -m earl_benchmark_b200.build` "
+                "(nvcc, sm_100a). earl_benchmark_b200 has no CPU or PyTorch fallback.")
+        L = C.CDLL(LIB_PATH)
+        for name, res, args in SIGNATURES:
+            fn = getattr(L, name)
+            fn.restype, fn.argtypes = res, args
+        if L.earl_abi_version() != EARL_ABI_VERSION:
+            raise ImportError(f"{LIB_PATH}: ABI version {L.earl_abi_version()} != {EARL_ABI_VERSION}; rebuild")
+        _lib = L
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise EarlError(rc, lib().earl_last_error().decode("utf-8", "replace"))

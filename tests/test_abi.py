@@ -1,0 +1,63 @@
+"""The C-ABI library loads on a CPU-only box and exports every symbol include/earl_b200.h declares."""
+import ctypes
+import os
+import re
+import subprocess
+
+import pytest
+
+from conftest import REPO
+from earl_benchmark_b200 import _lib, build
+
+HEADER = os.path.join(REPO, "include", "earl_b200.h")
+
+
+def header_symbols():
+    text = open(HEADER).read()
+    return re.findall(r"^EARL_API\s+[\w\s\*]+?\b(earl_\w+)\s*\(", text, flags=re.M)
+
+
+def test_library_builds_and_loads():
+    build.build()
+    L = _lib.lib()
+    assert L.earl_abi_version() == _lib.EARL_ABI_VERSION
+
+
+def test_every_declared_symbol_is_exported_and_bound():
+    build.build()
+    syms = header_symbols()
+    assert len(syms) >= 25 and len(set(syms)) == len(syms)
+    L = ctypes.CDLL(_lib.LIB_PATH)
+    for s in syms:
+        assert hasattr(L, s), f"{s} declared in the header but not exported"
+    bound = {name for name, _, _ in _lib.SIGNATURES}
+    assert bound == set(syms), (bound ^ set(syms))
+    exported = subprocess.check_output(["nm", "-D", "--defined-only", _lib.LIB_PATH], text=True)
+    extra = [l.split()[-1] for l in exported.splitlines() if " T " in l and not l.split()[-1].startswith("earl_")]
+    assert not extra, f"non-API symbols exported: {extra}"
+
+
+def test_struct_layouts_match_header():
+    # sizes the C side checks against (earl_create rejects blobs of any other size)
+    assert ctypes.sizeof(_lib.EarlConfig) == 40
+    assert ctypes.sizeof(_lib.TabletopModel) == 8 + 4 * 8 + 6 * 8 + 256 * 6 * 8
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is visible")
+    import earl_benchmark_b200 as e
+    tr, _ = e.EARLEnvs("tabletop_manipulation", num_envs=4).get_envs()
+    with pytest.raises(_lib.EarlError) as ei:
+        tr.reset()
+    assert ei.value.code == -2  # EARL_ERR_CUDA: fails loudly, no silent CPU path
+
+
+def test_product_package_never_imports_the_oracle():
+    pkg = os.path.join(REPO, "earl_benchmark_b200")
+    for root, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".hpp", ".h")):
+                text = open(os.path.join(root, f)).read()
+                assert "oracle" not in text.replace("oracle/gen_golden.py", "").replace("tests/golden", ""), os.path.join(root, f)

@@ -1,0 +1,77 @@
+"""Host-side mirror of the reference loader surface (earl_benchmark/__init__.py) -- no GPU needed."""
+import os
+
+import numpy as np
+import pytest
+
+import earl_benchmark_b200 as eb
+from earl_benchmark_b200 import demos, shard_range
+from earl_benchmark_b200.wrappers import lifelong_wrapper, persistent_state_wrapper
+
+
+def test_config_tables_and_horizons():
+    e = eb.EARLEnvs("tabletop_manipulation", reward_type="sparse", num_envs=8)
+    tr, ev = e.get_envs()
+    assert isinstance(tr, persistent_state_wrapper.PersistentStateWrapper)
+    assert tr._episode_horizon == 200000 and ev._episode_horizon == 200
+    assert tr.env is not ev.env  # two independent env instances (reference :104-105)
+    e = eb.EARLEnvs("tabletop_manipulation", train_horizon=123, eval_horizon=7)
+    tr, ev = e.get_envs()
+    assert tr.env._episode_horizon == 123 and ev.env._episode_horizon == 7
+    e = eb.EARLEnvs("tabletop_manipulation", setup_as_lifelong_learning=True)
+    ll = e.get_envs()
+    assert isinstance(ll, lifelong_wrapper.LifelongWrapper)
+    assert ll._goal_change_frequency == 400 and ll.env._episode_horizon == 50000
+    assert ll._base._lifelong and ll._base._goal_change_frequency == 400
+
+
+def test_unknown_env_is_keyerror_like_reference():
+    with pytest.raises(KeyError):
+        eb.EARLEnvs("no_such_env")
+
+
+def test_unbuilt_envs_fail_loudly():
+    for name in ("sawyer_door", "sawyer_peg", "kitchen"):
+        with pytest.raises(NotImplementedError):
+            eb.EARLEnvs(name, reward_type="dense")
+
+
+def test_states_and_demos(golden_dir):
+    e = eb.EARLEnvs("tabletop_manipulation")
+    g = np.load(os.path.join(golden_dir, "loader_constants.npz"))
+    assert np.array_equal(e.get_initial_states(), g["tabletop_manipulation_initial_states"])
+    assert np.array_equal(e.get_goal_states(), g["tabletop_manipulation_goal_states"])
+    assert e.has_demos()
+    fwd, rev = e.get_demonstrations()
+    assert set(fwd) == {"observations", "actions", "rewards", "terminals", "next_observations", "infos"}
+    assert fwd["observations"].shape == (1278, 12) and rev["actions"].shape == (1256, 3)
+    assert fwd["terminals"].sum() == 12 and fwd["rewards"].dtype == np.float32
+    for env, (nf, nr, od, ad) in {"sawyer_door": (395, 700, 14, 4), "sawyer_peg": (683, 1132, 14, 4)}.items():
+        assert demos.load(env, "forward")["observations"].shape == (nf, od)
+        assert demos.load(env, "reverse")["actions"].shape == (nr, ad)
+
+
+def test_shard_range_partitions_exactly():
+    for n in (1, 7, 8, 65536, 1000003):
+        for w in (1, 2, 3, 8):
+            spans = [shard_range(n, r, w) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_goal_table_and_custom_goals():
+    from earl_benchmark_b200.envs.tabletop_manipulation import TabletopManipulation, goal_states, initial_states
+    env = TabletopManipulation(reward_type="sparse", num_envs=3)
+    assert len(env._goal_table) == 5 and np.array_equal(env._goal_table[4], initial_states[0])
+    assert np.array_equal(env._goal_table[2][2:4], goal_states[2][2:4]) and np.array_equal(env._goal_table[2][:2], [0, 0])
+    assert env._task_to_row.tolist() == [0, 3, 1, 2]
+    rows = env._goal_rows_for(np.array([0.0, 0.0, 2.5, 0.0, -1, -1]))
+    assert rows.tolist() == [4, 4, 4]
+    rows = env._goal_rows_for(np.array([[0, 0, -2.5, 1, -1, -1], [0.5, 0, 1, 1, -1, -1], [0, 0, 2.5, 0, -1, -1]], float))
+    assert rows.tolist() == [1, 5, 4] and len(env._goal_table) == 6
+    with pytest.raises(ValueError):
+        TabletopManipulation(task_list="bc_r")
+    with pytest.raises(ValueError):
+        TabletopManipulation(reward_type="banana")

@@ -1,0 +1,431 @@
+"""Parity of the CUDA tabletop path (through the C ABI) against the pinned CPU oracle, the golden
+outputs of the unmodified reference, and the shipped demonstrations.  Needs a GPU: `-m gpu`.
+
+Bars (BASELINE.json north_star): observations bit-exact against the oracle (fp64 arithmetic, one rounding
+to fp32); integer bookkeeping bit-exact; sparse reward bit-exact outside 1e-5 of the 0.2 threshold (here it
+is bit-exact everywhere, the band is only used against numpy-2-evaluated reference rewards); dense reward
+within 2e-6 relative (fp32 output of an fp64 evaluation).
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+import earl_benchmark_b200 as eb  # noqa: E402
+from earl_benchmark_b200 import demos  # noqa: E402
+from earl_benchmark_b200.envs.tabletop_manipulation import TabletopManipulation  # noqa: E402
+from earl_benchmark_b200.wrappers.persistent_state_wrapper import PersistentStateWrapper  # noqa: E402
+from oracle import loader  # noqa: E402
+from oracle.loader import GOAL_STATES, TabletopOracle  # noqa: E402
+
+DEV = "cuda:0"
+BAND = 1e-5
+
+
+def make(n, horizon=10**9, **kw):
+    kw.setdefault("reward_type", "sparse")
+    return PersistentStateWrapper(TabletopManipulation(num_envs=n, device=DEV, **kw), horizon)
+
+
+def goal_row(obs):
+    d = np.abs(GOAL_STATES[None, :, 2:4] - obs[:, None, 8:10]).sum(-1)
+    return d.argmin(1)
+
+
+def actions(n, steps, seed, grip_bias=0.0):
+    rs = np.random.RandomState(seed)
+    a = rs.uniform(-1.2, 1.2, (steps, n, 3)).astype(np.float32)
+    a[..., 2] += grip_bias
+    return a
+
+
+def np_(t):
+    return t.detach().cpu().numpy()
+
+
+# ---------------------------------------------------------------------------------------- demos + goldens
+
+@pytest.mark.parametrize("state_dtype", ["float32", "float64"])
+@pytest.mark.parametrize("direction", ["forward", "reverse"])
+def test_demo_transitions(golden_dir, direction, state_dtype):
+    """All shipped tabletop transitions in ONE launch: == reference step() bit for bit."""
+    d = demos.load("tabletop_manipulation", direction)
+    ref = np.load(os.path.join(golden_dir, "tabletop_ref_demo_replay.npz"))
+    n = len(d["actions"])
+    env = make(n, state_dtype=state_dtype)
+    env.reset()
+    o = d["observations"]
+    rows = env._goal_rows_for(o[:, 6:].astype(np.float64))
+    env.set_state(qpos=o[:, :4].astype(np.float64), attached=(o[:, 4] == 0), goal_row=rows)
+    assert np.array_equal(np_(env.get_obs()), o)
+    obs, rew, done, info = env.step(torch.from_numpy(d["actions"]).to(DEV))
+    obs, rew = np_(obs), np_(rew)
+    assert np.array_equal(obs, ref[f"{direction}_ref_next_obs"])
+    assert np.array_equal(rew.astype(np.float64), ref[f"{direction}_ref_reward"])
+    assert np.abs(obs - d["next_observations"]).max() <= 2.4e-7     # stored fp32 snapshot of fp64 state: 1 ulp
+    assert np.array_equal(obs[:, 4:], d["next_observations"][:, 4:])  # attach flags and goals exact
+    assert np.array_equal(rew, d["rewards"][:, 0])                    # 100 % sparse-reward agreement
+    assert np.array_equal(np_(info["success"]), d["rewards"][:, 0] > 0)
+    assert not done.any() and env.total_steps == 1
+
+
+def _replay_golden(g, prefix, horizon, dense=False, wide=False, custom_init=False, reset_at_goal=False):
+    g = {k[len(prefix) + 1:]: g[k] for k in g.files if k.startswith(prefix + "_")}
+    n = len(g["actions"])
+    env = make(1, horizon, reward_type="dense" if dense else "sparse", wide_init_distr=wide,
+               reset_at_goal=reset_at_goal, state_dtype="float64")
+    acts = torch.from_numpy(g["actions"]).to(DEV)
+
+    def do_reset(obs_row, q):
+        return np_(env.reset(goal_rows=goal_row(obs_row), init_qpos=q if custom_init else None))
+
+    o = do_reset(g["obs"][0:1], g["qpos"][0:1])
+    assert np.array_equal(o[0], g["obs"][0])
+    resets = 1
+    for t in range(n):
+        ob, rw, dn, info = env.step(acts[t:t + 1])
+        ob, rw, dn, sc = np_(ob), np_(rw), np_(dn), np_(info["success"])
+        if not g["reset_after"][t]:
+            assert np.array_equal(ob[0], g["obs"][t + 1]), (prefix, t)
+        nrm = np.linalg.norm((ob[0, 2:4] - ob[0, 8:10]) if wide else (ob[0, :4] - ob[0, 6:10]))
+        if abs(nrm - 0.2) > BAND:
+            assert bool(sc[0]) == bool(g["success"][t]), (prefix, t)
+            if not dense:
+                assert rw[0] == g["reward"][t], (prefix, t)
+        if dense:
+            assert abs(rw[0] - g["reward"][t]) <= 2e-6 * max(1.0, abs(g["reward"][t])), (prefix, t)
+        assert bool(dn[0]) == bool(g["done"][t]), (prefix, t)
+        if g["reset_after"][t]:
+            o = do_reset(g["obs"][t + 1:t + 2], g["qpos"][t + 1:t + 2])
+            assert np.array_equal(o[0], g["obs"][t + 1]), (prefix, t)
+            resets += 1
+    assert env.total_steps == g["total_steps"][-1]
+    assert int(env.num_interventions[0]) == resets
+    return g
+
+
+@pytest.fixture(scope="module")
+def rollouts(golden_dir):
+    return np.load(os.path.join(golden_dir, "tabletop_ref_rollouts.npz"))
+
+
+def test_golden_sparse_train_rollout(rollouts):
+    """4,096-step reference trajectory (horizon 1000, 4 resets): every observation bit-exact (fp64 state)."""
+    _replay_golden(rollouts, "sparse_train", 1000)
+
+
+def test_golden_dense_rollout(rollouts):
+    _replay_golden(rollouts, "dense_train", 700, dense=True)
+
+
+def test_golden_wide_init_rollout(rollouts):
+    _replay_golden(rollouts, "wide_train", 250, wide=True, custom_init=True)
+
+
+def test_golden_reset_at_goal_rollout(rollouts):
+    # reset_at_goal: the reset kernel itself places the env at its drawn goal (no init_qpos passed)
+    _replay_golden(rollouts, "resetgoal_train", 300, reset_at_goal=True)
+
+
+def test_golden_no_reset_after_done(rollouts):
+    g = _replay_golden(rollouts, "noreset_train", 100)
+    assert g["done"][99:].all()
+
+
+def test_golden_lifelong(golden_dir):
+    """LifelongWrapper on device vs the reference: seed-7 `random` stream drives resets AND goal swaps."""
+    g = np.load(os.path.join(golden_dir, "tabletop_ref_lifelong.npz"))
+    freq, horizon, seed = int(g["goal_change_frequency"]), int(g["train_horizon"]), int(g["seed"])
+    env = eb.EARLEnvs("tabletop_manipulation", reward_type="sparse", setup_as_lifelong_learning=True,
+                      train_horizon=horizon, goal_change_frequency=freq, seed=seed, state_dtype="float64",
+                      device=DEV, goal_stream_rows=128).get_envs()
+    acts = torch.from_numpy(g["actions"]).to(DEV)
+    o = np_(env.reset())
+    assert np.array_equal(o[0], g["obs"][0])
+    for t in range(len(acts)):
+        ob, rw, dn, _ = env.step(acts[t:t + 1])
+        assert float(rw[0]) == g["reward"][t] and bool(dn[0]) == bool(g["done"][t]), t
+        if g["reset_after"][t]:
+            ob = env.reset()
+        assert np.array_equal(np_(ob)[0], g["obs"][t + 1]), t
+        assert float(env.lifelong_return[0]) == g["lifelong_return"][t]
+    assert int(env.num_interventions[0]) == int(g["num_interventions"][-1]) + int(g["reset_after"][-1])
+
+
+def test_shared_goal_stream_order(golden_dir):
+    """16 envs, 3 resets: goals equal those of 16 reference envs sharing the global `random` stream."""
+    g = np.load(os.path.join(golden_dir, "tabletop_ref_streams.npz"))["shared_stream_seed11_16envs_3resets"]
+    env = make(16, seed=11)
+    for r in range(3):
+        o = np_(env.reset())
+        assert np.array_equal(goal_row(o), g[r])
+    assert np_(env.num_interventions).tolist() == [3] * 16
+
+
+# ---------------------------------------------------------------------------------------- random batched parity
+
+@pytest.mark.parametrize("n", [1, 31, 33, 257, 100003])
+@pytest.mark.parametrize("state_dtype", ["float32", "float64"])
+def test_random_rollout_vs_oracle(n, state_dtype):
+    """Ragged batch sizes, random actions (some out of range), horizon firing mid-run: bit-exact vs oracle."""
+    steps, horizon = 60, 41
+    env = make(n, horizon, state_dtype=state_dtype, seed=n)
+    orc = TabletopOracle(n, horizon, state_f32=(state_dtype == "float32"))
+    o = np_(env.reset())
+    rows = goal_row(o)
+    assert np.array_equal(orc.reset(rows), o)
+    acts = actions(n, steps, seed=n, grip_bias=0.3)
+    # start half of the envs next to the mug so attach / drag / clip paths are busy
+    q = np.tile([0.0, 0.0, 2.5, 0.0], (n, 1))
+    q[::2, 0] = 2.3
+    q = q.astype(np.float32).astype(np.float64)  # representable in either state dtype
+    env.set_state(qpos=q)
+    orc.qpos[:] = q
+    for t in range(steps):
+        ob, rw, dn, info = env.step(torch.from_numpy(acts[t]).to(DEV))
+        o2, r2, d2, s2 = orc.step(acts[t])
+        assert np.array_equal(np_(ob), o2), t
+        assert np.array_equal(np_(rw).astype(np.float64), r2), t
+        assert np.array_equal(np_(dn), d2.astype(bool)), t
+        assert np.array_equal(np_(info["success"]), s2.astype(bool)), t
+    if n >= 257:  # the run exercised attach and the workspace clip
+        assert (orc.attached != 0).any() and (np.abs(orc.qpos) == 2.8).any()
+    total, interv, since, _ = env.env._counters()
+    assert total == steps == orc.total_steps[0]
+    assert np.array_equal(np_(since).astype(np.int64), orc.steps_since_reset)
+    assert np.array_equal(np_(interv), orc.num_interventions)
+    snap = env.get_state()
+    if state_dtype == "float64":
+        assert np.array_equal(snap["qpos"], orc.qpos)
+    assert np.array_equal(snap["attached"], orc.attached != 0)
+
+
+def test_full_size_batch_vs_oracle():
+    """BASELINE config 2 size (1,048,576 envs): direct comparison with the oracle + order-independence."""
+    n, steps = 1 << 20, 6
+    env = make(n, 4)
+    orc = TabletopOracle(n, 4, state_f32=True)
+    orc.reset(goal_row(np_(env.reset())))
+    acts = actions(n, steps, seed=99, grip_bias=0.5)
+    rs = np.random.RandomState(5)
+    q = rs.uniform(-2.8, 2.8, (n, 4)).astype(np.float32).astype(np.float64)
+    q[::3, 2:4] = q[::3, 0:2] + 0.1  # a third of the envs start within the attach radius
+    q = np.clip(q, -2.8, 2.8).astype(np.float32).astype(np.float64)
+    env.set_state(qpos=q)
+    orc.qpos[:] = q
+    perm = rs.permutation(n)
+    env_p = make(n, 4)
+    env_p.reset(goal_rows=goal_row(orc.get_obs())[perm])
+    env_p.set_state(qpos=q[perm])
+    for t in range(steps):
+        ob, rw, dn, _ = env.step(torch.from_numpy(acts[t]).to(DEV))
+        o2, r2, d2, _ = orc.step(acts[t])
+        assert np.array_equal(np_(ob), o2) and np.array_equal(np_(rw).astype(np.float64), r2)
+        assert np.array_equal(np_(dn), d2.astype(bool))
+        obp, rwp, _, _ = env_p.step(torch.from_numpy(acts[t][perm]).to(DEV))
+        assert torch.equal(obp, ob[torch.from_numpy(perm).to(DEV)])  # envs are independent of their index
+    assert (orc.attached != 0).mean() > 0.05 and np_(dn).all()
+
+
+def test_f32_state_drift_is_bounded():
+    """fp32 device state vs the reference's fp64 state over a long open-loop rollout: one-step error is one
+    fp32 rounding (<=1.2e-7 * |x|), so drift stays far inside north_star's 1e-4."""
+    n, steps = 512, 3000
+    env = make(n, seed=1)
+    orc = TabletopOracle(n, 10**9, state_f32=False)
+    orc.reset(goal_row(np_(env.reset())))
+    acts = actions(n, steps, seed=3)
+    acts[..., 2] = -1.0  # no attach decisions, pure integration
+    dev = torch.from_numpy(acts).to(DEV)
+    for t in range(steps):
+        ob, _, _, _ = env.step(dev[t])
+        orc.step(acts[t])
+    err = np.abs(np_(ob)[:, :4].astype(np.float64) - orc.qpos).max()
+    assert err < 1e-4, err
+
+
+# ---------------------------------------------------------------------------------------- features
+
+def test_dense_reward_and_compute_reward_vs_oracle():
+    n = 5000
+    env = make(n, reward_type="dense")
+    env.reset()
+    rs = np.random.RandomState(0)
+    q = rs.uniform(-2.8, 2.8, (n, 4))
+    q[::4, 2:4] = np.array([0.0, 2.0]) + rs.normal(0, 0.05, (len(q[::4]), 2))
+    env.set_state(qpos=q, goal_row=2)
+    a = actions(n, 1, 7)[0]
+    ob, rw, _, info = env.step(torch.from_numpy(a).to(DEV))
+    ob = np_(ob)
+    want = np.zeros(n)
+    ws = np.zeros(n, np.uint8)
+    loader.lib().earl_oracle_tt_reward(n, np.ascontiguousarray(ob), 1, 0, want, ws)
+    assert np.abs(np_(rw) - want).max() <= 2e-6 * np.abs(want).max()
+    assert np.array_equal(np_(info["success"]), ws.astype(bool))
+    # compute_reward / is_successful on caller-supplied observations (device and host inputs)
+    r2 = env.compute_reward(torch.from_numpy(ob).to(DEV))
+    assert np.abs(np_(r2) - want).max() <= 2e-6 * np.abs(want).max()
+    assert np.array_equal(env.is_successful(ob), ws.astype(bool))
+    sparse = make(n)
+    sparse.reset()
+    loader.lib().earl_oracle_tt_reward(n, np.ascontiguousarray(ob), 0, 0, want, ws)
+    assert np.array_equal(sparse.compute_reward(ob).astype(np.float64), want)
+    wide = make(n, wide_init_distr=True)
+    wide.reset(init_qpos=q)
+    loader.lib().earl_oracle_tt_reward(n, np.ascontiguousarray(ob), 0, 1, want, ws)
+    assert np.array_equal(wide.is_successful(ob), ws.astype(bool)) and ws.sum() > 0
+
+
+def test_auto_reset_matches_manual_reset():
+    """In-kernel reset at the horizon == the user calling reset() after done (goal stream order included)."""
+    n, horizon, steps = 1000, 17, 70
+    auto = make(n, horizon, auto_reset=True, seed=4)
+    manual = make(n, horizon, seed=4)
+    oa, om = auto.reset(), manual.reset()
+    assert torch.equal(oa, om)
+    acts = torch.from_numpy(actions(n, steps, 11, 0.4)).to(DEV)
+    for t in range(steps):
+        oa, ra, da, _ = auto.step(acts[t])
+        om, rm, dm, _ = manual.step(acts[t])
+        assert torch.equal(ra, rm) and torch.equal(da, dm)
+        if bool(dm.all()):
+            om = manual.reset()
+        assert torch.equal(oa, om), t
+    assert torch.equal(auto.num_interventions, manual.num_interventions)
+    assert int(auto.num_interventions[0]) == 1 + steps // horizon
+    ra_goal = make(n, horizon, auto_reset=True, reset_at_goal=True, seed=4)
+    o = ra_goal.reset()
+    assert torch.equal(o[:, :4], o[:, 6:10])  # reset_at_goal: env starts at its goal
+    for t in range(horizon):
+        o, _, d, _ = ra_goal.step(acts[t])
+    assert bool(d.all()) and torch.equal(o[:, :4], o[:, 6:10])
+
+
+def test_masked_reset_and_counters():
+    n = 300
+    env = make(n, 50)
+    env.reset()
+    acts = torch.from_numpy(actions(n, 10, 2)).to(DEV)
+    for t in range(10):
+        env.step(acts[t])
+    mask = torch.zeros(n, dtype=torch.bool, device=DEV)
+    mask[::3] = True
+    before = np_(env.get_obs())
+    o = np_(env.reset(mask=mask))
+    m = np_(mask)
+    assert np.array_equal(o[~m, :6], before[~m, :6])            # untouched envs keep their state
+    assert np.array_equal(o[m, :4], np.tile([0, 0, 2.5, 0], (m.sum(), 1)))
+    assert np.array_equal(np_(env.num_interventions), 1 + m.astype(np.int64))
+    assert np.array_equal(np_(env.steps_since_reset), np.where(m, 0, 10))
+    assert env.total_steps == 10
+
+
+def test_reset_goal_custom_and_stream():
+    n = 64
+    env = make(n, seed=9)
+    o0 = np_(env.reset())
+    custom = np.array([0.0, 0.0, 1.25, -0.5, -1.0, -1.0])
+    env.reset_goal(custom)
+    o = np_(env.get_obs())
+    assert np.array_equal(o[:, 6:], np.tile(custom.astype(np.float32), (n, 1))) and np.array_equal(o[:, :6], o0[:, :6])
+    assert np.array_equal(env.goal, np.tile(custom, (n, 1)))
+    env.reset_goal()  # next draw of every env's stream
+    from earl_benchmark_b200 import rng
+    stream = rng.PyRandom(9).tabletop_goal_rows(2 * n).reshape(2, n)
+    assert np.array_equal(goal_row(np_(env.get_obs())), stream[1])
+    nxt = env.get_next_goal()  # third draw, returned but not installed
+    stream3 = rng.PyRandom(9).tabletop_goal_rows(3 * n).reshape(3, n)
+    assert np.array_equal(nxt[:, 2:4], GOAL_STATES[stream3[2], 2:4])
+    assert np.array_equal(goal_row(np_(env.get_obs())), stream[1])
+
+
+def test_snapshot_roundtrip():
+    n = 1234
+    env = make(n, 30, seed=2)
+    env.reset()
+    acts = torch.from_numpy(actions(n, 40, 5, 0.4)).to(DEV)
+    for t in range(20):
+        env.step(acts[t])
+    snap = env.get_state()
+    ref = [tuple(x.clone() for x in env.step(acts[t])[:3]) for t in range(20, 40)]
+    env2 = make(n, 30, seed=2)
+    env2.set_state(snap)
+    assert env2.total_steps == 20
+    for t in range(20, 40):
+        o, r, d, _ = env2.step(acts[t])
+        assert torch.equal(o, ref[t - 20][0]) and torch.equal(r, ref[t - 20][1]) and torch.equal(d, ref[t - 20][2])
+
+
+def test_host_buffer_path_equals_device_path():
+    n = 4099
+    dev_env, host_env = make(n, 9), make(n, 9)
+    dev_env.reset(), host_env.reset()
+    acts = actions(n, 12, 8, 0.3)
+    for t in range(12):
+        o, r, d, i = dev_env.step(torch.from_numpy(acts[t]).to(DEV))
+        ho, hr, hd, hi = host_env.step(acts[t])  # numpy in -> numpy out, copies inside the call
+        assert isinstance(ho, np.ndarray)
+        assert np.array_equal(ho, np_(o)) and np.array_equal(hr, np_(r)) and np.array_equal(hd, np_(d))
+        assert np.array_equal(hi["success"], np_(i["success"]))
+    pinned = torch.from_numpy(acts[0]).pin_memory()
+    ho, _, _, _ = host_env.step(pinned)
+    assert ho.shape == (n, 12) and host_env.total_steps == 13
+
+
+def test_rollout_equals_repeated_step():
+    n, k, steps = 777, 5, 13
+    a, b = make(n, 7), make(n, 7)
+    a.reset(), b.reset()
+    acts = torch.from_numpy(actions(n, k, 21, 0.3)).to(DEV)
+    obs = torch.empty((4, n, 12), device=DEV)
+    rew = torch.empty((4, n), device=DEV)
+    done = torch.empty((4, n), dtype=torch.uint8, device=DEV)
+    a.rollout_into(acts, steps, obs, rew, done)
+    for t in range(steps):
+        o, r, d, _ = b.step(acts[t % k])
+        if t >= steps - 4:
+            assert torch.equal(obs[t % 4], o) and torch.equal(rew[t % 4], r) and torch.equal(done[t % 4].bool(), d)
+    assert a.total_steps == b.total_steps == steps
+
+
+def test_eval_stats():
+    n, horizon = 2000, 25
+    loader_ = eb.EARLEnvs("tabletop_manipulation", reward_type="sparse", num_envs=n, eval_horizon=horizon, device=DEV)
+    _, ev = loader_.get_envs()
+    ev.reset()
+    rs = np.random.RandomState(1)
+    q = np.tile([0.0, 0.0, 2.5, 0.0], (n, 1))
+    goals = np_(ev.get_obs())[:, 6:10].astype(np.float64)
+    q[::2] = goals[::2] + rs.normal(0, 0.08, (n // 2, 4))  # half of the envs start near success
+    ev.set_state(qpos=np.clip(q, -2.8, 2.8))
+    acts = torch.from_numpy((0.3 * actions(n, horizon, 3)).astype(np.float32)).to(DEV)
+    ret = np.zeros(n)
+    anyv = np.zeros(n, bool)
+    for t in range(horizon):
+        o, r, d, i = ev.step(acts[t])
+        ret += np_(r)
+        anyv |= np_(i["success"])
+    last = np_(i["success"])
+    s = np_(ev.eval_stats())
+    assert s[3] == n and s[0] == ret.sum() and s[1] == last.sum() and s[2] == anyv.sum() and ret.sum() > 0
+    from earl_benchmark_b200.distributed import all_reduce_eval_stats
+    res = all_reduce_eval_stats(ev.eval_stats())
+    assert abs(res["mean_return"] - ret.mean()) < 1e-12 and res["num_envs"] == n
+    ev.reset()
+    assert np_(ev.eval_stats())[:3].tolist() == [0.0, 0.0, 0.0]
+
+
+def test_invalid_arguments_fail_loudly():
+    from earl_benchmark_b200 import _lib
+    env = make(8)
+    env.reset()
+    with pytest.raises(ValueError):
+        env.step(torch.zeros((7, 3), device=DEV))
+    with pytest.raises(_lib.EarlError):
+        TabletopManipulation(num_envs=0, device=DEV, reward_type="sparse").reset()
+    with pytest.raises(_lib.EarlError):  # misaligned observation buffer
+        buf = torch.empty(8 * 12 + 1, device=DEV)[1:].view(8, 12)
+        env.step(torch.zeros((8, 3), device=DEV), out=(buf, env._reward, env._done, env._success))
