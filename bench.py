@@ -203,7 +203,7 @@ def run_ours(args):
     env.rollout_into(actions, max(args.warmup, 3), obs, rew, done)
     torch.cuda.synchronize()
     t_w = time.perf_counter()
-    while time.perf_counter() - t_w < 1.0:
+    while not args.profile and time.perf_counter() - t_w < 1.0:
         env.rollout_into(actions, 256, obs, rew, done)
         torch.cuda.synchronize()
 
@@ -223,6 +223,8 @@ def run_ours(args):
 
     # ---- end to end through the public API with host buffers
     e2e_steps = args.steps if args.e2e_steps is None else args.e2e_steps
+    if args.profile:
+        e2e_steps = 1
     host_actions = [(torch.rand((n, 3), dtype=torch.float32) * 2 - 1).pin_memory() for _ in range(4)]
     for k in range(3):
         train.step(host_actions[k % 4])
@@ -237,8 +239,36 @@ def run_ours(args):
     d2h = n * (12 * 4 + 4 + 1 + 1)
     clocks = sampler.stop(t_region0, t_region1) if sampler else None
 
+    # ---- second operating point: 8,388,608 envs per GPU, where state, actions and outputs all stream from HBM
+    big = None
+    if not args.profile and not args.no_hbm_check and n < (1 << 23):
+        del actions, obs, rew, done
+        nb, kb = 1 << 23, max(20, min(args.steps, 300))
+        lb = eb.EARLEnvs("tabletop_manipulation", reward_type="sparse", num_envs=nb * world, rank=rank, world_size=world,
+                         device=dev, seed=0, train_horizon=TRAIN_HORIZON, goal_stream_rows=2)
+        tb, _ = lb.get_envs()
+        tb.reset()
+        a_b = torch.rand((8, nb, 3), generator=gen, device=dev, dtype=torch.float32) * 2 - 1
+        o_b = torch.empty((4, nb, 12), device=dev, dtype=torch.float32)
+        r_b = torch.empty((4, nb), device=dev, dtype=torch.float32)
+        d_b = torch.empty((4, nb), device=dev, dtype=torch.uint8)
+        tb.env.rollout_into(a_b, 20, o_b, r_b, d_b)
+        barrier()
+        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        b0.record()
+        tb.env.rollout_into(a_b, kb, o_b, r_b, d_b)
+        b1.record()
+        barrier()
+        ms_b = max_over_ranks(b0.elapsed_time(b1), dev)
+        big = {"envs_per_gpu": nb, "steps": kb, "value": nb * world * kb / (ms_b * 1e-3), "unit": UNIT,
+               "achieved": ALG_BYTES_PER_ENV_STEP * nb / (ms_b * 1e-3 / kb) / 1e9,
+               "kernel": "earl::tabletop_step_tma_kernel<3,256>  (cp.async.bulk pipeline)"}
+        del a_b, o_b, r_b, d_b, tb, lb
+
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
+        if big is not None:
+            big["frac"] = big["achieved"] / peak
         per_launch_s = ms * 1e-3 / args.steps
         achieved = ALG_BYTES_PER_ENV_STEP * n / per_launch_s / 1e9
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -250,11 +280,16 @@ def run_ours(args):
                 "gpu_launches": launches,
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "traffic": args.traffic_bytes, "peak_source": peak_src,
-                             "kernel": "earl::tabletop_step_kernel<false,true>",
+                             "kernel": ("earl::tabletop_step_kernel<false,true,1>  (LSU path, PDL)" if n <= 3 * 1024 * 1024
+                                        else "earl::tabletop_step_tma_kernel<3,256>  (cp.async.bulk pipeline, PDL)"),
+                             "note": "per-env state (24 B) stays L2-resident at this batch size, so the algorithmic-byte "
+                                     "rate can exceed the HBM copy peak; hbm_bound_check is the all-HBM operating point",
                              "algorithmic_bytes_per_launch": ALG_BYTES_PER_ENV_STEP * n,
                              "avg_launch_us": per_launch_s * 1e6},
                 "clocks": clocks}
-        if world == 1 and not args.no_cpu_baseline:
+        if big is not None:
+            line["hbm_bound_check"] = big
+        if world == 1 and not args.no_cpu_baseline and not args.profile:
             threads = os.cpu_count() or 1
             rate, n_sample, el = cpu_port_rate(n, min(args.steps, 200), threads, budget_s=15.0)
             line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
@@ -276,9 +311,16 @@ def main():
     ap.add_argument("--num-envs", type=int, default=1 << 20, help="envs per GPU")
     ap.add_argument("--e2e-steps", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-hbm-check", action="store_true", help="skip the 8M-env all-HBM operating point")
+    ap.add_argument("--profile", action="store_true", help="under ncu: no sustained warm-up, 1 e2e step, no CPU leg")
     ap.add_argument("--traffic-bytes", type=float, default=None,
-                    help="dram bytes per launch from the committed ncu capture (profiles/), else null")
+                    help="dram bytes per launch from the committed ncu capture; default: profiles/r01 value for the "
+                         "default workload, else null")
     args = ap.parse_args()
+    if args.traffic_bytes is None and args.num_envs == 1 << 20:
+        # profiles/r01/prof_step_lsu_1M_r01.raw.csv: dram__bytes_read.sum 37.76 MB + dram__bytes_write.sum 23.88 MB per
+        # launch (ncu --set full, cold L2; the remaining writes are still dirty in the 126 MB L2 when the kernel ends)
+        args.traffic_bytes = 37.759488e6 + 23.884032e6
     if args.impl == "reference":
         return run_reference(args)
     if args.gpus > 1 and "WORLD_SIZE" not in os.environ:

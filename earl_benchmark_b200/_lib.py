@@ -40,6 +40,7 @@ _VP, _I32, _I64, _U32, _SZ = C.c_void_p, C.c_int32, C.c_int64, C.c_uint32, C.c_s
 SIGNATURES = [
     ("earl_abi_version", C.c_int, []),
     ("earl_last_error", C.c_char_p, []),
+    ("earl_tabletop_thresholds", None, [C.c_double, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_float)]),
     ("earl_create", C.c_int, [C.POINTER(EarlConfig), _VP, _SZ, C.POINTER(_VP)]),
     ("earl_destroy", C.c_int, [_VP]),
     ("earl_num_envs", C.c_int, [_VP]),

@@ -3,8 +3,10 @@
 // Device side: tabletop_kernels.cuh.  There is no CPU fallback anywhere in this file.
 #include "../../include/earl_b200.h"
 
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -51,6 +53,13 @@ struct earl_handle {
   int device = 0;
   int sm_count = 0;
   int step_grid = 0;
+  int variant = -1;       // EARL_TT_VARIANT: -1 = auto (LSU kernel up to 3M envs, 3-stage TMA pipeline above);
+                          // 0 = LSU kernel; 6/8 = LSU kernel with min 6/8 CTAs per SM; 2/3/4 = TMA pipeline stages
+  bool pdl = true;        // EARL_TT_PDL=0 disables programmatic dependent launch between consecutive steps
+  int tma_grid = 0;
+  int tma_tile = 256;
+  size_t tma_smem = 0;
+  void (*tma_kernel)(const earl::TabletopParams, int) = nullptr;
   int64_t total_steps = 0;
   int64_t launches = 0;
   // owned device memory
@@ -62,6 +71,9 @@ struct earl_handle {
   uint8_t* d_done = nullptr;
   uint8_t* d_succ = nullptr;
   cudaStream_t host_stream = nullptr;
+  cudaStream_t in_stream = nullptr;
+  static constexpr int kMaxChunks = 8;
+  cudaEvent_t chunk_ev[kMaxChunks] = {};
   double* d_stats = nullptr;
 
   template <typename T>
@@ -105,6 +117,36 @@ int upload_goal_tables(earl_handle* h) {
   return 0;
 }
 
+// Launch with the programmatic-stream-serialization attribute (PDL) when enabled.
+template <typename K>
+cudaError_t launch_pdl(K kernel, int grid, int block, size_t smem, cudaStream_t s, bool pdl, const earl::TabletopParams& p) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3((unsigned)block);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, p);
+}
+template <typename K>
+cudaError_t launch_pdl(K kernel, int grid, int block, size_t smem, cudaStream_t s, bool pdl, const earl::TabletopParams& p, int tiles) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3((unsigned)block);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, p, tiles);
+}
+
 template <typename K>
 int occupancy_grid(K kernel, int sm_count, int* grid) {
   int per_sm = 0;
@@ -114,27 +156,50 @@ int occupancy_grid(K kernel, int sm_count, int* grid) {
   return 0;
 }
 
-int launch_step(earl_handle* h, const float* actions, float* obs, float* reward, uint8_t* done, uint8_t* success,
-                cudaStream_t s) {
+// One step of envs [first, first+count) (whole batch: first=0, count=N).  IO pointers are those of env 0.
+int launch_step_range(earl_handle* h, int first, int count, const float* actions, float* obs, float* reward,
+                      uint8_t* done, uint8_t* success, cudaStream_t s) {
   earl::TabletopParams p = h->p;
+  p.n = first + count;
   p.actions = actions;
   p.obs = obs;
   p.reward = reward;
   p.done = done;
   p.success = success;
-  const int tiles = (p.n + earl::kTTBlock - 1) / earl::kTTBlock;
-  const int grid = tiles < h->step_grid ? tiles : h->step_grid;
   const bool fast = fast_path(h);
+  p.first = first;
+  const uintptr_t all_ptrs = (uintptr_t)actions | (uintptr_t)obs | (uintptr_t)reward | (uintptr_t)done | (uintptr_t)success;
+  const bool tma = (h->variant == 2 || h->variant == 3 || h->variant == 4) && fast && !f64(h) && !(all_ptrs & 15u);
+  if (tma) {  // whole tiles through the bulk-copy pipeline, ragged tail below
+    const int full_tiles = count / h->tma_tile;
+    if (full_tiles > 0) {
+      const int g = full_tiles < h->tma_grid ? full_tiles : h->tma_grid;
+      CU(launch_pdl(h->tma_kernel, g, h->tma_tile, h->tma_smem, s, h->pdl, p, full_tiles));
+      h->launches += 1;
+    }
+    p.first = first + full_tiles * h->tma_tile;
+    if (p.first >= p.n) return 0;
+  }
+  const int tiles = (p.n - p.first + earl::kTTBlock - 1) / earl::kTTBlock;
+  const int grid = tiles < h->step_grid ? tiles : h->step_grid;
   if (f64(h)) {
     if (fast) earl::tabletop_step_kernel<true, true><<<grid, earl::kTTBlock, 0, s>>>(p);
     else earl::tabletop_step_kernel<true, false><<<grid, earl::kTTBlock, 0, s>>>(p);
   } else {
-    if (fast) earl::tabletop_step_kernel<false, true><<<grid, earl::kTTBlock, 0, s>>>(p);
+    if (fast && h->variant == 8) CU(launch_pdl(earl::tabletop_step_kernel<false, true, 8>, grid, earl::kTTBlock, 0, s, h->pdl, p));
+    else if (fast && h->variant == 6) CU(launch_pdl(earl::tabletop_step_kernel<false, true, 6>, grid, earl::kTTBlock, 0, s, h->pdl, p));
+    else if (fast) CU(launch_pdl(earl::tabletop_step_kernel<false, true>, grid, earl::kTTBlock, 0, s, h->pdl, p));
     else earl::tabletop_step_kernel<false, false><<<grid, earl::kTTBlock, 0, s>>>(p);
   }
   CU(cudaGetLastError());
-  h->total_steps += 1;
   h->launches += 1;
+  return 0;
+}
+
+int launch_step(earl_handle* h, const float* actions, float* obs, float* reward, uint8_t* done, uint8_t* success,
+                cudaStream_t s) {
+  if (int rc = launch_step_range(h, 0, h->p.n, actions, obs, reward, done, success, s)) return rc;
+  h->total_steps += 1;
   return 0;
 }
 
@@ -151,6 +216,19 @@ extern "C" {
 int earl_abi_version(void) { return EARL_ABI_VERSION; }
 
 const char* earl_last_error(void) { return g_err; }
+
+void earl_tabletop_thresholds(double threshold, double success_radius, double* attach_sq, float* success_sq) {
+  // smallest double x with sqrt(x) >= threshold  =>  (sqrt(s) < threshold) == (s < x) for every s
+  double x = threshold * threshold;
+  while (std::sqrt(x) >= threshold && x > 0.0) x = std::nextafter(x, 0.0);
+  while (std::sqrt(x) < threshold) x = std::nextafter(x, INFINITY);
+  *attach_sq = x;
+  // largest float y with (double)sqrtf(y) <= radius  =>  ((double)sqrtf(s) <= radius) == (s <= y)
+  float y = (float)(success_radius * success_radius);
+  while ((double)std::sqrt(y) <= success_radius) y = std::nextafterf(y, INFINITY);
+  while ((double)std::sqrt(y) > success_radius && y > 0.f) y = std::nextafterf(y, 0.f);
+  *success_sq = y;
+}
 
 int earl_create(const earl_config* cfg, const void* model_blob, size_t model_nbytes, earl_handle** out) {
   if (!cfg || !out) return fail(EARL_ERR_INVALID, "null cfg/out");
@@ -214,6 +292,7 @@ int earl_create(const earl_config* cfg, const void* model_blob, size_t model_nby
   p.threshold = m->threshold;
   p.clip = m->clip;
   p.success_radius = m->success_radius;
+  earl_tabletop_thresholds(m->threshold, m->success_radius, &p.attach_sq, &p.success_sq);
   for (int k = 0; k < 4; ++k) p.init_qpos[k] = m->initial_state[k];
   rc = upload_goal_tables(h);
   if (rc) { earl_destroy(h); return rc; }
@@ -224,6 +303,40 @@ int earl_create(const earl_config* cfg, const void* model_blob, size_t model_nby
   else rc = fast ? occupancy_grid(earl::tabletop_step_kernel<false, true>, h->sm_count, &h->step_grid)
                  : occupancy_grid(earl::tabletop_step_kernel<false, false>, h->sm_count, &h->step_grid);
   if (rc) { earl_destroy(h); return rc; }
+  if (const char* v = getenv("EARL_TT_VARIANT")) h->variant = atoi(v);
+  // measured on B200 (profiles/round1_variants.md): while the 24 B/env state fits in L2 next to the streams
+  // the LSU kernel wins (more resident warps hide L2 latency); once everything streams from HBM the
+  // bulk-copy pipeline keeps more bytes in flight and wins.
+  if (h->variant < 0) h->variant = cfg->num_envs > 3 * 1024 * 1024 ? 3 : 0;
+  if (const char* v = getenv("EARL_TT_PDL")) h->pdl = atoi(v) != 0;
+  if (fast && !f64(h) && (h->variant == 8 || h->variant == 6)) {
+    rc = h->variant == 8 ? occupancy_grid(earl::tabletop_step_kernel<false, true, 8>, h->sm_count, &h->step_grid)
+                         : occupancy_grid(earl::tabletop_step_kernel<false, true, 6>, h->sm_count, &h->step_grid);
+    if (rc) { earl_destroy(h); return rc; }
+  }
+  if ((h->variant == 2 || h->variant == 3 || h->variant == 4) && fast && !f64(h)) {
+    int per_sm = 0;
+    cudaError_t e2 = cudaSuccess;
+    if (const char* v = getenv("EARL_TT_TILE")) h->tma_tile = atoi(v) == 128 ? 128 : 256;
+    auto setup = [&](auto kernel, size_t smem) {
+      h->tma_smem = smem;
+      h->tma_kernel = kernel;
+      e2 = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, h->tma_tile, smem);
+    };
+    if (h->tma_tile == 128) {
+      if (h->variant == 4) setup(earl::tabletop_step_tma_kernel<4, 128>, sizeof(earl::TTStage<128>) * 4);
+      else if (h->variant == 2) setup(earl::tabletop_step_tma_kernel<2, 128>, sizeof(earl::TTStage<128>) * 2);
+      else setup(earl::tabletop_step_tma_kernel<3, 128>, sizeof(earl::TTStage<128>) * 3);
+    } else {
+      if (h->variant == 4) setup(earl::tabletop_step_tma_kernel<4, 256>, sizeof(earl::TTStage<256>) * 4);
+      else if (h->variant == 2) setup(earl::tabletop_step_tma_kernel<2, 256>, sizeof(earl::TTStage<256>) * 2);
+      else setup(earl::tabletop_step_tma_kernel<3, 256>, sizeof(earl::TTStage<256>) * 3);
+    }
+    if (e2 != cudaSuccess) { earl_destroy(h); return fail(EARL_ERR_CUDA, "TMA kernel setup: %s", cudaGetErrorString(e2)); }
+    if (const char* v = getenv("EARL_TT_CTAS_PER_SM")) { int c = atoi(v); if (c >= 1 && c < per_sm) per_sm = c; }
+    h->tma_grid = h->sm_count * (per_sm < 1 ? 1 : per_sm);
+  }
   e = cudaStreamCreateWithFlags(&h->host_stream, cudaStreamNonBlocking);
   if (e != cudaSuccess) { earl_destroy(h); return fail(EARL_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
   *out = h;
@@ -235,6 +348,8 @@ int earl_destroy(earl_handle* h) {
   cudaSetDevice(h->device);
   for (void* q : h->owned) cudaFree(q);
   if (h->host_stream) cudaStreamDestroy(h->host_stream);
+  if (h->in_stream) cudaStreamDestroy(h->in_stream);
+  for (auto& ev : h->chunk_ev) if (ev) cudaEventDestroy(ev);
   delete h;
   return 0;
 }
@@ -321,15 +436,33 @@ int earl_step_host(earl_handle* h, const float* actions_host, float* obs_host, f
     if (!rc) rc = h->alloc(&h->d_done, n, false);
     if (!rc) rc = h->alloc(&h->d_succ, n, false);
     if (rc) return rc;
+    CU(cudaStreamCreateWithFlags(&h->in_stream, cudaStreamNonBlocking));
+    for (auto& ev : h->chunk_ev) CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
   }
-  cudaStream_t s = h->host_stream;
-  CU(cudaMemcpyAsync(h->d_act, actions_host, n * earl::kTTAct * sizeof(float), cudaMemcpyHostToDevice, s));
-  if (int rc = launch_step(h, h->d_act, h->d_obs, h->d_rew, h->d_done, success_host ? h->d_succ : nullptr, s)) return rc;
-  CU(cudaMemcpyAsync(obs_host, h->d_obs, n * earl::kTTObs * sizeof(float), cudaMemcpyDeviceToHost, s));
-  CU(cudaMemcpyAsync(reward_host, h->d_rew, n * sizeof(float), cudaMemcpyDeviceToHost, s));
-  CU(cudaMemcpyAsync(done_host, h->d_done, n, cudaMemcpyDeviceToHost, s));
-  if (success_host) CU(cudaMemcpyAsync(success_host, h->d_succ, n, cudaMemcpyDeviceToHost, s));
-  CU(cudaStreamSynchronize(s));
+  // Chunked software pipeline over the PCIe link: the host->device copy of chunk c+1 (in_stream) overlaps the
+  // kernel and the device->host copies of chunk c (host_stream); the link is full duplex.
+  constexpr int kMaxChunks = earl_handle::kMaxChunks;
+  int chunks = (int)(n / (128 * 1024));
+  chunks = chunks < 1 ? 1 : (chunks > kMaxChunks ? kMaxChunks : chunks);
+  const size_t per = ((n / chunks + 255) / 256) * 256;  // chunk boundaries stay tile- and 16-byte aligned
+  cudaStream_t si = h->in_stream, so = h->host_stream;
+  uint8_t* d_succ = success_host ? h->d_succ : nullptr;
+  int c = 0;
+  for (size_t off = 0; off < n; off += per, ++c) {
+    const size_t cnt = off + per <= n ? per : n - off;
+    CU(cudaMemcpyAsync(h->d_act + off * earl::kTTAct, actions_host + off * earl::kTTAct, cnt * earl::kTTAct * sizeof(float),
+                       cudaMemcpyHostToDevice, si));
+    CU(cudaEventRecord(h->chunk_ev[c], si));
+    CU(cudaStreamWaitEvent(so, h->chunk_ev[c], 0));
+    if (int rc = launch_step_range(h, (int)off, (int)cnt, h->d_act, h->d_obs, h->d_rew, h->d_done, d_succ, so)) return rc;
+    CU(cudaMemcpyAsync(obs_host + off * earl::kTTObs, h->d_obs + off * earl::kTTObs, cnt * earl::kTTObs * sizeof(float),
+                       cudaMemcpyDeviceToHost, so));
+    CU(cudaMemcpyAsync(reward_host + off, h->d_rew + off, cnt * sizeof(float), cudaMemcpyDeviceToHost, so));
+    CU(cudaMemcpyAsync(done_host + off, h->d_done + off, cnt, cudaMemcpyDeviceToHost, so));
+    if (success_host) CU(cudaMemcpyAsync(success_host + off, h->d_succ + off, cnt, cudaMemcpyDeviceToHost, so));
+  }
+  h->total_steps += 1;
+  CU(cudaStreamSynchronize(so));
   return 0;
 }
 
@@ -352,7 +485,7 @@ int earl_compute_reward(earl_handle* h, const float* obs_dev, int64_t num_obs, f
   if (num_obs == 0) return 0;
   const unsigned grid = (unsigned)((num_obs + 255) / 256);
   earl::tabletop_reward_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      obs_dev, num_obs, h->cfg.flags, h->model.success_radius, reward_dev, success_dev);
+      obs_dev, num_obs, h->cfg.flags, h->p.success_sq, reward_dev, success_dev);
   CU(cudaGetLastError());
   h->launches += 1;
   return 0;

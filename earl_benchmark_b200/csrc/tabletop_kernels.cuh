@@ -62,6 +62,8 @@ struct TabletopParams {
   uint8_t* done;         // [N]
   uint8_t* success;      // [N] or null
   int n;
+  int first;  // first env this launch touches (chunked host path; ragged tail after the TMA kernel); multiple of 32
+              // the launch covers envs [first, n)
   int goal_stream_rows;
   uint32_t features;
   unsigned long long horizon;
@@ -69,8 +71,21 @@ struct TabletopParams {
   // constants of the task (earl_tabletop_model)
   double act_lo, act_span;  // -move_distance, move_distance - (-move_distance)
   double threshold, clip, success_radius;
+  // sqrt-free forms of the two radius tests, exact by monotonicity of correctly rounded sqrt (computed on
+  // the host by earl_tabletop_thresholds): sqrt(s) < threshold <=> s < attach_sq;
+  // (double)sqrtf(s) <= success_radius <=> s <= success_sq
+  double attach_sq;
+  float success_sq;
   double init_qpos[4];
 };
+
+// Programmatic dependent launch: step t+1 may be scheduled while step t drains; nothing of the state is
+// touched before the previous grid has completed and flushed (griddepcontrol.wait).  Both are no-ops
+// for launches without the programmatic-serialization attribute.
+__device__ __forceinline__ void pdl_wait_prior_grid() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
 
 __device__ __forceinline__ double clipd(double x, double lo, double hi) {
   // np.clip: NaN propagates (both comparisons false)
@@ -81,20 +96,22 @@ __device__ __forceinline__ double clipd(double x, double lo, double hi) {
 __device__ __forceinline__ float norm2_f32(float a, float b) {
   return __fsqrt_rn(__fadd_rn(__fmul_rn(a, a), __fmul_rn(b, b)));
 }
-__device__ __forceinline__ float norm4_f32(float a, float b, float c, float d) {
-  float s = __fadd_rn(__fmul_rn(a, a), __fmul_rn(b, b));
-  s = __fadd_rn(s, __fmul_rn(c, c));
-  s = __fadd_rn(s, __fmul_rn(d, d));
-  return __fsqrt_rn(s);
-}
 
-// is_successful on an fp32 observation (tabletop_manipulation.py:197-204)
-__device__ __forceinline__ bool tt_success(const float4& pos, const float4& g0, bool wide, double radius) {
+// is_successful on an fp32 observation (tabletop_manipulation.py:197-204): fp32 squared norm in index
+// order, nothing fused; `success_sq` is the exact sqrt-free threshold (see TabletopParams)
+__device__ __forceinline__ bool tt_success(const float4& pos, const float4& g0, bool wide, float success_sq) {
   // pos = obs[0:4]; g0 = obs[6:10] = goal[0:4]
-  float nrm = wide ? norm2_f32(__fsub_rn(pos.z, g0.z), __fsub_rn(pos.w, g0.w))
-                   : norm4_f32(__fsub_rn(pos.x, g0.x), __fsub_rn(pos.y, g0.y), __fsub_rn(pos.z, g0.z),
-                               __fsub_rn(pos.w, g0.w));
-  return (double)nrm <= radius;
+  const float dz = __fsub_rn(pos.z, g0.z), dw = __fsub_rn(pos.w, g0.w);
+  float s;
+  if (wide) {
+    s = __fadd_rn(__fmul_rn(dz, dz), __fmul_rn(dw, dw));
+  } else {
+    const float dx = __fsub_rn(pos.x, g0.x), dy = __fsub_rn(pos.y, g0.y);
+    s = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+    s = __fadd_rn(s, __fmul_rn(dz, dz));
+    s = __fadd_rn(s, __fmul_rn(dw, dw));
+  }
+  return s <= success_sq;
 }
 
 // dense reward (tabletop_manipulation.py:179-189), fp64 after the fp32 norms as numpy 1.22 evaluates it
@@ -123,8 +140,7 @@ __device__ __forceinline__ void tt_move(TTState& s, float a0f, float a1f, float 
     if (!attached) {
       // dist = np.linalg.norm(fist - mug) < threshold, on the PRE-move positions (:144-152)
       const double dx = __dsub_rn(s.fx, s.mx), dy = __dsub_rn(s.fy, s.my);
-      const double dist = __dsqrt_rn(__fma_rn(dy, dy, __dmul_rn(dx, dx)));
-      attached = dist < p.threshold;
+      attached = __fma_rn(dy, dy, __dmul_rn(dx, dx)) < p.attach_sq;  // == sqrt(.) < threshold, exactly
     }
   } else {
     attached = false;
@@ -184,15 +200,16 @@ __device__ __forceinline__ void tt_store_obs_tile(float* __restrict__ obs, const
 
 // The hot kernel.  FAST = sparse reward, no lifelong / auto-reset / eval-stats (the headline config);
 // the general instantiation handles every feature with warp-uniform runtime branches.
-template <bool F64, bool FAST>
-__global__ void __launch_bounds__(kTTBlock) tabletop_step_kernel(const TabletopParams p) {
+template <bool F64, bool FAST, int MINB = 1>
+__global__ void __launch_bounds__(kTTBlock, MINB) tabletop_step_kernel(const TabletopParams p) {
   __shared__ __align__(16) float tiles[kTTBlock / 32][32 * kTTObs];
+  pdl_wait_prior_grid();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float* tile = tiles[warp];
   const bool dense = !FAST && (p.features & kDense);
   const bool wide = p.features & kWide;
 
-  for (int base = blockIdx.x * kTTBlock; base < p.n; base += gridDim.x * kTTBlock) {
+  for (int base = p.first + blockIdx.x * kTTBlock; base < p.n; base += gridDim.x * kTTBlock) {
     const int i = base + threadIdx.x;
     const int warp_base = base + warp * 32;
     if (warp_base >= p.n) break;  // warp-uniform
@@ -213,7 +230,7 @@ __global__ void __launch_bounds__(kTTBlock) tabletop_step_kernel(const TabletopP
       tt_move(s, a0, a1, a2, p);
       pos32 = make_float4(__double2float_rn(s.fx), __double2float_rn(s.fy), __double2float_rn(s.mx),
                           __double2float_rn(s.my));
-      const bool succ = tt_success(pos32, g0, wide, p.success_radius);
+      const bool succ = tt_success(pos32, g0, wide, p.success_sq);
       float rew = succ ? 1.f : 0.f;
       if (!FAST && dense) rew = (float)tt_dense_reward(pos32, g0);
 
@@ -277,6 +294,148 @@ __global__ void __launch_bounds__(kTTBlock) tabletop_step_kernel(const TabletopP
     tt_store_obs_tile(p.obs, tile, warp_base, p.n, lane);
     __syncwarp();
   }
+}
+
+// ------------------------------------------------------------------------------------------ TMA pipeline
+// Same step, restructured around the Blackwell/Hopper bulk-copy engine (cp.async.bulk, SASS UBLKCP):
+// a persistent CTA walks its tiles of kTile envs through an S-stage shared-memory ring.  One elected
+// thread issues three bulk loads per tile (qpos, meta, actions: contiguous 4 KB / 2 KB / 3 KB runs) that
+// complete on an mbarrier, every thread computes its env out of shared memory, the results are laid
+// out in shared memory exactly as they sit in HBM, and the elected thread issues bulk stores
+// (qpos, meta, obs 12 KB, reward, done[, success]).  Bytes in flight are set by the ring depth instead of
+// by occupancy x registers, loads/stores are full-line by construction, and the LSU sees no global
+// traffic at all.  Only whole tiles go through this kernel; a ragged tail (< kTile envs) is finished by
+// tabletop_step_kernel launched on the remainder.
+
+template <int kTile>
+struct alignas(128) TTStage {
+  float4 in_qpos[kTile];
+  uint2 in_meta[kTile];
+  float in_act[kTile * kTTAct];
+  float4 out_qpos[kTile];
+  uint2 out_meta[kTile];
+  float out_obs[kTile * kTTObs];
+  float out_reward[kTile];
+  uint8_t out_done[kTile];
+  uint8_t out_success[kTile];
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void* dst_gmem, const void* src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)),
+               "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// FAST configuration only: fp32 state, sparse reward, no lifelong / auto-reset / eval-stats.
+template <int STAGES, int kTile>
+__global__ void __launch_bounds__(kTile) tabletop_step_tma_kernel(const TabletopParams p, int num_tiles) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  TTStage<kTile>* st = reinterpret_cast<TTStage<kTile>*>(smem_raw);
+  __shared__ __align__(8) uint64_t full[STAGES];
+  const int tid = threadIdx.x;
+  const bool wide = p.features & kWide;
+  constexpr uint32_t kInBytes = kTile * (16 + 8 + 4 * kTTAct);
+
+  auto issue_loads = [&](int tile, int s) {
+    const size_t e = (size_t)p.first + (size_t)tile * kTile;
+    mbar_expect_tx(&full[s], kInBytes);
+    bulk_g2s(st[s].in_qpos, reinterpret_cast<const float4*>(p.qpos) + e, kTile * 16, &full[s]);
+    bulk_g2s(st[s].in_meta, p.meta + e, kTile * 8, &full[s]);
+    bulk_g2s(st[s].in_act, p.actions + e * kTTAct, kTile * 4 * kTTAct, &full[s]);
+  };
+
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < STAGES; ++s) mbar_init(&full[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  pdl_wait_prior_grid();  // barrier setup above overlaps the previous step's tail
+  __syncthreads();
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < STAGES; ++s) {
+      const int tile = blockIdx.x + s * gridDim.x;
+      if (tile < num_tiles) issue_loads(tile, s);
+    }
+  }
+
+  int it = 0;
+  for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    const int s = it % STAGES;
+    const uint32_t parity = (uint32_t)(it / STAGES) & 1u;
+    mbar_wait(&full[s], parity);
+    TTStage<kTile>& b = st[s];
+
+    TTState sdev;
+    const float4 q = b.in_qpos[tid];
+    const uint2 m = b.in_meta[tid];
+    const float a0 = b.in_act[tid * kTTAct + 0], a1 = b.in_act[tid * kTTAct + 1], a2 = b.in_act[tid * kTTAct + 2];
+    sdev.fx = q.x; sdev.fy = q.y; sdev.mx = q.z; sdev.my = q.w;
+    sdev.flags = m.x;
+    uint32_t steps = m.y;
+    const uint32_t gi = (sdev.flags & kGoalMask) >> kGoalShift;
+    const float4 g0 = __ldg(p.goal32 + 2 * gi);
+    const float4 g1 = __ldg(p.goal32 + 2 * gi + 1);
+    tt_move(sdev, a0, a1, a2, p);
+    const float4 pos32 = make_float4(__double2float_rn(sdev.fx), __double2float_rn(sdev.fy),
+                                     __double2float_rn(sdev.mx), __double2float_rn(sdev.my));
+    const bool succ = tt_success(pos32, g0, wide, p.success_sq);
+    steps = steps == 0xffffffffu ? steps : steps + 1u;
+    const bool done = (unsigned long long)steps >= p.horizon;
+    const float att = (sdev.flags & kAttached) ? 0.f : -1.f;
+
+    b.out_qpos[tid] = pos32;
+    b.out_meta[tid] = make_uint2(sdev.flags, steps);
+    float4* row = reinterpret_cast<float4*>(b.out_obs + tid * kTTObs);
+    row[0] = pos32;
+    row[1] = make_float4(att, att, g0.x, g0.y);
+    row[2] = make_float4(g0.z, g0.w, g1.x, g1.y);
+    b.out_reward[tid] = succ ? 1.f : 0.f;
+    b.out_done[tid] = done ? 1 : 0;
+    b.out_success[tid] = succ ? 1 : 0;
+    fence_proxy_async();  // generic-proxy smem writes -> visible to the bulk-copy (async) proxy
+    // out[] of the stage the NEXT iteration writes must have been drained by its previous bulk stores
+    if (tid == 0) bulk_wait_read<(STAGES >= 2 ? STAGES - 2 : 0)>();
+    __syncthreads();
+    if (tid == 0) {
+      const size_t e = (size_t)p.first + (size_t)tile * kTile;
+      bulk_s2g(reinterpret_cast<float4*>(p.qpos) + e, b.out_qpos, kTile * 16);
+      bulk_s2g(p.meta + e, b.out_meta, kTile * 8);
+      bulk_s2g(p.obs + e * kTTObs, b.out_obs, kTile * 4 * kTTObs);
+      bulk_s2g(p.reward + e, b.out_reward, kTile * 4);
+      bulk_s2g(p.done + e, b.out_done, kTile);
+      if (p.success) bulk_s2g(p.success + e, b.out_success, kTile);
+      bulk_commit();
+      const int next = tile + STAGES * gridDim.x;  // in[] of this stage is free: everyone passed the barrier
+      if (next < num_tiles) issue_loads(next, s);
+    }
+  }
+  if (tid == 0) bulk_wait_all();
 }
 
 // ------------------------------------------------------------------------------------------ cold kernels
@@ -354,14 +513,14 @@ __global__ void tabletop_get_obs_kernel(const TabletopParams p, float* __restric
 }
 
 // compute_reward(obs) / is_successful(obs) on caller-supplied observations
-__global__ void tabletop_reward_kernel(const float* __restrict__ obs, long long m, uint32_t features, double radius,
+__global__ void tabletop_reward_kernel(const float* __restrict__ obs, long long m, uint32_t features, float success_sq,
                                        float* __restrict__ reward, uint8_t* __restrict__ success) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= m) return;
   const float4* row = reinterpret_cast<const float4*>(obs + i * kTTObs);
   const float4 pos = row[0], r1 = row[1], r2 = row[2];
   const float4 g0 = make_float4(r1.z, r1.w, r2.x, r2.y);
-  const bool succ = tt_success(pos, g0, features & kWide, radius);
+  const bool succ = tt_success(pos, g0, features & kWide, success_sq);
   if (reward) reward[i] = (features & kDense) ? (float)tt_dense_reward(pos, g0) : (succ ? 1.f : 0.f);
   if (success) success[i] = succ ? 1 : 0;
 }

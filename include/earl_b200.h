@@ -89,6 +89,11 @@ typedef struct {
 } earl_tabletop_model;
 #define EARL_TABLETOP_MAGIC 0x54544142u /* 'TTAB' */
 
+/* Pure host helper: the exact sqrt-free forms of the two radius tests the kernels use
+ * (tabletop_manipulation.py:149 `dist < self.threshold`, :204 `norm <= 0.2`):
+ *   sqrt(s) < threshold  <=>  s < *attach_sq   (fp64);   (double)sqrtf(s) <= success_radius  <=>  s <= *success_sq  (fp32) */
+EARL_API void earl_tabletop_thresholds(double threshold, double success_radius, double* attach_sq, float* success_sq);
+
 /* ---------------------------------------------------------------- lifecycle */
 
 EARL_API int earl_abi_version(void);

@@ -90,8 +90,8 @@ class TabletopOracle:
         self.qpos[m] = q[m]
         if self.state_f32:
             self.qpos[m] = self.qpos[m].astype(np.float32).astype(np.float64)
-        lib().earl_oracle_psw_reset(self.n, np.ascontiguousarray(m, np.uint8).ctypes.data, self.steps_since_reset,
-                                    self.num_interventions)
+        m8 = np.ascontiguousarray(m, np.uint8)  # keep alive across the call: only its address is passed
+        lib().earl_oracle_psw_reset(self.n, m8.ctypes.data, self.steps_since_reset, self.num_interventions)
         return self.get_obs()
 
     def step(self, action):

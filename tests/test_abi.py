@@ -61,3 +61,27 @@ def test_product_package_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".hpp", ".h")):
                 text = open(os.path.join(root, f)).read()
                 assert "oracle" not in text.replace("oracle/gen_golden.py", "").replace("tests/golden", ""), os.path.join(root, f)
+
+
+def test_sqrt_free_thresholds_are_exact():
+    """The kernels test s < attach_sq and s <= success_sq instead of taking square roots; both forms must
+    agree with the reference's sqrt-then-compare for EVERY s, checked here around the boundary."""
+    import numpy as np
+    a, s = ctypes.c_double(), ctypes.c_float()
+    _lib.lib().earl_tabletop_thresholds(0.4, 0.2, ctypes.byref(a), ctypes.byref(s))
+    x = np.float64(a.value)
+    xs = [x]
+    lo = hi = x
+    for _ in range(2000):
+        lo, hi = np.nextafter(lo, 0.0), np.nextafter(hi, np.inf)
+        xs += [lo, hi]
+    xs = np.array(xs + list(np.random.RandomState(0).uniform(0, 1, 20000)))
+    assert np.array_equal(np.sqrt(xs) < 0.4, xs < x)
+    y = np.float32(s.value)
+    ys = [y]
+    lo = hi = y
+    for _ in range(2000):
+        lo, hi = np.nextafter(lo, np.float32(0)), np.nextafter(hi, np.float32(np.inf))
+        ys += [lo, hi]
+    ys = np.array(ys + list(np.random.RandomState(1).uniform(0, 0.2, 20000).astype(np.float32)), dtype=np.float32)
+    assert np.array_equal(np.sqrt(ys).astype(np.float64) <= 0.2, ys <= y)
