@@ -1,0 +1,148 @@
+"""ctypes binding of oracle/libearl_mjengine.so + the metaworld / EARL Sawyer env logic on top of it.
+TEST INFRASTRUCTURE ONLY."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+PTR = dict(qpos=0, qvel=1, ctrl=2, mocap_pos=3, mocap_quat=4, xpos=5, site_xpos=6, geom_xpos=7, qacc=8, qacc_warmstart=9, M=10,
+           qfrc_bias=11, efc_force=12, efc_pos=13, qfrc_constraint=14, xmat=15, qfrc_smooth=16, qacc_smooth=17, con_pos=18,
+           con_dist=19, con_frame=20)
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        so = os.path.join(_HERE, "libearl_mjengine.so")
+        srcs = [os.path.join(_HERE, f) for f in ("mjengine.c", "mjcollide.c", "mjengine.h")]
+        if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+            subprocess.check_call(["make", "-C", _HERE, "-B", "libearl_mjengine.so"], stdout=subprocess.DEVNULL)
+        L = C.CDLL(so)
+        L.mje_load.restype = C.c_void_p
+        L.mje_load.argtypes = [C.c_char_p, C.c_longlong]
+        L.mje_make_data.restype = C.c_void_p
+        L.mje_ptr.restype = C.POINTER(C.c_double)
+        L.mje_ptr.argtypes = [C.c_void_p, C.c_int]
+        L.mje_int.argtypes = [C.c_void_p, C.c_int]
+        L.mje_flops.restype = C.c_longlong
+        L.mje_flops.argtypes = [C.c_void_p]
+        for f in ("mje_reset", "mje_forward", "mje_step", "mje_kinematics", "mje_mass_matrix", "mje_bias"):
+            getattr(L, f).argtypes = [C.c_void_p, C.c_void_p]
+            getattr(L, f).restype = None
+        L.mje_multi_step.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        L.mje_free.argtypes = [C.c_void_p]
+        L.mje_free_data.argtypes = [C.c_void_p]
+        _LIB = L
+    return _LIB
+
+
+class Engine:
+    """One fp64 environment instance of the fused model `model` (earl_benchmark_b200.mjcf.compile.Model)."""
+
+    def __init__(self, model):
+        self.model = model
+        blob = model.to_blob()
+        self.m = lib().mje_load(blob, len(blob))
+        if not self.m:
+            raise RuntimeError("mje_load rejected the model blob")
+        self.d = lib().mje_make_data()
+        self.nq, self.nv = int(model.nq), int(model.nv)
+        self.reset()
+
+    def __del__(self):
+        try:
+            lib().mje_free_data(self.d)
+            lib().mje_free(self.m)
+        except Exception:
+            pass
+
+    def arr(self, name, shape):
+        p = lib().mje_ptr(self.d, PTR[name])
+        return np.ctypeslib.as_array(p, shape=(int(np.prod(shape)),)).reshape(shape)
+
+    qpos = property(lambda s: s.arr("qpos", (s.nq,)))
+    qvel = property(lambda s: s.arr("qvel", (s.nv,)))
+    ctrl = property(lambda s: s.arr("ctrl", (int(s.model.nu),)))
+    mocap_pos = property(lambda s: s.arr("mocap_pos", (3,)))
+    mocap_quat = property(lambda s: s.arr("mocap_quat", (4,)))
+    qacc = property(lambda s: s.arr("qacc", (s.nv,)))
+    nefc = property(lambda s: lib().mje_int(s.d, 0))
+    ncon = property(lambda s: lib().mje_int(s.d, 1))
+    solver_iter = property(lambda s: lib().mje_int(s.d, 2))
+    flops = property(lambda s: lib().mje_flops(s.d))
+
+    def reset(self):
+        lib().mje_reset(self.m, self.d)
+
+    def forward(self):
+        lib().mje_forward(self.m, self.d)
+
+    def step(self, n=1):
+        lib().mje_multi_step(self.m, self.d, int(n))
+
+    def site_xpos(self, name):
+        return self.arr("site_xpos", (40, 3))[self.model.site_id(name)].copy()
+
+    def geom_xpos(self, name):
+        return self.arr("geom_xpos", (160, 3))[self.model.geom_id(name)].copy()
+
+    def mass_matrix(self):
+        lib().mje_kinematics(self.m, self.d)
+        lib().mje_mass_matrix(self.m, self.d)
+        return self.arr("M", (32, 32))[:self.nv, :self.nv].copy()
+
+    def bias(self):
+        lib().mje_kinematics(self.m, self.d)
+        lib().mje_bias(self.m, self.d)
+        return self.arr("qfrc_bias", (32,))[:self.nv].copy()
+
+
+class SawyerDoorOracle:
+    """metaworld SawyerXYZEnv.step / reset semantics + EARL SawyerDoorV2 observation and sparse reward
+    (reference earl_benchmark/envs/sawyer_door.py:86-125,141-177)."""
+    MOCAP_LOW = np.array([-0.5, 0.40, 0.05])
+    MOCAP_HIGH = np.array([0.5, 1.0, 0.5])
+    HAND_INIT = np.array([0, 0.4, 0.2], dtype=np.float32).astype(np.float64)
+    GOAL = np.array([0.29072163, 0.74286009, 0.10003595, 1.0, 0.29072163, 0.74286009, 0.10003595])
+    FRAME_SKIP, ACTION_SCALE = 5, 1.0 / 100
+
+    def __init__(self, model):
+        self.e = Engine(model)
+        self.goal = self.GOAL.copy()
+        self.door_qadr = int(model.jnt_qposadr[model.names["joint"].index("doorjoint")])
+
+    def reset_hand(self, steps=50):
+        for _ in range(steps):
+            self.e.mocap_pos[:] = self.HAND_INIT
+            self.e.mocap_quat[:] = [1, 0, 1, 0]
+            self.e.ctrl[:] = [-1, 1]
+            self.e.step(self.FRAME_SKIP)
+
+    def reset(self, door_angle=-np.pi / 3):
+        self.e.reset()
+        self.reset_hand()
+        self.e.qpos[self.door_qadr] = door_angle
+        self.e.qvel[self.door_qadr] = 0
+        self.e.forward()
+        return self.obs()
+
+    def obs(self):
+        e = self.e
+        hand = e.site_xpos("body:hand")
+        grip = np.clip(np.linalg.norm(e.site_xpos("rightEndEffector") - e.site_xpos("leftEndEffector")) / 0.1, 0.0, 1.0)
+        return np.concatenate([hand, [grip], e.geom_xpos("handle"), self.goal])
+
+    def step(self, action):
+        a = np.clip(np.asarray(action, np.float64), -1, 1)
+        self.e.mocap_pos[:] = np.clip(self.e.mocap_pos + a[:3] * self.ACTION_SCALE, self.MOCAP_LOW, self.MOCAP_HIGH)
+        self.e.mocap_quat[:] = [1, 0, 1, 0]
+        self.e.ctrl[:] = [a[3], -a[3]]
+        self.e.step(self.FRAME_SKIP)
+        # NO forward() here: mj_step integrates AFTER its mj_forward, so the body / site / geom poses the env reads right
+        # after sim.step() are those of the state BEFORE the last substep's integration (one substep stale).
+        o = self.obs()
+        reward = float(np.linalg.norm(o[4:7] - o[11:14]) <= 0.02)
+        return o, reward

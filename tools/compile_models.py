@@ -1,0 +1,32 @@
+#!/usr/bin/env python
+"""Compile the reference's MJCF assets into structure-of-arrays model files (earl_benchmark_b200/models/*.npz).
+
+Run in the build container (needs /root/reference); the GPU box only sees the committed .npz files.
+    python tools/compile_models.py
+"""
+import os
+import sys
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, REPO)
+from earl_benchmark_b200.mjcf import compile as C, parser  # noqa: E402
+
+REF = os.environ.get("EARL_REFERENCE", "/root/reference")
+MW = os.path.join(REF, "earl_benchmark/envs/metaworld_assets/sawyer_xyz")
+OUT = os.path.join(REPO, "earl_benchmark_b200", "models")
+
+
+def sawyer_door():
+    spec = parser.load(os.path.join(MW, "sawyer_door_pull.xml"))
+    # reset_model() moves the door body to obj_init_pos, an fp32 array (reference envs/sawyer_door.py:36,119-120)
+    door_pos = np.array([0.1, 0.95, 0.1], dtype=np.float32).astype(np.float64)
+    return C.compile_model(spec, body_pos_overrides={"door": door_pos}, keep_geoms=("handle",), frame_sites=("hand",))
+
+
+if __name__ == "__main__":
+    os.makedirs(OUT, exist_ok=True)
+    m = sawyer_door()
+    m.save(os.path.join(OUT, "sawyer_door.npz"))
+    print("sawyer_door: bodies", int(m.nbody), "nv", int(m.nv), "geoms", int(m.ngeom), "blob", len(m.to_blob()), "B")
