@@ -21,12 +21,18 @@ def _bool(s):
 
 
 class Transform:
-    def __init__(self, pos=None, R=None):
+    """Rigid transform carried as (pos, unit quaternion).  Composition multiplies the quaternions WITHOUT
+    canonicalising their sign: MuJoCo builds body orientations the same way (xquat = xquat[parent] * body_quat),
+    and the sign is observable -- the weld residual is the vector part of a quaternion product, so q and -q pull a
+    body with a large orientation error the opposite way round."""
+
+    def __init__(self, pos=None, quat=None):
         self.pos = np.zeros(3) if pos is None else np.asarray(pos, float)
-        self.R = np.eye(3) if R is None else np.asarray(R, float)
+        self.quat = np.array([1.0, 0, 0, 0]) if quat is None else np.asarray(quat, float)
+        self.R = quat2mat(self.quat)
 
     def __matmul__(self, o):  # self o other:  x -> self.R (o.R x + o.pos) + self.pos
-        return Transform(self.R @ o.pos + self.pos, self.R @ o.R)
+        return Transform(self.R @ o.pos + self.pos, quat_mul(self.quat, o.quat))
 
     def apply(self, p):
         return self.R @ np.asarray(p, float) + self.pos
@@ -277,7 +283,7 @@ class RawModel:
 
 class Model:
     """Fused structure-of-arrays model.  Every field is a numpy array (see `FIELDS`), so it serialises to a flat
-    blob the C oracle and the CUDA library read identically (save/load)."""
+    blob every consumer (the CUDA library, test checkers) reads identically (save/load)."""
 
     FIELDS = (
         # scalars
@@ -374,7 +380,7 @@ def compile_model(spec, body_pos_overrides=None, keep_geoms=(), keep_sites=None,
     anchor = np.zeros(nb, int)
     T = [Transform() for _ in range(nb)]
     for b in range(1, nb):
-        local = Transform(raw.pos[b], quat2mat(raw.quat[b]))
+        local = Transform(raw.pos[b], raw.quat[b])
         if raw.body_joints[b]:
             anchor[b] = b
         elif raw.mocap[b]:
@@ -400,8 +406,8 @@ def compile_model(spec, body_pos_overrides=None, keep_geoms=(), keep_sites=None,
         p = raw.parent[b]
         pa = anchor[p]
         m.body_parent[fid[b]] = fid[pa]
-        loc = T[p] @ Transform(raw.pos[b], quat2mat(raw.quat[b]))
-        m.body_pos[fid[b]], m.body_quat[fid[b]] = loc.pos, mat2quat(loc.R)
+        loc = T[p] @ Transform(raw.pos[b], raw.quat[b])
+        m.body_pos[fid[b]], m.body_quat[fid[b]] = loc.pos, loc.quat
     # composite inertias
     acc = {f: [] for f in range(nf)}
     for b in range(1, nb):
@@ -466,7 +472,7 @@ def compile_model(spec, body_pos_overrides=None, keep_geoms=(), keep_sites=None,
     m.geom_type = arr(lambda g: GEOM_TYPES.index(g["type"]), np.int32)
     m.geom_size = arr(lambda g: _floats(g.get("size", "0"), 3)[:3]).reshape(ng, 3)
     m.geom_pos = arr(lambda g: T[g["body"]].apply(g["lpos"])).reshape(ng, 3)
-    m.geom_quat = arr(lambda g: mat2quat(T[g["body"]].R @ quat2mat(g["lquat"]))).reshape(ng, 4)
+    m.geom_quat = arr(lambda g: quat_mul(T[g["body"]].quat, g["lquat"])).reshape(ng, 4)
     m.geom_contype = arr(lambda g: int(g["contype"]), np.int32)
     m.geom_conaffinity = arr(lambda g: int(g["conaffinity"]), np.int32)
     m.geom_condim = arr(lambda g: int(g["condim"]), np.int32)
@@ -499,7 +505,7 @@ def compile_model(spec, body_pos_overrides=None, keep_geoms=(), keep_sites=None,
     m.nhullvert = np.int32(len(m.hull_vert))
     # sites (+ frames of requested original bodies)
     sites = [s for s in raw.sites if keep_sites is None or s.get("name") in keep_sites]
-    recs = [(s.get("name", "site"), anchor[s["body"]], T[s["body"]] @ Transform(s["lpos"], quat2mat(s["lquat"]))) for s in sites]
+    recs = [(s.get("name", "site"), anchor[s["body"]], T[s["body"]] @ Transform(s["lpos"], s["lquat"])) for s in sites]
     for bname in frame_sites:
         b = raw.names.index(bname)
         recs.append((f"body:{bname}", anchor[b], T[b] if anchor[b] != b else Transform()))
@@ -507,7 +513,7 @@ def compile_model(spec, body_pos_overrides=None, keep_geoms=(), keep_sites=None,
     m.names["site"] = [r[0] for r in recs]
     m.site_body = np.array([fid[r[1]] if r[1] >= 0 else 0 for r in recs], np.int32)
     m.site_pos = np.array([r[2].pos for r in recs]).reshape(len(recs), 3)
-    m.site_quat = np.array([mat2quat(r[2].R) for r in recs]).reshape(len(recs), 4)
+    m.site_quat = np.array([r[2].quat for r in recs]).reshape(len(recs), 4)
     # actuators
     acts = spec.actuators
     m.nu = np.int32(len(acts))
@@ -533,7 +539,7 @@ def compile_model(spec, body_pos_overrides=None, keep_geoms=(), keep_sites=None,
         wb.append(fid[anchor[b2]])
         t2 = T[b2] if anchor[b2] != b2 else Transform()
         wp.append(t2.pos)
-        wq.append(mat2quat(t2.R))
+        wq.append(t2.quat)
         # metaworld's reset_mocap_welds() overwrites eq_data with the identity relative pose
         wr.append(_floats(e.get("relpose", "0 0 0 1 0 0 0"), 7))
         wsr.append(_floats(e["solref"], 2))
