@@ -34,6 +34,20 @@ class TabletopModel(C.Structure):
                 ("initial_state", C.c_double * 6), ("goal_table", (C.c_double * 6) * 256)]
 
 
+class MjConfig(C.Structure):
+    """earl_mj_config (include/earl_mj_b200.h)"""
+    _fields_ = [("env_kind", C.c_int32), ("num_envs", C.c_int32), ("device", C.c_int32), ("flags", C.c_uint32),
+                ("episode_horizon", C.c_int64)]
+
+
+class MjTask(C.Structure):
+    """earl_mj_task (include/earl_mj_b200.h)"""
+    _fields_ = [("frame_skip", C.c_int32), ("hand_site", C.c_int32), ("ree_site", C.c_int32), ("lee_site", C.c_int32),
+                ("obj_geom", C.c_int32), ("obj_site", C.c_int32), ("max_newton", C.c_int32), ("reserved", C.c_int32),
+                ("mocap_low", C.c_float * 3), ("mocap_high", C.c_float * 3), ("action_scale", C.c_float),
+                ("success_radius", C.c_float)]
+
+
 # (name, restype, argtypes) for EVERY symbol the header declares; tests/test_abi.py checks the list
 # against the header text and the built library.
 _VP, _I32, _I64, _U32, _SZ = C.c_void_p, C.c_int32, C.c_int64, C.c_uint32, C.c_size_t
@@ -68,6 +82,25 @@ SIGNATURES = [
     ("earl_rng_tabletop_goal_rows", None, [_VP, _VP, _U32, _I64, _VP]),
     ("earl_rng_np_randint", None, [_VP, _U32, _I64, _VP]),
     ("earl_rng_np_uniform", None, [_VP, C.c_double, C.c_double, _I64, _VP]),
+    # include/earl_mj_b200.h
+    ("earl_mj_create", C.c_int, [C.POINTER(MjConfig), C.c_char_p, _SZ, C.POINTER(MjTask), C.POINTER(_VP)]),
+    ("earl_mj_destroy", C.c_int, [_VP]),
+    ("earl_mj_obs_dim", C.c_int, [_VP]),
+    ("earl_mj_action_dim", C.c_int, [_VP]),
+    ("earl_mj_nq", C.c_int, [_VP]),
+    ("earl_mj_nv", C.c_int, [_VP]),
+    ("earl_mj_set_goal_table", C.c_int, [_VP, _VP, _I32]),
+    ("earl_mj_build_reset_template", C.c_int, [_VP, _VP, _VP, _I32]),
+    ("earl_mj_reset", C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP]),
+    ("earl_mj_step", C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP, _VP]),
+    ("earl_mj_step_host", C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP]),
+    ("earl_mj_get_obs", C.c_int, [_VP, _VP, _VP]),
+    ("earl_mj_get_state", C.c_int, [_VP, _VP, _VP, _VP, _VP]),
+    ("earl_mj_set_state", C.c_int, [_VP, _VP, _VP, _VP, _VP]),
+    ("earl_mj_counters", C.c_int, [_VP, C.POINTER(_I64), _VP, _VP, _VP]),
+    ("earl_mj_eval_stats", C.c_int, [_VP, _VP, _VP]),
+    ("earl_mj_work_counters", C.c_int, [_VP, _VP]),
+    ("earl_mj_launch_count", _I64, [_VP]),
 ]
 
 _lib = None

@@ -2,7 +2,9 @@
 
     python -m earl_benchmark_b200.build [--force] [--verbose]
 
-The .so is git-ignored but travels to the GPU box with the repo snapshot.
+Two translation units: the tabletop step (bit-exact fp64 arithmetic, so no FMA contraction) and the
+articulated-body engine of the Sawyer tasks (fp32, FMA on).  The .so is git-ignored but travels to the GPU box with
+the repo snapshot.
 """
 import os
 import subprocess
@@ -12,13 +14,15 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 INCLUDE = os.path.join(os.path.dirname(PKG), "include")
 LIB = os.path.join(PKG, "libearl_b200.so")
-SOURCES = [os.path.join(CSRC, "earl_b200.cu")]
-DEPS = SOURCES + [os.path.join(CSRC, f) for f in ("tabletop_kernels.cuh", "mt19937.hpp")] + [
-    os.path.join(INCLUDE, "earl_b200.h")]
+OBJDIR = os.path.join(PKG, "build")
+# (source, extra flags)
+UNITS = [("earl_b200.cu", ["--fmad=false"]), ("earl_mj.cu", [])]
+SOURCES = [os.path.join(CSRC, u[0]) for u in UNITS]
+DEPS = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(INCLUDE, f) for f in os.listdir(INCLUDE)]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-    "-Xcompiler", "-fPIC,-O2,-fvisibility=hidden", "-shared", "--fmad=false",
+    "-Xcompiler", "-fPIC,-O2,-fvisibility=hidden",
 ]
 
 
@@ -33,7 +37,19 @@ def build(force=False, verbose=False):
     if not force and not stale():
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + SOURCES
+    os.makedirs(OBJDIR, exist_ok=True)
+    objs, procs = [], []
+    for src, extra in UNITS:
+        obj = os.path.join(OBJDIR, src.replace(".cu", ".o"))
+        cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, os.path.join(CSRC, src)]
+        if verbose:
+            print(" ".join(cmd))
+        procs.append((cmd, subprocess.Popen(cmd)))
+        objs.append(obj)
+    for cmd, p in procs:
+        if p.wait() != 0:
+            raise subprocess.CalledProcessError(p.returncode, cmd)
+    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB] + objs
     if verbose:
         print(" ".join(cmd))
     subprocess.check_call(cmd)

@@ -35,6 +35,18 @@ int fail(int code, const char* fmt, ...) {
       return fail(EARL_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
   } while (0)
 
+}  // namespace
+
+namespace earl {
+// shared with earl_mj.cu: sets the thread-local message behind earl_last_error() and returns `code`
+int set_error(int code, const char* msg) {
+  snprintf(g_err, sizeof(g_err), "%s", msg);
+  return code;
+}
+}  // namespace earl
+
+namespace {
+
 struct SnapshotHeader {
   uint32_t magic;  // 'ESNP'
   int32_t env_kind;

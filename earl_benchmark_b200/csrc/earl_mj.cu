@@ -1,0 +1,544 @@
+// earl_mj.cu -- C-ABI implementation (include/earl_mj_b200.h) of the batched Sawyer-task step: one warp per
+// environment instance, all frame_skip substeps of an env step inside ONE launch so the 256-byte state record makes
+// one HBM round trip per env step.  Device code: mj_engine.cuh / mj_collide.cuh / mj_step.cuh.  No CPU fallback.
+#include "../../include/earl_mj_b200.h"
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "mj_model_host.hpp"
+#include "mj_step.cuh"
+
+namespace earl {
+int set_error(int code, const char* msg);  // earl_b200.cu: thread-local message behind earl_last_error()
+}
+
+namespace {
+
+int failf(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  return earl::set_error(code, buf);
+}
+
+#define CU(call)                                                                                                 \
+  do {                                                                                                           \
+    cudaError_t e_ = (call);                                                                                     \
+    if (e_ != cudaSuccess)                                                                                       \
+      return failf(EARL_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__);    \
+  } while (0)
+
+using namespace earl::mj;
+
+constexpr int kWPB = 8;  // warps (= environments in flight) per block
+constexpr int kObs = 14, kAct = 4, kGoal = 7, kMaxGoals = 32;
+constexpr size_t kModelBytes = (sizeof(Model) + 15) & ~size_t(15);
+constexpr size_t kSmemBytes = kModelBytes + kWPB * ((sizeof(Work) + 15) & ~size_t(15));
+constexpr size_t kWorkStride = (sizeof(Work) + 15) & ~size_t(15);
+
+struct StepArgs {
+  const Model* model;
+  const float* hull;
+  float* state;              // [N][REC_FLOATS]
+  const float* goals;        // [kMaxGoals][8]
+  long long* interventions;  // [N]
+  double* ep_return;         // [N] or null
+  unsigned long long* work;  // 6 counters
+  int n;
+  unsigned horizon;
+  unsigned flags;
+  // step
+  const float* actions;
+  float* obs;
+  float* reward;
+  uint8_t* done;
+  uint8_t* success;
+  // reset
+  const float* tmpl;         // [REC_FLOATS]
+  const uint8_t* mask;
+  const double* obj_qpos;
+  const int* goal_idx;
+  int obj_qadr, obj_dadr;
+  // settle
+  double hand_init[3];
+  float ctrl[2];
+  int steps;
+};
+
+__device__ __forceinline__ void load_model(Model* sm, const Model* gm) {
+  const uint32_t* src = reinterpret_cast<const uint32_t*>(gm);
+  uint32_t* dst = reinterpret_cast<uint32_t*>(sm);
+  for (unsigned i = threadIdx.x; i < sizeof(Model) / 4; i += blockDim.x) dst[i] = src[i];
+  __syncthreads();
+}
+
+__device__ __forceinline__ void scatter_rec(Work& w, int idx, float v) {
+  if (idx < REC_QVEL) w.qpos[idx] = v;
+  else if (idx < REC_WARM) w.qvel[idx - REC_QVEL] = v;
+  else if (idx < REC_MOCAP) w.warm[idx - REC_WARM] = v;
+  else if (idx < REC_STEPS) reinterpret_cast<float*>(w.mocap_pos)[idx - REC_MOCAP] = v;
+  else if (idx == REC_STEPS) w.steps = __float_as_uint(v);
+  else if (idx == REC_FLAGS) w.flags = __float_as_uint(v);
+  else if (idx == REC_GOALROW) w.goalrow = __float_as_uint(v);
+}
+__device__ __forceinline__ float gather_rec(const Work& w, int idx) {
+  if (idx < REC_QVEL) return w.qpos[idx];
+  if (idx < REC_WARM) return w.qvel[idx - REC_QVEL];
+  if (idx < REC_MOCAP) return w.warm[idx - REC_WARM];
+  if (idx < REC_STEPS) return reinterpret_cast<const float*>(w.mocap_pos)[idx - REC_MOCAP];
+  if (idx == REC_STEPS) return __uint_as_float(w.steps);
+  if (idx == REC_FLAGS) return __uint_as_float(w.flags);
+  if (idx == REC_GOALROW) return __uint_as_float(w.goalrow);
+  return 0.0f;
+}
+__device__ __forceinline__ void load_env(Work& w, const float* rec, int lane) {
+  scatter_rec(w, lane, rec[lane]);
+  scatter_rec(w, lane + 32, rec[lane + 32]);
+  if (lane == 0) { w.bad = 0; w.acc_iter = w.acc_rows = w.acc_con = 0; }
+  __syncwarp();
+}
+__device__ __forceinline__ void store_env(const Work& w, float* rec, int lane) {
+  __syncwarp();
+  rec[lane] = gather_rec(w, lane);
+  rec[lane + 32] = gather_rec(w, lane + 32);
+}
+
+// observation row [hand(3), gripper(1), object(3), goal(7)] + sparse success (sawyer_door.py:86-94,168-177)
+__device__ __forceinline__ bool write_obs(const Model& m, Work& w, const float* goals, float* obs_row, int lane) {
+  if (lane == 0) observe(m, w, w.obs7);
+  __syncwarp();
+  const float* g = goals + 8 * w.goalrow;
+  if (obs_row && lane < kObs) obs_row[lane] = lane < 7 ? w.obs7[lane] : g[lane - 7];
+  const float dx = w.obs7[4] - g[4], dy = w.obs7[5] - g[5], dz = w.obs7[6] - g[6];
+  return sqrtf(dx * dx + dy * dy + dz * dz) <= m.success_radius;
+}
+
+__global__ void __launch_bounds__(kWPB * 32) mj_step_kernel(const StepArgs a) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  Model* sm = reinterpret_cast<Model*>(smem);
+  load_model(sm, a.model);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  Work& w = *reinterpret_cast<Work*>(smem + kModelBytes + warp * kWorkStride);
+  unsigned long long it = 0, rows = 0, cons = 0, bad = 0, envs = 0;
+  for (int env = blockIdx.x * kWPB + warp; env < a.n; env += gridDim.x * kWPB) {
+    float* rec = a.state + (size_t)env * REC_FLOATS;
+    load_env(w, rec, lane);
+    if (lane < kAct) w.action[lane] = a.actions[(size_t)env * kAct + lane];
+    __syncwarp();
+    env_step<32>(*sm, a.hull, w, w.action, lane);
+    const bool ok = write_obs(*sm, w, a.goals, a.obs + (size_t)env * kObs, lane);
+    if (lane == 0) {
+      // PersistentStateWrapper.step: counters, horizon `done` (persistent_state_wrapper.py:22-31)
+      const unsigned steps = w.steps == 0xffffffffu ? w.steps : w.steps + 1;
+      w.steps = steps;
+      w.flags = (w.flags & ~2u) | (ok ? 3u : 0u) | (w.bad ? 4u : 0u);
+      const float r = ok ? 1.0f : 0.0f;
+      a.reward[env] = r;
+      a.done[env] = steps >= a.horizon ? 1 : 0;
+      if (a.success) a.success[env] = ok ? 1 : 0;
+      if (a.ep_return) a.ep_return[env] += (double)r;
+      it += w.acc_iter; rows += w.acc_rows; cons += w.acc_con; bad += w.bad ? 1 : 0; envs += 1;
+    }
+    store_env(w, rec, lane);
+    __syncwarp();
+  }
+  if (lane == 0 && envs) {
+    atomicAdd(&a.work[0], envs);
+    atomicAdd(&a.work[1], envs * (unsigned long long)sm->frame_skip);
+    atomicAdd(&a.work[2], it);
+    atomicAdd(&a.work[3], rows);
+    atomicAdd(&a.work[4], cons);
+    atomicAdd(&a.work[5], bad);
+  }
+}
+
+// reset (mode 0) / get_obs (mode 1): fresh kinematics of the (new) state, observation out
+__global__ void __launch_bounds__(kWPB * 32) mj_reset_kernel(const StepArgs a, const int mode) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  Model* sm = reinterpret_cast<Model*>(smem);
+  load_model(sm, a.model);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  Work& w = *reinterpret_cast<Work*>(smem + kModelBytes + warp * kWorkStride);
+  for (int env = blockIdx.x * kWPB + warp; env < a.n; env += gridDim.x * kWPB) {
+    if (mode == 0 && a.mask && !a.mask[env]) continue;
+    float* rec = a.state + (size_t)env * REC_FLOATS;
+    load_env(w, mode == 0 ? a.tmpl : rec, lane);
+    if (mode == 0 && lane == 0) {
+      if (a.obj_qpos) { w.qpos[a.obj_qadr] = (float)a.obj_qpos[env]; w.qvel[a.obj_dadr] = 0.0f; }  // _set_obj_xyz
+      w.goalrow = a.goal_idx ? (unsigned)a.goal_idx[env] : 0u;
+      w.steps = 0;
+      w.flags = 0;
+      a.interventions[env] += 1;  // PersistentStateWrapper.reset (persistent_state_wrapper.py:17-20)
+      if (a.ep_return) a.ep_return[env] = 0.0;
+    }
+    __syncwarp();
+    kinematics<32>(*sm, w, lane);
+    write_obs(*sm, w, a.goals, a.obs ? a.obs + (size_t)env * kObs : nullptr, lane);
+    if (mode == 0) store_env(w, rec, lane);
+    __syncwarp();
+  }
+}
+
+// sim.reset() + _reset_hand(steps) for ONE environment -> reset template record
+__global__ void __launch_bounds__(32) mj_settle_kernel(const StepArgs a, float* tmpl_out) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  Model* sm = reinterpret_cast<Model*>(smem);
+  load_model(sm, a.model);
+  const int lane = threadIdx.x & 31;
+  Work& w = *reinterpret_cast<Work*>(smem + kModelBytes);
+  if (lane == 0) {
+    for (int k = 0; k < MAXQ; ++k) w.qpos[k] = k < sm->nq ? sm->qpos0[k] : 0.0f;
+    for (int k = 0; k < MAXV; ++k) { w.qvel[k] = 0; w.warm[k] = 0; }
+    w.steps = 0; w.flags = 0; w.goalrow = 0; w.bad = 0; w.acc_iter = w.acc_rows = w.acc_con = 0;
+  }
+  __syncwarp();
+  for (int s = 0; s < a.steps; ++s) {
+    if (lane == 0) {
+      for (int k = 0; k < 3; ++k) w.mocap_pos[k] = a.hand_init[k];
+      w.mocap_quat[0] = 1; w.mocap_quat[1] = 0; w.mocap_quat[2] = 1; w.mocap_quat[3] = 0;
+      w.ctrl[0] = a.ctrl[0]; w.ctrl[1] = a.ctrl[1];
+    }
+    __syncwarp();
+    for (int k = 0; k < sm->frame_skip; ++k) substep<32>(*sm, a.hull, w, lane);
+  }
+  store_env(w, tmpl_out, lane);
+}
+
+__global__ void mj_eval_stats_kernel(const float* state, const double* ep_return, int n, double* out4) {
+  double ret = 0, last = 0, any = 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const unsigned fl = __float_as_uint(state[(size_t)i * REC_FLOATS + REC_FLAGS]);
+    ret += ep_return[i];
+    last += (fl & 2u) ? 1.0 : 0.0;
+    any += (fl & 1u) ? 1.0 : 0.0;
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    ret += __shfl_xor_sync(0xffffffffu, ret, o);
+    last += __shfl_xor_sync(0xffffffffu, last, o);
+    any += __shfl_xor_sync(0xffffffffu, any, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(&out4[0], ret);
+    atomicAdd(&out4[1], last);
+    atomicAdd(&out4[2], any);
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&out4[3], (double)n);
+}
+
+}  // namespace
+
+struct earl_mj_handle {
+  earl_mj_config cfg{};
+  HostModel hm;
+  int device = 0, sm_count = 0, grid = 0;
+  int obj_qadr = -1, obj_dadr = -1;
+  bool have_template = false;
+  int64_t total_steps = 0, launches = 0;
+  std::vector<void*> owned;
+  StepArgs a{};
+  float* d_tmpl = nullptr;
+  float* d_goals = nullptr;
+  // host-path staging
+  float* d_act = nullptr;
+  float* d_obs = nullptr;
+  float* d_rew = nullptr;
+  uint8_t* d_done = nullptr;
+  uint8_t* d_succ = nullptr;
+  cudaStream_t host_stream = nullptr;
+
+  template <typename T>
+  int alloc(T** ptr, size_t count) {
+    void* q = nullptr;
+    cudaError_t e = cudaMalloc(&q, count * sizeof(T) + 16);
+    if (e != cudaSuccess) return failf(EARL_ERR_NOMEM, "cudaMalloc(%zu B) failed: %s", count * sizeof(T), cudaGetErrorString(e));
+    e = cudaMemset(q, 0, count * sizeof(T));
+    if (e != cudaSuccess) return failf(EARL_ERR_CUDA, "cudaMemset failed: %s", cudaGetErrorString(e));
+    owned.push_back(q);
+    *ptr = static_cast<T*>(q);
+    return 0;
+  }
+};
+
+namespace {
+int check_handle(const earl_mj_handle* h) {
+  if (!h) return failf(EARL_ERR_INVALID, "null handle");
+  cudaError_t e = cudaSetDevice(h->device);
+  if (e != cudaSuccess) return failf(EARL_ERR_CUDA, "cudaSetDevice(%d) failed: %s", h->device, cudaGetErrorString(e));
+  return 0;
+}
+int grid_for(const earl_mj_handle* h, int n) {
+  const int blocks = (n + kWPB - 1) / kWPB;
+  return blocks < h->grid ? blocks : h->grid;
+}
+}  // namespace
+
+extern "C" {
+
+int earl_mj_create(const earl_mj_config* cfg, const void* model_blob, size_t model_nbytes, const earl_mj_task* task,
+                   earl_mj_handle** out) {
+  if (!cfg || !out || !task || !model_blob) return failf(EARL_ERR_INVALID, "null argument");
+  *out = nullptr;
+  if (cfg->env_kind != EARL_ENV_SAWYER_DOOR)
+    return failf(EARL_ERR_UNSUPPORTED, "env_kind %d is not built yet on the articulated-body engine (only sawyer_door)", cfg->env_kind);
+  if (cfg->num_envs < 1) return failf(EARL_ERR_INVALID, "num_envs must be >= 1");
+  if (cfg->episode_horizon < 1) return failf(EARL_ERR_INVALID, "episode_horizon must be >= 1");
+  if (cfg->flags & ~(uint32_t)(EARL_FLAG_EVAL_STATS)) return failf(EARL_ERR_UNSUPPORTED, "unsupported flags %#x", cfg->flags);
+  static_assert(sizeof(earl_mj_task) == sizeof(TaskSpec), "earl_mj_task must mirror earl::mj::TaskSpec");
+  int ndev = 0;
+  CU(cudaGetDeviceCount(&ndev));
+  if (cfg->device < 0 || cfg->device >= ndev) return failf(EARL_ERR_INVALID, "device %d out of range (%d visible)", cfg->device, ndev);
+  CU(cudaSetDevice(cfg->device));
+  earl_mj_handle* h = new (std::nothrow) earl_mj_handle();
+  if (!h) return failf(EARL_ERR_NOMEM, "host allocation failed");
+  h->cfg = *cfg;
+  h->device = cfg->device;
+  TaskSpec ts;
+  memcpy(&ts, task, sizeof(ts));
+  std::string err;
+  if (!build_model(model_blob, model_nbytes, ts, &h->hm, &err)) {
+    delete h;
+    return failf(EARL_ERR_INVALID, "%s", err.c_str());
+  }
+  const Model& m = h->hm.m;
+  // the observed object: the joint of the body that carries it (door hinge)
+  {
+    const int b = ts.obj_geom >= 0 ? m.geom_body[ts.obj_geom] : m.site_body[ts.obj_site];
+    if (b <= 0) { delete h; return failf(EARL_ERR_INVALID, "observed object is attached to the world"); }
+    const int j = m.body_jnt[b];
+    h->obj_qadr = m.jnt_qposadr[j];
+    h->obj_dadr = m.jnt_dofadr[j];
+  }
+  cudaDeviceProp prop;
+  cudaError_t e = cudaGetDeviceProperties(&prop, cfg->device);
+  if (e != cudaSuccess) { delete h; return failf(EARL_ERR_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e)); }
+  h->sm_count = prop.multiProcessorCount;
+  const size_t n = (size_t)cfg->num_envs;
+  StepArgs& a = h->a;
+  Model* d_model = nullptr;
+  float* d_hull = nullptr;
+  int rc = h->alloc(&d_model, 1);
+  if (!rc) rc = h->alloc(&d_hull, h->hm.hull_vert.size() + 4);
+  if (!rc) rc = h->alloc(&a.state, n * REC_FLOATS);
+  if (!rc) rc = h->alloc(&h->d_goals, kMaxGoals * 8);
+  if (!rc) rc = h->alloc(&a.interventions, n);
+  if (!rc && (cfg->flags & EARL_FLAG_EVAL_STATS)) rc = h->alloc(&a.ep_return, n);
+  if (!rc) rc = h->alloc(&a.work, 8);
+  if (!rc) rc = h->alloc(&h->d_tmpl, REC_FLOATS);
+  if (rc) { earl_mj_destroy(h); return rc; }
+  e = cudaMemcpy(d_model, &m, sizeof(Model), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess && !h->hm.hull_vert.empty())
+    e = cudaMemcpy(d_hull, h->hm.hull_vert.data(), h->hm.hull_vert.size() * sizeof(float), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(mj_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(mj_reset_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(mj_settle_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+  int per_sm = 0;
+  if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mj_step_kernel, kWPB * 32, kSmemBytes);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->host_stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) { earl_mj_destroy(h); return failf(EARL_ERR_CUDA, "engine setup: %s", cudaGetErrorString(e)); }
+  if (per_sm < 1) { earl_mj_destroy(h); return failf(EARL_ERR_CUDA, "step kernel does not fit on an SM (%zu B shared memory)", kSmemBytes); }
+  h->grid = h->sm_count * per_sm;
+  a.model = d_model;
+  a.hull = d_hull;
+  a.goals = h->d_goals;
+  a.n = cfg->num_envs;
+  a.horizon = cfg->episode_horizon > 0xffffffffLL ? 0xffffffffu : (unsigned)cfg->episode_horizon;
+  a.flags = cfg->flags;
+  a.obj_qadr = h->obj_qadr;
+  a.obj_dadr = h->obj_dadr;
+  *out = h;
+  return 0;
+}
+
+int earl_mj_destroy(earl_mj_handle* h) {
+  if (!h) return 0;
+  cudaSetDevice(h->device);
+  for (void* q : h->owned) cudaFree(q);
+  if (h->host_stream) cudaStreamDestroy(h->host_stream);
+  delete h;
+  return 0;
+}
+
+int earl_mj_obs_dim(const earl_mj_handle* h) { return h ? kObs : 0; }
+int earl_mj_action_dim(const earl_mj_handle* h) { return h ? kAct : 0; }
+int earl_mj_nq(const earl_mj_handle* h) { return h ? h->hm.m.nq : 0; }
+int earl_mj_nv(const earl_mj_handle* h) { return h ? h->hm.m.nv : 0; }
+int64_t earl_mj_launch_count(const earl_mj_handle* h) { return h ? h->launches : 0; }
+
+int earl_mj_set_goal_table(earl_mj_handle* h, const double* rows_host, int32_t count) {
+  if (int rc = check_handle(h)) return rc;
+  if (!rows_host || count < 1 || count > kMaxGoals) return failf(EARL_ERR_INVALID, "goal table must have 1..%d rows", kMaxGoals);
+  std::vector<float> g(kMaxGoals * 8, 0.f);
+  for (int r = 0; r < count; ++r)
+    for (int c = 0; c < kGoal; ++c) g[r * 8 + c] = (float)rows_host[r * kGoal + c];
+  CU(cudaDeviceSynchronize());
+  CU(cudaMemcpy(h->d_goals, g.data(), g.size() * sizeof(float), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+int earl_mj_build_reset_template(earl_mj_handle* h, const double* hand_init_pos_host, const float* ctrl_host, int32_t steps) {
+  if (int rc = check_handle(h)) return rc;
+  if (!hand_init_pos_host || !ctrl_host || steps < 0) return failf(EARL_ERR_INVALID, "bad reset-template arguments");
+  StepArgs a = h->a;
+  for (int k = 0; k < 3; ++k) a.hand_init[k] = hand_init_pos_host[k];
+  a.ctrl[0] = ctrl_host[0];
+  a.ctrl[1] = ctrl_host[1];
+  a.steps = steps;
+  mj_settle_kernel<<<1, 32, kSmemBytes>>>(a, h->d_tmpl);
+  CU(cudaGetLastError());
+  CU(cudaDeviceSynchronize());
+  h->launches += 1;
+  h->have_template = true;
+  return 0;
+}
+
+int earl_mj_reset(earl_mj_handle* h, const uint8_t* mask_dev, const double* obj_qpos_dev, const int32_t* goal_idx_dev,
+                  float* obs_out_dev, void* stream) {
+  if (int rc = check_handle(h)) return rc;
+  if (!h->have_template) return failf(EARL_ERR_INVALID, "earl_mj_build_reset_template must run before the first reset");
+  StepArgs a = h->a;
+  a.tmpl = h->d_tmpl;
+  a.mask = mask_dev;
+  a.obj_qpos = obj_qpos_dev;
+  a.goal_idx = goal_idx_dev;
+  a.obs = obs_out_dev;
+  mj_reset_kernel<<<grid_for(h, a.n), kWPB * 32, kSmemBytes, static_cast<cudaStream_t>(stream)>>>(a, 0);
+  CU(cudaGetLastError());
+  h->launches += 1;
+  return 0;
+}
+
+int earl_mj_get_obs(earl_mj_handle* h, float* obs_dev, void* stream) {
+  if (int rc = check_handle(h)) return rc;
+  if (!obs_dev) return failf(EARL_ERR_INVALID, "null obs");
+  StepArgs a = h->a;
+  a.obs = obs_dev;
+  mj_reset_kernel<<<grid_for(h, a.n), kWPB * 32, kSmemBytes, static_cast<cudaStream_t>(stream)>>>(a, 1);
+  CU(cudaGetLastError());
+  h->launches += 1;
+  return 0;
+}
+
+int earl_mj_step(earl_mj_handle* h, const float* actions_dev, float* obs_dev, float* reward_dev, uint8_t* done_dev,
+                 uint8_t* success_dev, void* stream) {
+  if (int rc = check_handle(h)) return rc;
+  if (!actions_dev || !obs_dev || !reward_dev || !done_dev) return failf(EARL_ERR_INVALID, "actions, obs, reward and done must be non-null");
+  StepArgs a = h->a;
+  a.actions = actions_dev;
+  a.obs = obs_dev;
+  a.reward = reward_dev;
+  a.done = done_dev;
+  a.success = success_dev;
+  mj_step_kernel<<<grid_for(h, a.n), kWPB * 32, kSmemBytes, static_cast<cudaStream_t>(stream)>>>(a);
+  CU(cudaGetLastError());
+  h->launches += 1;
+  h->total_steps += 1;
+  return 0;
+}
+
+int earl_mj_step_host(earl_mj_handle* h, const float* actions_host, float* obs_host, float* reward_host, uint8_t* done_host,
+                      uint8_t* success_host) {
+  if (int rc = check_handle(h)) return rc;
+  if (!actions_host || !obs_host || !reward_host || !done_host) return failf(EARL_ERR_INVALID, "null host buffer");
+  const size_t n = (size_t)h->a.n;
+  if (!h->d_act) {
+    int rc = h->alloc(&h->d_act, n * kAct);
+    if (!rc) rc = h->alloc(&h->d_obs, n * kObs);
+    if (!rc) rc = h->alloc(&h->d_rew, n);
+    if (!rc) rc = h->alloc(&h->d_done, n);
+    if (!rc) rc = h->alloc(&h->d_succ, n);
+    if (rc) return rc;
+  }
+  cudaStream_t s = h->host_stream;
+  CU(cudaMemcpyAsync(h->d_act, actions_host, n * kAct * sizeof(float), cudaMemcpyHostToDevice, s));
+  if (int rc = earl_mj_step(h, h->d_act, h->d_obs, h->d_rew, h->d_done, success_host ? h->d_succ : nullptr, s)) return rc;
+  CU(cudaMemcpyAsync(obs_host, h->d_obs, n * kObs * sizeof(float), cudaMemcpyDeviceToHost, s));
+  CU(cudaMemcpyAsync(reward_host, h->d_rew, n * sizeof(float), cudaMemcpyDeviceToHost, s));
+  CU(cudaMemcpyAsync(done_host, h->d_done, n, cudaMemcpyDeviceToHost, s));
+  if (success_host) CU(cudaMemcpyAsync(success_host, h->d_succ, n, cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  return 0;
+}
+
+int earl_mj_get_state(earl_mj_handle* h, double* qpos_host, double* qvel_host, double* warm_host, double* mocap_host) {
+  if (int rc = check_handle(h)) return rc;
+  const size_t n = (size_t)h->a.n;
+  const int nq = h->hm.m.nq, nv = h->hm.m.nv;
+  std::vector<float> rec(n * REC_FLOATS);
+  CU(cudaDeviceSynchronize());
+  CU(cudaMemcpy(rec.data(), h->a.state, rec.size() * sizeof(float), cudaMemcpyDeviceToHost));
+  for (size_t i = 0; i < n; ++i) {
+    const float* r = &rec[i * REC_FLOATS];
+    if (qpos_host) for (int k = 0; k < nq; ++k) qpos_host[i * nq + k] = r[REC_QPOS + k];
+    if (qvel_host) for (int k = 0; k < nv; ++k) qvel_host[i * nv + k] = r[REC_QVEL + k];
+    if (warm_host) for (int k = 0; k < nv; ++k) warm_host[i * nv + k] = r[REC_WARM + k];
+    if (mocap_host) memcpy(&mocap_host[i * 3], &r[REC_MOCAP], 3 * sizeof(double));
+  }
+  return 0;
+}
+
+int earl_mj_set_state(earl_mj_handle* h, const double* qpos_host, const double* qvel_host, const double* warm_host,
+                      const double* mocap_host) {
+  if (int rc = check_handle(h)) return rc;
+  const size_t n = (size_t)h->a.n;
+  const int nq = h->hm.m.nq, nv = h->hm.m.nv;
+  std::vector<float> rec(n * REC_FLOATS);
+  CU(cudaDeviceSynchronize());
+  CU(cudaMemcpy(rec.data(), h->a.state, rec.size() * sizeof(float), cudaMemcpyDeviceToHost));
+  for (size_t i = 0; i < n; ++i) {
+    float* r = &rec[i * REC_FLOATS];
+    if (qpos_host) for (int k = 0; k < nq; ++k) r[REC_QPOS + k] = (float)qpos_host[i * nq + k];
+    if (qvel_host) for (int k = 0; k < nv; ++k) r[REC_QVEL + k] = (float)qvel_host[i * nv + k];
+    if (warm_host) for (int k = 0; k < nv; ++k) r[REC_WARM + k] = (float)warm_host[i * nv + k];
+    if (mocap_host) memcpy(&r[REC_MOCAP], &mocap_host[i * 3], 3 * sizeof(double));
+  }
+  CU(cudaMemcpy(h->a.state, rec.data(), rec.size() * sizeof(float), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+int earl_mj_counters(earl_mj_handle* h, int64_t* total_steps_host, int64_t* num_interventions_dev, uint32_t* steps_since_reset_dev,
+                     void* stream) {
+  if (int rc = check_handle(h)) return rc;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const size_t n = (size_t)h->a.n;
+  if (total_steps_host) *total_steps_host = h->total_steps;
+  if (num_interventions_dev)
+    CU(cudaMemcpyAsync(num_interventions_dev, h->a.interventions, n * sizeof(int64_t), cudaMemcpyDeviceToDevice, s));
+  if (steps_since_reset_dev)
+    CU(cudaMemcpy2DAsync(steps_since_reset_dev, sizeof(uint32_t), h->a.state + REC_STEPS, REC_FLOATS * sizeof(float),
+                         sizeof(uint32_t), n, cudaMemcpyDeviceToDevice, s));
+  return 0;
+}
+
+int earl_mj_eval_stats(earl_mj_handle* h, double* out4_dev, void* stream) {
+  if (int rc = check_handle(h)) return rc;
+  if (!out4_dev) return failf(EARL_ERR_INVALID, "null out4");
+  if (!h->a.ep_return) return failf(EARL_ERR_INVALID, "eval stats need EARL_FLAG_EVAL_STATS");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  CU(cudaMemsetAsync(out4_dev, 0, 4 * sizeof(double), s));
+  int grid = (h->a.n + 255) / 256;
+  if (grid > h->sm_count * 4) grid = h->sm_count * 4;
+  mj_eval_stats_kernel<<<grid, 256, 0, s>>>(h->a.state, h->a.ep_return, h->a.n, out4_dev);
+  CU(cudaGetLastError());
+  h->launches += 1;
+  return 0;
+}
+
+int earl_mj_work_counters(earl_mj_handle* h, uint64_t* out6_host) {
+  if (int rc = check_handle(h)) return rc;
+  if (!out6_host) return failf(EARL_ERR_INVALID, "null out");
+  CU(cudaDeviceSynchronize());
+  CU(cudaMemcpy(out6_host, h->a.work, 6 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,243 @@
+// mj_model_host.hpp -- host side of the articulated-body engine: reads the serialized structure-of-arrays model
+// (earl_benchmark_b200/mjcf/compile.py: Model.to_blob, fields in Model.FIELDS order) and fills the fixed-size
+// fp32 `earl::mj::Model` the kernels read.  Plain C++, no CUDA.
+#pragma once
+
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "mj_engine.cuh"
+
+namespace earl {
+namespace mj {
+
+// task constants that are not part of the MJCF (metaworld SawyerXYZEnv / EARL env classes)
+struct TaskSpec {
+  int32_t frame_skip;      // SawyerXYZEnv frame_skip = 5
+  int32_t hand_site;       // site 'body:hand'   (get_endeff_pos = body 'hand' xpos)
+  int32_t ree_site;        // site 'rightEndEffector'
+  int32_t lee_site;        // site 'leftEndEffector'
+  int32_t obj_geom;        // door: geom 'handle' (sawyer_door._get_pos_objects); -1 if the object is a site
+  int32_t obj_site;        // peg: site 'pegHead' (sawyer_peg.py:186-187); -1 otherwise
+  int32_t max_newton;      // device cap on Newton iterations per substep
+  int32_t reserved;
+  float mocap_low[3];      // hand_low  (sawyer_peg.py:66 / metaworld SawyerDoorEnvV2)
+  float mocap_high[3];     // hand_high
+  float action_scale;      // 1/100
+  float success_radius;    // 0.02 door (sawyer_door.py:177), 0.05 peg (sawyer_peg.py:305)
+};
+
+class BlobReader {
+ public:
+  BlobReader(const void* blob, size_t nbytes) : p_(static_cast<const uint8_t*>(blob)), end_(p_ + nbytes) {}
+  bool header() {
+    if (end_ - p_ < 8) return false;
+    int32_t h[2];
+    memcpy(h, p_, 8);
+    p_ += 8;
+    return h[0] == 0x4C444D45 && h[1] == 1;
+  }
+  // next field as doubles / ints; returns element count or -1
+  template <typename T>
+  long field(std::vector<T>* out, int elem) {
+    if (end_ - p_ < 4) return -1;
+    int32_t ndim;
+    memcpy(&ndim, p_, 4);
+    if (ndim < 0 || ndim > 4 || end_ - p_ < 4 * (1 + ndim)) return -1;
+    long n = 1;
+    for (int i = 0; i < ndim; ++i) {
+      int32_t d;
+      memcpy(&d, p_ + 4 * (1 + i), 4);
+      n *= d;
+    }
+    size_t hb = 4 * (size_t)(1 + ndim);
+    if (hb % 8) hb += 4;
+    p_ += hb;
+    size_t db = (size_t)n * elem;
+    size_t padded = db % 8 ? db + 8 - db % 8 : db;
+    if ((size_t)(end_ - p_) < padded) return -1;
+    out->resize((size_t)n);
+    if (n) memcpy(out->data(), p_, db);
+    p_ += padded;
+    return n;
+  }
+  bool done() const { return p_ == end_; }
+
+ private:
+  const uint8_t* p_;
+  const uint8_t* end_;
+};
+
+// hull vertices of mesh geoms are kept separately (too large for the fixed-size struct)
+struct HostModel {
+  Model m;
+  std::vector<float> hull_vert;  // [nhull][3]
+};
+
+inline bool build_model(const void* blob, size_t nbytes, const TaskSpec& task, HostModel* out, std::string* err) {
+  BlobReader rd(blob, nbytes);
+  auto bad = [&](const char* what) { if (err) *err = what; return false; };
+  if (!rd.header()) return bad("model blob: bad magic / version");
+  std::vector<int32_t> I;
+  std::vector<double> D;
+  Model& m = out->m;
+  memset(&m, 0, sizeof(m));
+#define RI(dst) do { if (rd.field(&I, 4) != 1) return bad("model blob: scalar int field"); dst = I[0]; } while (0)
+#define RD(dst) do { if (rd.field(&D, 8) != 1) return bad("model blob: scalar double field"); dst = (real)D[0]; } while (0)
+  int nhullvert = 0, cone_elliptic = 0;
+  double tolerance = 0;
+  RI(m.nbody); RI(m.nq); RI(m.nv); RI(m.ngeom); RI(m.nsite); RI(m.nu); RI(m.nweld); RI(nhullvert); RI(m.iterations);
+  RI(cone_elliptic);
+  RD(m.timestep);
+  if (rd.field(&D, 8) != 1) return bad("tolerance");
+  tolerance = D[0];
+  (void)tolerance;
+  RD(m.impratio);
+  if (!cone_elliptic) return bad("model blob: only elliptic friction cones are built");
+  if (m.nbody > MAXB || m.nv > MAXV || m.nq > MAXQ || m.ngeom > MAXG || m.nsite > MAXS || m.nu > MAXU || m.nweld > MAXW)
+    return bad("model blob: model exceeds the engine's fixed sizes");
+  const int nb = m.nbody, nv = m.nv, ng = m.ngeom, ns = m.nsite, nu = m.nu, nw = m.nweld;
+#define VI(n, expr) do { if (rd.field(&I, 4) != (long)(n)) return bad("model blob: int array size"); for (long k = 0; k < (long)(n); ++k) { expr; } } while (0)
+#define VD(n, expr) do { if (rd.field(&D, 8) != (long)(n)) return bad("model blob: double array size"); for (long k = 0; k < (long)(n); ++k) { expr; } } while (0)
+  VD(3, m.gravity[k] = (real)D[k]);
+  VI(nb, m.body_parent[k] = I[k]);
+  VD(nb * 3, m.body_pos[k / 3][k % 3] = (real)D[k]);
+  VD(nb * 4, m.body_quat[k / 4][k % 4] = (real)D[k]);
+  VD(nb, m.body_mass[k] = (real)D[k]);
+  VD(nb * 3, m.body_ipos[k / 3][k % 3] = (real)D[k]);
+  VD(nb * 6, m.body_inertia[k / 6][k % 6] = (real)D[k]);
+  VI(nb, m.body_jnt[k] = I[k]);
+  // joints: count from the next field
+  long nj = rd.field(&I, 4);
+  if (nj < 0 || nj > MAXJ) return bad("model blob: joint count");
+  m.njnt = (int)nj;
+  for (long k = 0; k < nj; ++k) m.jnt_type[k] = I[k];
+  VI(nj, m.jnt_body[k] = I[k]);
+  VI(nj, m.jnt_qposadr[k] = I[k]);
+  VI(nj, m.jnt_dofadr[k] = I[k]);
+  VD(nj * 3, m.jnt_pos[k / 3][k % 3] = (real)D[k]);
+  VD(nj * 3, m.jnt_axis[k / 3][k % 3] = (real)D[k]);
+  VI(nj, m.jnt_limited[k] = I[k]);
+  VD(nj * 2, m.jnt_range[k / 2][k % 2] = (real)D[k]);
+  VD(nj, m.jnt_margin[k] = (real)D[k]);
+  VD(nj * 2, m.jnt_solref[k / 2][k % 2] = (real)D[k]);
+  VD(nj * 5, m.jnt_solimp[k / 5][k % 5] = (real)D[k]);
+  VD(nj, m.jnt_stiffness[k] = (real)D[k]);
+  VD(nj, m.jnt_springref[k] = (real)D[k]);
+  VI(nv, m.dof_body[k] = I[k]);
+  VD(nv, m.dof_damping[k] = (real)D[k]);
+  VD(nv, m.dof_armature[k] = (real)D[k]);
+  VD(nv, (void)D[k]);  // dof_frictionloss (zero in the Sawyer scenes; kitchen needs it)
+  for (int k = 0; k < nv; ++k) if (D[k] != 0.0) return bad("model blob: frictionloss is not built");
+  VD(nv, m.dof_invweight0[k] = (real)D[k]);
+  VD(m.nq, m.qpos0[k] = (real)D[k]);
+  VI(ng, m.geom_body[k] = I[k]);
+  VI(ng, m.geom_type[k] = I[k]);
+  VD(ng * 3, m.geom_size[k / 3][k % 3] = (real)D[k]);
+  VD(ng * 3, m.geom_pos[k / 3][k % 3] = (real)D[k]);
+  VD(ng * 4, m.geom_quat[k / 4][k % 4] = (real)D[k]);
+  std::vector<int32_t> contype(ng), conaff(ng);
+  VI(ng, contype[k] = I[k]);
+  VI(ng, conaff[k] = I[k]);
+  VI(ng, m.geom_condim[k] = I[k]);
+  VI(ng, m.geom_priority[k] = I[k]);
+  VD(ng * 3, m.geom_friction[k / 3][k % 3] = (real)D[k]);
+  VD(ng, m.geom_margin[k] = (real)D[k]);
+  VD(ng, m.geom_gap[k] = (real)D[k]);
+  VD(ng * 2, m.geom_solref[k / 2][k % 2] = (real)D[k]);
+  VD(ng * 5, m.geom_solimp[k / 5][k % 5] = (real)D[k]);
+  VD(ng, m.geom_solmix[k] = (real)D[k]);
+  VD(ng * 2, m.geom_invweight0[k / 2][k % 2] = (real)D[k]);
+  VD(ng, m.geom_rbound[k] = (real)D[k]);
+  VI(ng, m.geom_hulladr[k] = I[k]);
+  VI(ng, m.geom_hullnum[k] = I[k]);
+  VI(ng, (void)I[k]);  // geom_srcbody
+  VI(ng, (void)I[k]);  // geom_srcparent
+  if (rd.field(&D, 8) != (long)nhullvert * 3) return bad("model blob: hull_vert");
+  out->hull_vert.resize(D.size());
+  for (size_t k = 0; k < D.size(); ++k) out->hull_vert[k] = (float)D[k];
+  m.nhull = nhullvert;
+  VI(ns, m.site_body[k] = I[k]);
+  VD(ns * 3, m.site_pos[k / 3][k % 3] = (real)D[k]);
+  VD(ns * 4, (void)D[k]);  // site_quat (orientation of sites is not observed by the door / peg tasks)
+  VI(nu, m.act_dof[k] = I[k]);
+  VI(nu, m.act_qposadr[k] = I[k]);
+  VD(nu, m.act_kp[k] = (real)D[k]);
+  VD(nu * 2, m.act_ctrlrange[k / 2][k % 2] = (real)D[k]);
+  VI(nu, m.act_ctrllimited[k] = I[k]);
+  VD(nu * 2, m.act_forcerange[k / 2][k % 2] = (real)D[k]);
+  VI(nu, m.act_forcelimited[k] = I[k]);
+  VI(nw, m.weld_body[k] = I[k]);
+  VD(nw * 3, m.weld_pos[k / 3][k % 3] = (real)D[k]);
+  VD(nw * 4, m.weld_quat[k / 4][k % 4] = (real)D[k]);
+  VD(nw * 7, m.weld_relpose[k / 7][k % 7] = (real)D[k]);
+  VD(nw * 2, m.weld_solref[k / 2][k % 2] = (real)D[k]);
+  VD(nw * 5, m.weld_solimp[k / 5][k % 5] = (real)D[k]);
+  VD(nw * 2, m.weld_invweight[k / 2][k % 2] = (real)D[k]);
+  VD(3, (void)D[k]);  // mocap_pos0
+  VD(4, (void)D[k]);  // mocap_quat0
+#undef RI
+#undef RD
+#undef VI
+#undef VD
+  if (!rd.done()) return bad("model blob: trailing bytes");
+  // derived tables
+  for (int b = 0; b < nb; ++b) {
+    unsigned mask = 0;
+    for (int c = b; c > 0; c = m.body_parent[c]) mask |= 1u << c;
+    m.body_anc[b] = mask;
+  }
+  for (int j = 0; j < m.njnt; ++j) {
+    const int da = m.jnt_dofadr[j], b = m.jnt_body[j];
+    m.jnt_qpos0[j] = m.qpos0[m.jnt_qposadr[j]];
+    int pd = -1;  // last dof of the nearest moving ancestor
+    const int pb = m.body_parent[b];
+    if (pb > 0) {
+      const int pj = m.body_jnt[pb];
+      pd = m.jnt_dofadr[pj] + (m.jnt_type[pj] == 0 ? 5 : 0);
+    }
+    if (m.jnt_type[j] == 0) {
+      for (int k = 0; k < 6; ++k) { m.dof_rot[da + k] = k >= 3; m.dof_parent[da + k] = k == 0 ? pd : da + k - 1; }
+    } else if (m.jnt_type[j] == 1) {
+      return bad("ball joints are not built");
+    } else {
+      m.dof_rot[da] = m.jnt_type[j] == 3;
+      m.dof_parent[da] = pd;
+    }
+  }
+  // candidate collision pairs: contype/conaffinity, same fused body, fused parent-child unless one side is the world
+  // (MuJoCo engine_collision_driver.c: filterBodyPair on weld ids, filterBitmask)
+  int np = 0;
+  for (int g1 = 0; g1 < ng; ++g1)
+    for (int g2 = g1 + 1; g2 < ng; ++g2) {
+      if (!((contype[g1] & conaff[g2]) || (contype[g2] & conaff[g1]))) continue;
+      const int b1 = m.geom_body[g1], b2 = m.geom_body[g2];
+      if (b1 == b2) continue;
+      if (b1 != 0 && b2 != 0 && (m.body_parent[b1] == b2 || m.body_parent[b2] == b1)) continue;
+      if (np >= MAXPAIR) return bad("too many candidate collision pairs");
+      m.pair_g1[np] = g1;
+      m.pair_g2[np] = g2;
+      ++np;
+    }
+  m.npair = np;
+  m.frame_skip = task.frame_skip;
+  if (task.max_newton > 0 && task.max_newton < m.iterations) m.iterations = task.max_newton;
+  m.obs_hand_site = task.hand_site;
+  m.obs_ree_site = task.ree_site;
+  m.obs_lee_site = task.lee_site;
+  m.obs_obj_geom = task.obj_geom;
+  m.obs_obj_site = task.obj_site;
+  for (int k = 0; k < 3; ++k) { m.mocap_low[k] = task.mocap_low[k]; m.mocap_high[k] = task.mocap_high[k]; }
+  m.action_scale = task.action_scale;
+  m.success_radius = task.success_radius;
+  if (task.hand_site < 0 || task.hand_site >= ns || task.ree_site < 0 || task.ree_site >= ns || task.lee_site < 0 ||
+      task.lee_site >= ns || (task.obj_geom < 0 && (task.obj_site < 0 || task.obj_site >= ns)) || task.obj_geom >= ng)
+    return bad("task spec: observation site / geom index out of range");
+  return true;
+}
+
+}  // namespace mj
+}  // namespace earl

@@ -1,0 +1,106 @@
+/*
+ * earl_mj_b200.h -- C ABI of the articulated-body half of libearl_b200.so: batched, device-resident step of the
+ * reference's MuJoCo-backed Sawyer tasks (sawyer_door now; sawyer_peg next), one warp per environment instance.
+ *
+ * The reference has no FFI on this path: `SawyerDoorV2` / `SawyerPegV2` (earl_benchmark/envs/sawyer_door.py,
+ * sawyer_peg.py) inherit metaworld's SawyerXYZEnv.step, which drives MuJoCo 2.1.0 through mujoco-py
+ * (frame_skip x sim.step()).  Every entry point cites the reference METHOD it replaces.  Same conventions as
+ * include/earl_b200.h: plain C, device pointers unless marked host, `stream` is a cudaStream_t passed as void*,
+ * 0 = ok / <0 = earl_status (earl_last_error() has the message), no CPU fallback.
+ */
+#ifndef EARL_MJ_B200_H_
+#define EARL_MJ_B200_H_
+
+#include "earl_b200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct earl_mj_handle earl_mj_handle;
+
+typedef struct {
+  int32_t env_kind;         /* EARL_ENV_SAWYER_DOOR (EARL_ENV_SAWYER_PEG: not built yet) */
+  int32_t num_envs;
+  int32_t device;
+  uint32_t flags;           /* EARL_FLAG_AUTO_RESET | EARL_FLAG_EVAL_STATS */
+  int64_t episode_horizon;  /* PersistentStateWrapper(episode_horizon), persistent_state_wrapper.py:10-12 */
+} earl_mj_config;
+
+/* Task constants that live in the metaworld / EARL Python classes rather than in the MJCF. */
+typedef struct {
+  int32_t frame_skip;       /* SawyerXYZEnv frame_skip = 5 substeps per env step */
+  int32_t hand_site;        /* site index of the 'hand' body frame (get_endeff_pos) */
+  int32_t ree_site;         /* 'rightEndEffector' */
+  int32_t lee_site;         /* 'leftEndEffector' */
+  int32_t obj_geom;         /* door: geom 'handle' (sawyer_door.py:113 get_geom_xpos); -1 when the object is a site */
+  int32_t obj_site;         /* peg: site 'pegHead' (sawyer_peg.py:186-187); -1 otherwise */
+  int32_t max_newton;       /* cap on Newton iterations per substep (0 = the model's <option iterations>) */
+  int32_t reserved;
+  float mocap_low[3];       /* hand_low */
+  float mocap_high[3];      /* hand_high */
+  float action_scale;       /* 1/100 (SawyerXYZEnv.action_scale) */
+  float success_radius;     /* 0.02 door (sawyer_door.py:177) */
+} earl_mj_task;
+
+/* model_blob: the serialized structure-of-arrays model written by earl_benchmark_b200.mjcf.compile.Model.to_blob()
+ * (the reference loads the same MJCF through mujoco_py.load_model_from_path, sawyer_door.py:67-70).
+ * Replaces constructing SawyerDoorV2 + PersistentStateWrapper, earl_benchmark/__init__.py:119-123,140-141. */
+EARL_API int earl_mj_create(const earl_mj_config* cfg, const void* model_blob, size_t model_nbytes, const earl_mj_task* task,
+                            earl_mj_handle** out);
+EARL_API int earl_mj_destroy(earl_mj_handle* h);
+EARL_API int earl_mj_obs_dim(const earl_mj_handle* h);    /* 14 */
+EARL_API int earl_mj_action_dim(const earl_mj_handle* h); /* 4 */
+EARL_API int earl_mj_nq(const earl_mj_handle* h);
+EARL_API int earl_mj_nv(const earl_mj_handle* h);
+
+/* Goal table, f64 [count,7] on the host (goal_states, sawyer_door.py:15-16; reset_goal(goal) for custom goals). */
+EARL_API int earl_mj_set_goal_table(earl_mj_handle* h, const double* rows_host, int32_t count);
+
+/* sim.reset() + SawyerXYZEnv._reset_hand(steps): from qpos0, `steps` times { mocap_pos <- hand_init_pos; mocap_quat <-
+ * [1,0,1,0]; do_simulation(ctrl, frame_skip) }.  Deterministic, so it is run ONCE on the device and the resulting
+ * state is kept as the reset template every later earl_mj_reset copies (sawyer_door.py:111-112). */
+EARL_API int earl_mj_build_reset_template(earl_mj_handle* h, const double* hand_init_pos_host, const float* ctrl_host,
+                                          int32_t steps);
+
+/* PersistentStateWrapper.reset + reset_model (persistent_state_wrapper.py:17-20, sawyer_door.py:111-125) for every env
+ * with mask[i] != 0 (NULL = all): state <- reset template, object joint <- obj_qpos[i] with zero velocity
+ * (_set_obj_xyz), goal <- goal_idx[i] (NULL = row 0), num_interventions += 1, steps_since_reset = 0, then a fresh
+ * forward-kinematics pass and the observation (obs_out may be NULL).  obj_qpos is f64 [N]: the host draws it from
+ * the bit-exact replica of the reference's np.random stream (earl_rng_np_uniform). */
+EARL_API int earl_mj_reset(earl_mj_handle* h, const uint8_t* mask_dev, const double* obj_qpos_dev, const int32_t* goal_idx_dev,
+                           float* obs_out_dev, void* stream);
+
+/* One PersistentStateWrapper.step of every env: SawyerXYZEnv.step (set_xyz_action, do_simulation = frame_skip x
+ * mj_step), EARL observation + sparse reward (sawyer_door.py:86-94,168-177), counters and horizon `done`
+ * (persistent_state_wrapper.py:22-31).  actions [N,4] f32; obs [N,14] f32; reward [N] f32; done [N] u8;
+ * success [N] u8 or NULL. */
+EARL_API int earl_mj_step(earl_mj_handle* h, const float* actions_dev, float* obs_dev, float* reward_dev, uint8_t* done_dev,
+                          uint8_t* success_dev, void* stream);
+/* Same with HOST buffers (copies inside the call, synchronous). */
+EARL_API int earl_mj_step_host(earl_mj_handle* h, const float* actions_host, float* obs_host, float* reward_host,
+                               uint8_t* done_host, uint8_t* success_host);
+/* env._get_obs() from a fresh kinematics pass of the current state. */
+EARL_API int earl_mj_get_obs(earl_mj_handle* h, float* obs_dev, void* stream);
+
+/* Physics state of every env as host arrays (synchronous): qpos f64 [N,nq], qvel f64 [N,nv], qacc_warmstart f64 [N,nv],
+ * mocap_pos f64 [N,3].  The engine keeps qpos / qvel / warm start in fp32 and mocap_pos in fp64.
+ * Replaces sim.get_state() / sim.set_state() (mujoco-py), used by _set_obj_xyz and by state snapshots. */
+EARL_API int earl_mj_get_state(earl_mj_handle* h, double* qpos_host, double* qvel_host, double* warm_host, double* mocap_host);
+EARL_API int earl_mj_set_state(earl_mj_handle* h, const double* qpos_host, const double* qvel_host, const double* warm_host,
+                               const double* mocap_host);
+
+/* total_steps (host scalar), num_interventions i64 [N], steps_since_reset u32 [N]; arrays may be NULL. */
+EARL_API int earl_mj_counters(earl_mj_handle* h, int64_t* total_steps_host, int64_t* num_interventions_dev,
+                              uint32_t* steps_since_reset_dev, void* stream);
+/* out4 = { sum of episode returns, #envs successful at their last step, #envs successful at any step since reset, N } */
+EARL_API int earl_mj_eval_stats(earl_mj_handle* h, double* out4_dev, void* stream);
+/* Work counters accumulated by the step kernel since creation (host): { env_steps, substeps, newton_iterations,
+ * constraint_rows, contacts, bad_states }. */
+EARL_API int earl_mj_work_counters(earl_mj_handle* h, uint64_t* out6_host);
+EARL_API int64_t earl_mj_launch_count(const earl_mj_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EARL_MJ_B200_H_ */

@@ -9,11 +9,11 @@ import pytest
 from conftest import REPO
 from earl_benchmark_b200 import _lib, build
 
-HEADER = os.path.join(REPO, "include", "earl_b200.h")
+HEADERS = [os.path.join(REPO, "include", f) for f in ("earl_b200.h", "earl_mj_b200.h")]
 
 
 def header_symbols():
-    text = open(HEADER).read()
+    text = "\n".join(open(h).read() for h in HEADERS)
     return re.findall(r"^EARL_API\s+[\w\s\*]+?\b(earl_\w+)\s*\(", text, flags=re.M)
 
 
@@ -41,6 +41,8 @@ def test_struct_layouts_match_header():
     # sizes the C side checks against (earl_create rejects blobs of any other size)
     assert ctypes.sizeof(_lib.EarlConfig) == 40
     assert ctypes.sizeof(_lib.TabletopModel) == 8 + 4 * 8 + 6 * 8 + 256 * 6 * 8
+    assert ctypes.sizeof(_lib.MjConfig) == 24
+    assert ctypes.sizeof(_lib.MjTask) == 8 * 4 + 8 * 4
 
 
 def test_no_cpu_fallback_without_gpu():

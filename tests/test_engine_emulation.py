@@ -1,0 +1,82 @@
+"""The engine kernel source (csrc/mj_*.cuh) compiled for the host with one lane, checked against the fp64 checker
+(oracle/mjengine.c) -- the CPU-side guard for the code the GPU runs.  North-star bar: from identical states and
+actions, one-step qpos / qvel within 1e-4 absolute (fp32 engine vs fp64)."""
+import numpy as np
+import pytest
+
+from earl_benchmark_b200.envs.sawyer_door import MODEL_PATH
+from earl_benchmark_b200.mjcf.compile import Model
+from host_emulation.emu import Emu, door_task
+from oracle.engine import SawyerDoorOracle
+
+TOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def door():
+    m = Model.load(MODEL_PATH)
+    return m, SawyerDoorOracle(m), Emu(m, door_task(m))
+
+
+def test_mass_matrix_bias_and_kinematics_match(door):
+    m, o, em = door
+    rs = np.random.RandomState(0)
+    for _ in range(8):
+        q = m.qpos0 + rs.uniform(-1, 1, int(m.nq)) * np.array([1.0] * 7 + [0.02, 0.02, 0.7])
+        q[1] -= 1.5
+        v = rs.uniform(-2, 2, int(m.nv))
+        o.e.reset()
+        o.e.qpos[:], o.e.qvel[:] = q, v
+        M_ref, b_ref = o.e.mass_matrix(), o.e.bias()
+        x_ref = o.e.arr("xpos", (24, 3))[:int(m.nbody)].copy()
+        em.set_state(q, v, np.zeros(int(m.nv)), [0, 0.4, 0.2])
+        M, b, x = em.forward_parts()
+        assert np.abs(M - M_ref).max() <= 1e-6 * np.abs(M_ref).max()
+        assert np.abs(b - b_ref).max() <= 2e-6 * max(1.0, np.abs(b_ref).max())
+        assert np.abs(x - x_ref).max() <= 1e-6
+
+
+def test_one_env_step_parity_along_the_reset_transient(door):
+    """sim.reset() + _reset_hand(): 50 x 5 substeps with joint limits active and the weld pulling the arm 1 m;
+    before every env step the emulated engine is re-synchronised to the checker's state (one-step test)."""
+    m, o, em = door
+    e = o.e
+    e.reset()
+    nv = int(m.nv)
+    worst_q = worst_v = 0.0
+    for it in range(50):
+        e.mocap_pos[:], e.mocap_quat[:], e.ctrl[:] = o.HAND_INIT, [1, 0, 1, 0], [-1, 1]
+        em.set_state(e.qpos, e.qvel, e.arr("qacc_warmstart", (32,))[:nv], o.HAND_INIT, ctrl=(-1, 1))
+        e.step(5)
+        em.substeps(5)
+        q, v, _, _ = em.get_state()
+        worst_q, worst_v = max(worst_q, np.abs(q - e.qpos).max()), max(worst_v, np.abs(v - e.qvel).max())
+        assert em.info("bad") == 0
+        assert em.info("iter") <= 4          # Newton converges in a handful of iterations in fp32 too
+    assert worst_q < TOL and worst_v < TOL, (worst_q, worst_v)
+
+
+def test_open_loop_rollout_tracks_the_checker(door):
+    """250 settle substeps + 60 random-action env steps without any re-synchronisation."""
+    m, o, em = door
+    e = o.e
+    e.reset()
+    em.set_state(e.qpos, e.qvel, np.zeros(int(m.nv)), o.HAND_INIT, ctrl=(-1, 1))
+    for _ in range(50):
+        e.mocap_pos[:], e.mocap_quat[:], e.ctrl[:] = o.HAND_INIT, [1, 0, 1, 0], [-1, 1]
+        e.step(5)
+        em.substeps(5)
+    q, v, w, _ = em.get_state()
+    assert np.abs(q - e.qpos).max() < TOL and np.abs(v - e.qvel).max() < TOL
+    e.qpos[o.door_qadr], e.qvel[o.door_qadr] = -1.0, 0.0
+    q[o.door_qadr], v[o.door_qadr] = -1.0, 0.0
+    em.set_state(q, v, w, o.HAND_INIT)
+    rs = np.random.RandomState(1)
+    for _ in range(60):
+        a = rs.uniform(-1, 1, 4).astype(np.float32)
+        ob_ref, _ = o.step(a)
+        ob = em.env_step(a)
+        assert np.abs(ob_ref[:7] - ob).max() < 1e-5
+    q, v, _, mp = em.get_state()
+    assert np.abs(q - e.qpos).max() < TOL and np.abs(v - e.qvel).max() < TOL
+    assert np.abs(mp - e.mocap_pos).max() < 1e-7

@@ -1,0 +1,136 @@
+"""GPU parity tests of the batched Sawyer door step (C ABI: include/earl_mj_b200.h) against the fp64 checker.
+
+Bars (BASELINE.json north_star): from identical states and actions, one-step qpos / qvel within 1e-4 absolute (fp32
+engine vs fp64); integer bookkeeping (step counters, horizon `done`, intervention counts) bit-exact."""
+import numpy as np
+import pytest
+import torch
+
+import earl_benchmark_b200 as eb
+from earl_benchmark_b200.envs import sawyer_door
+from earl_benchmark_b200.mjcf.compile import Model
+from oracle.engine import SawyerDoorOracle
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def oracle():
+    return SawyerDoorOracle(Model.load(sawyer_door.MODEL_PATH))
+
+
+def _reference_states(o, count, seed):
+    """`count` diverse (qpos, qvel, warmstart, mocap) tuples sampled along random-action checker rollouts."""
+    rs = np.random.RandomState(seed)
+    e, nv = o.e, o.e.nv
+    out = []
+    while len(out) < count:
+        o.reset(door_angle=-np.pi / 3 + rs.uniform(0, np.pi / 20))
+        bias = rs.uniform(-0.5, 0.5, 4)
+        for t in range(40):
+            o.step(np.clip(bias + rs.uniform(-1, 1, 4), -1, 1))
+            if t % 4 == 3:
+                out.append((e.qpos.copy(), e.qvel.copy(), e.arr("qacc_warmstart", (32,))[:nv].copy(), e.mocap_pos.copy()))
+    return out[:count]
+
+
+def test_one_step_parity_from_identical_states(oracle):
+    n = 96
+    states = _reference_states(oracle, n, seed=3)
+    env = sawyer_door.SawyerDoorV2(num_envs=n, device="cuda:0")
+    env.reset()
+    env.set_state(qpos=np.stack([s[0] for s in states]), qvel=np.stack([s[1] for s in states]),
+                  qacc_warmstart=np.stack([s[2] for s in states]), mocap_pos=np.stack([s[3] for s in states]))
+    rs = np.random.RandomState(4)
+    actions = rs.uniform(-1.2, 1.2, (n, 4)).astype(np.float32)
+    obs, rew, done, info = env.step(torch.from_numpy(actions).cuda())
+    got = env.get_state()
+    obs = obs.cpu().numpy()
+    e = oracle.e
+    worst = dict(q=0.0, v=0.0, obs=0.0)
+    for i, (q, v, w, mp) in enumerate(states):
+        e.reset()
+        e.qpos[:], e.qvel[:], e.mocap_pos[:] = q, v, mp
+        e.arr("qacc_warmstart", (32,))[:e.nv] = w
+        ob_ref, r_ref = oracle.step(actions[i])
+        worst["q"] = max(worst["q"], np.abs(got["qpos"][i] - e.qpos).max())
+        worst["v"] = max(worst["v"], np.abs(got["qvel"][i] - e.qvel).max())
+        worst["obs"] = max(worst["obs"], np.abs(obs[i] - ob_ref).max())
+        assert np.abs(got["mocap_pos"][i] - e.mocap_pos).max() < 1e-7
+        d = np.linalg.norm(ob_ref[4:7] - ob_ref[11:14])
+        if abs(d - 0.02) > 1e-5:
+            assert float(rew[i]) == r_ref
+    assert worst["q"] < TOL and worst["v"] < TOL and worst["obs"] < 1e-5, worst
+    assert env.work_counters()["bad_states"] == 0
+
+
+def test_reset_template_and_open_loop_rollout(oracle):
+    """Device reset (sim.reset + _reset_hand simulated on the GPU, door angle set, fresh kinematics) and 40 open-loop
+    random-action steps against the checker doing the same."""
+    n = 8
+    angles = -np.pi / 3 + np.linspace(0, np.pi / 20, n)
+    env = sawyer_door.SawyerDoorV2(num_envs=n, device="cuda:0")
+    obs0 = env.reset(door_angle=angles).cpu().numpy()
+    rs = np.random.RandomState(5)
+    actions = rs.uniform(-1, 1, (40, n, 4)).astype(np.float32)
+    dev_obs = []
+    for t in range(40):
+        o, r, d, _ = env.step(torch.from_numpy(actions[t]).cuda())
+        dev_obs.append(o.cpu().numpy().copy())
+    for i in (0, n - 1):
+        ob = oracle.reset(door_angle=angles[i])
+        assert np.abs(ob - obs0[i]).max() < 2e-5, np.abs(ob - obs0[i]).max()
+        for t in range(40):
+            ob, _ = oracle.step(actions[t, i])
+            assert np.abs(ob - dev_obs[t][i]).max() < 5e-5, (t, np.abs(ob - dev_obs[t][i]).max())
+
+
+def test_loader_surface_counters_and_horizon():
+    n, horizon = 33, 5
+    train, ev = eb.EARLEnvs("sawyer_door", reward_type="sparse", num_envs=n, train_horizon=horizon, device="cuda:0").get_envs()
+    obs = train.reset()
+    assert obs.shape == (n, 14) and obs.dtype == torch.float32
+    # reset draws: obj_init_angle + np.random.uniform(0, pi/20) from np.random.seed(0), env order
+    ang = -np.pi / 3 + np.random.RandomState(0).uniform(0, np.pi / 20, n)
+    qadr = 9
+    assert np.allclose(train.env.get_state()["qpos"][:, qadr], ang.astype(np.float32), atol=0, rtol=0)
+    a = torch.zeros((n, 4), device="cuda")
+    for t in range(horizon + 2):
+        o, r, d, info = train.step(a)
+        assert bool(d.all()) == (t + 1 >= horizon)
+    assert train.total_steps == horizon + 2
+    assert int(train.num_interventions.min()) == 1 == int(train.num_interventions.max())
+    assert int(train.steps_since_reset[0]) == horizon + 2
+    train.reset()
+    assert int(train.num_interventions[0]) == 2 and int(train.steps_since_reset[0]) == 0
+    assert eb.EARLEnvs("sawyer_door", num_envs=1, device="cuda:0").get_goal_states().shape == (1, 7)
+    assert ev.env._episode_horizon == 300
+
+
+def test_host_path_matches_device_path():
+    n = 17
+    e1 = sawyer_door.SawyerDoorV2(num_envs=n, device="cuda:0", seed=2)
+    e2 = sawyer_door.SawyerDoorV2(num_envs=n, device="cuda:0", seed=2)
+    e1.reset(), e2.reset()
+    rs = np.random.RandomState(9)
+    for _ in range(5):
+        a = rs.uniform(-1, 1, (n, 4)).astype(np.float32)
+        o1, r1, d1, _ = e1.step(torch.from_numpy(a).cuda())
+        o2, r2, d2, _ = e2.step(a)
+        assert np.array_equal(o1.cpu().numpy(), o2) and np.array_equal(r1.cpu().numpy(), r2)
+    assert e1.launch_count >= 6
+
+
+def test_eval_stats_and_success_flag(oracle):
+    """Door placed at the goal angle: success on every step, eval stats count it."""
+    n = 4
+    env = sawyer_door.SawyerDoorV2(num_envs=n, device="cuda:0", eval_stats=True)
+    env._configure(episode_horizon=3)
+    env.reset(door_angle=np.zeros(n))
+    a = torch.zeros((n, 4), device="cuda")
+    for _ in range(3):
+        o, r, d, info = env.step(a)
+    assert bool(info["success"].all()) and float(r.sum()) == n
+    st = env.eval_stats().cpu().numpy()
+    assert st[0] == 3 * n and st[1] == n and st[2] == n and st[3] == n

@@ -22,7 +22,8 @@ def sawyer_door():
     spec = parser.load(os.path.join(MW, "sawyer_door_pull.xml"))
     # reset_model() moves the door body to obj_init_pos, an fp32 array (reference envs/sawyer_door.py:36,119-120)
     door_pos = np.array([0.1, 0.95, 0.1], dtype=np.float32).astype(np.float64)
-    return C.compile_model(spec, body_pos_overrides={"door": door_pos}, keep_geoms=("handle",), frame_sites=("hand",))
+    return C.compile_model(spec, body_pos_overrides={"door": door_pos}, keep_geoms=("handle",), frame_sites=("hand",),
+                           keep_sites=("rightEndEffector", "leftEndEffector"))
 
 
 if __name__ == "__main__":
