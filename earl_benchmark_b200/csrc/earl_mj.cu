@@ -40,7 +40,7 @@ int failf(int code, const char* fmt, ...) {
 
 using namespace earl::mj;
 
-constexpr int kWPB = 8;  // warps (= environments in flight) per block
+constexpr int kWPB = 16;  // warps (= environments in flight) per block: 16 x 13.2 KB workspaces + the model fill one SM
 constexpr int kObs = 14, kAct = 4, kGoal = 7, kMaxGoals = 32;
 constexpr size_t kModelBytes = (sizeof(Model) + 15) & ~size_t(15);
 constexpr size_t kSmemBytes = kModelBytes + kWPB * ((sizeof(Work) + 15) & ~size_t(15));
@@ -105,6 +105,9 @@ __device__ __forceinline__ void load_env(Work& w, const float* rec, int lane) {
   scatter_rec(w, lane, rec[lane]);
   scatter_rec(w, lane + 32, rec[lane + 32]);
   if (lane == 0) { w.bad = 0; w.acc_iter = w.acc_rows = w.acc_con = 0; }
+#ifdef MJ_PHASE_TIMING
+  if (lane < 8) w.phase[lane] = 0;
+#endif
   __syncwarp();
 }
 __device__ __forceinline__ void store_env(const Work& w, float* rec, int lane) {
@@ -123,19 +126,24 @@ __device__ __forceinline__ bool write_obs(const Model& m, Work& w, const float* 
   return sqrtf(dx * dx + dy * dy + dz * dz) <= m.success_radius;
 }
 
-__global__ void __launch_bounds__(kWPB * 32) mj_step_kernel(const StepArgs a) {
+__global__ void __launch_bounds__(kWPB * 32, 1) mj_step_kernel(const StepArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
   Model* sm = reinterpret_cast<Model*>(smem);
   load_model(sm, a.model);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   Work& w = *reinterpret_cast<Work*>(smem + kModelBytes + warp * kWorkStride);
   unsigned long long it = 0, rows = 0, cons = 0, bad = 0, envs = 0;
-  for (int env = blockIdx.x * kWPB + warp; env < a.n; env += gridDim.x * kWPB) {
+  // every warp of a block makes the same number of trips (the substep has block-wide phase barriers); a warp without
+  // an environment in the last trip re-runs the last environment and discards the result
+  for (int base = blockIdx.x * kWPB; base < a.n; base += gridDim.x * kWPB) {
+    const bool live = base + warp < a.n;
+    const int env = live ? base + warp : a.n - 1;
     float* rec = a.state + (size_t)env * REC_FLOATS;
     load_env(w, rec, lane);
     if (lane < kAct) w.action[lane] = a.actions[(size_t)env * kAct + lane];
     __syncwarp();
     env_step<32>(*sm, a.hull, w, w.action, lane);
+    if (!live) continue;
     const bool ok = write_obs(*sm, w, a.goals, a.obs + (size_t)env * kObs, lane);
     if (lane == 0) {
       // PersistentStateWrapper.step: counters, horizon `done` (persistent_state_wrapper.py:22-31)
@@ -148,6 +156,9 @@ __global__ void __launch_bounds__(kWPB * 32) mj_step_kernel(const StepArgs a) {
       if (a.success) a.success[env] = ok ? 1 : 0;
       if (a.ep_return) a.ep_return[env] += (double)r;
       it += w.acc_iter; rows += w.acc_rows; cons += w.acc_con; bad += w.bad ? 1 : 0; envs += 1;
+#ifdef MJ_PHASE_TIMING
+      for (int k = 0; k < 8; ++k) atomicAdd(&a.work[8 + k], (unsigned long long)w.phase[k]);
+#endif
     }
     store_env(w, rec, lane);
     __syncwarp();
@@ -163,7 +174,7 @@ __global__ void __launch_bounds__(kWPB * 32) mj_step_kernel(const StepArgs a) {
 }
 
 // reset (mode 0) / get_obs (mode 1): fresh kinematics of the (new) state, observation out
-__global__ void __launch_bounds__(kWPB * 32) mj_reset_kernel(const StepArgs a, const int mode) {
+__global__ void __launch_bounds__(kWPB * 32, 1) mj_reset_kernel(const StepArgs a, const int mode) {
   extern __shared__ __align__(16) unsigned char smem[];
   Model* sm = reinterpret_cast<Model*>(smem);
   load_model(sm, a.model);
@@ -332,7 +343,7 @@ int earl_mj_create(const earl_mj_config* cfg, const void* model_blob, size_t mod
   if (!rc) rc = h->alloc(&h->d_goals, kMaxGoals * 8);
   if (!rc) rc = h->alloc(&a.interventions, n);
   if (!rc && (cfg->flags & EARL_FLAG_EVAL_STATS)) rc = h->alloc(&a.ep_return, n);
-  if (!rc) rc = h->alloc(&a.work, 8);
+  if (!rc) rc = h->alloc(&a.work, 16);
   if (!rc) rc = h->alloc(&h->d_tmpl, REC_FLOATS);
   if (rc) { earl_mj_destroy(h); return rc; }
   e = cudaMemcpy(d_model, &m, sizeof(Model), cudaMemcpyHostToDevice);
@@ -538,6 +549,14 @@ int earl_mj_work_counters(earl_mj_handle* h, uint64_t* out6_host) {
   if (!out6_host) return failf(EARL_ERR_INVALID, "null out");
   CU(cudaDeviceSynchronize());
   CU(cudaMemcpy(out6_host, h->a.work, 6 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+#ifdef MJ_PHASE_TIMING
+  uint64_t ph[8];
+  CU(cudaMemcpy(ph, h->a.work + 8, sizeof(ph), cudaMemcpyDeviceToHost));
+  static const char* names[8] = {"kinematics", "mass_matrix", "collide", "constraint_rows", "bias", "smooth", "solve", "euler"};
+  uint64_t tot = 0;
+  for (int k = 0; k < 8; ++k) tot += ph[k];
+  for (int k = 0; k < 8; ++k) fprintf(stderr, "[mj phase] %-16s %6.2f %%  %10.0f cycles/env-step\n", names[k], 100.0 * ph[k] / (tot ? tot : 1), (double)ph[k] / (out6_host[0] ? out6_host[0] : 1));
+#endif
   return 0;
 }
 

@@ -9,6 +9,9 @@
 #include <string>
 #include <vector>
 
+#include <cmath>
+
+#include "mj_collide.cuh"
 #include "mj_engine.cuh"
 
 namespace earl {
@@ -77,6 +80,83 @@ struct HostModel {
   std::vector<float> hull_vert;  // [nhull][3]
 };
 
+// Compile-time pruning of candidate pairs (static geom gs, geom gm on a body whose only ancestor is the world and whose
+// single hinge / slide joint is limited): the joint range, widened by 0.15, is swept in steps that move no point of
+// the body by more than ~1 mm; if no sample brings the pair within margin + 4 mm the pair can never produce a contact
+// and is dropped.  Box-box pairs are swept with the separating-axis test itself, everything else with the
+// bounding-sphere-vs-box / sphere-sphere / sphere-plane bound the runtime broad phase uses.
+inline bool never_touch(const Model& m, int gs, int gm) {
+  if (m.geom_body[gs] != 0) return false;
+  const int b = m.geom_body[gm];
+  if (b == 0 || m.body_parent[b] != 0) return false;
+  const int j = m.body_jnt[b];
+  if (m.jnt_type[j] < 2 || !m.jnt_limited[j]) return false;
+  const double lo = m.jnt_range[j][0] - 0.15, hi = m.jnt_range[j][1] + 0.15;
+  const double slack = 0.004, margin = std::fmax(m.geom_margin[gs], m.geom_margin[gm]) + slack;
+  const double reach = 1.0;  // bound on the distance of any body point from the joint (metres)
+  const int nsamp = (int)((hi - lo) * reach / 0.001) + 2;
+  Work* w = new Work();
+  memset(w, 0, sizeof(Work));
+  bool clear = true;
+  for (int s = 0; s < nsamp && clear; ++s) {
+    const double q = lo + (hi - lo) * s / (nsamp - 1);
+    for (int k = 0; k < m.nq; ++k) w->qpos[k] = m.qpos0[k];
+    w->qpos[m.jnt_qposadr[j]] = (real)q;
+    // pose of body b alone (its parent is the world): same formulas as kinematics()
+    real quat[4], R[9], pos[3];
+    for (int k = 0; k < 4; ++k) quat[k] = m.body_quat[b][k];
+    for (int k = 0; k < 3; ++k) pos[k] = m.body_pos[b][k];
+    quat2mat(R, quat);
+    if (m.jnt_type[j] == 3) {
+      real anchor[3], t[3], qj[4];
+      mulmatvec3(t, R, m.jnt_pos[j]);
+      for (int k = 0; k < 3; ++k) anchor[k] = pos[k] + t[k];
+      const real half = 0.5f * (real)(q - m.jnt_qpos0[j]);
+      qj[0] = cosf(half);
+      for (int k = 0; k < 3; ++k) qj[1 + k] = m.jnt_axis[j][k] * sinf(half);
+      mulquat(quat, quat, qj);
+      normquat(quat);
+      quat2mat(R, quat);
+      mulmatvec3(t, R, m.jnt_pos[j]);
+      for (int k = 0; k < 3; ++k) pos[k] = anchor[k] - t[k];
+    } else {
+      real axis[3];
+      mulmatvec3(axis, R, m.jnt_axis[j]);
+      for (int k = 0; k < 3; ++k) pos[k] += axis[k] * (real)(q - m.jnt_qpos0[j]);
+    }
+    real gp[3], gR[9], t[3];
+    mulmatvec3(t, R, m.geom_pos[gm]);
+    for (int k = 0; k < 3; ++k) gp[k] = pos[k] + t[k];
+    for (int a = 0; a < 3; ++a)
+      for (int c = 0; c < 3; ++c) gR[3 * a + c] = R[3 * a] * m.geom_mat[gm][c] + R[3 * a + 1] * m.geom_mat[gm][3 + c] + R[3 * a + 2] * m.geom_mat[gm][6 + c];
+    const int ts = m.geom_type[gs], tm = m.geom_type[gm];
+    const real* sp = m.geom_pos[gs];
+    const real* sR = m.geom_mat[gs];
+    if (ts == GEOM_BOX && tm == GEOM_BOX) {
+      NarrowScratch* S = reinterpret_cast<NarrowScratch*>(&w->H[0][0]);
+      if (box_box(sp, sR, m.geom_size[gs], gp, gR, m.geom_size[gm], (real)margin, S->rc, S) > 0) clear = false;
+    } else if (ts == GEOM_PLANE) {
+      const real n[3] = {sR[2], sR[5], sR[8]};
+      real rel[3];
+      sub3(rel, gp, sp);
+      if (dot3(rel, n) <= m.geom_rbound[gm] + margin) clear = false;
+    } else if (ts == GEOM_BOX) {
+      const double r = m.geom_rbound[gm] + margin;
+      if (point_box_dist2(gp, sp, sR, m.geom_size[gs]) <= r * r) clear = false;
+    } else if (tm == GEOM_BOX) {
+      const double r = m.geom_rbound[gs] + margin;
+      if (point_box_dist2(sp, gp, gR, m.geom_size[gm]) <= r * r) clear = false;
+    } else {
+      real rel[3];
+      sub3(rel, gp, sp);
+      const double r = m.geom_rbound[gs] + m.geom_rbound[gm] + margin;
+      if (dot3(rel, rel) <= r * r) clear = false;
+    }
+  }
+  delete w;
+  return clear;
+}
+
 inline bool build_model(const void* blob, size_t nbytes, const TaskSpec& task, HostModel* out, std::string* err) {
   BlobReader rd(blob, nbytes);
   auto bad = [&](const char* what) { if (err) *err = what; return false; };
@@ -138,7 +218,13 @@ inline bool build_model(const void* blob, size_t nbytes, const TaskSpec& task, H
   VI(ng, m.geom_type[k] = I[k]);
   VD(ng * 3, m.geom_size[k / 3][k % 3] = (real)D[k]);
   VD(ng * 3, m.geom_pos[k / 3][k % 3] = (real)D[k]);
-  VD(ng * 4, m.geom_quat[k / 4][k % 4] = (real)D[k]);
+  if (rd.field(&D, 8) != (long)ng * 4) return bad("model blob: geom_quat");
+  for (int g = 0; g < ng; ++g) {  // local rotation matrix of the geom frame (row-major), from its unit quaternion
+    const double w = D[4 * g], x = D[4 * g + 1], y = D[4 * g + 2], z = D[4 * g + 3];
+    const double R[9] = {1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y), 2 * (x * y + w * z), 1 - 2 * (x * x + z * z),
+                         2 * (y * z - w * x), 2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)};
+    for (int k = 0; k < 9; ++k) m.geom_mat[g][k] = (real)R[k];
+  }
   std::vector<int32_t> contype(ng), conaff(ng);
   VI(ng, contype[k] = I[k]);
   VI(ng, conaff[k] = I[k]);
@@ -184,6 +270,12 @@ inline bool build_model(const void* blob, size_t nbytes, const TaskSpec& task, H
 #undef VI
 #undef VD
   if (!rd.done()) return bad("model blob: trailing bytes");
+  {  // the device impedance function only carries the power-1 and power-2 sigmoids
+    auto pw_ok = [](real p) { return p == 1.0f || p == 2.0f; };
+    for (int j = 0; j < m.njnt; ++j) if (!pw_ok(m.jnt_solimp[j][4])) return bad("solimp power must be 1 or 2");
+    for (int g = 0; g < ng; ++g) if (!pw_ok(m.geom_solimp[g][4])) return bad("solimp power must be 1 or 2");
+    for (int k = 0; k < nw; ++k) if (!pw_ok(m.weld_solimp[k][4])) return bad("solimp power must be 1 or 2");
+  }
   // derived tables
   for (int b = 0; b < nb; ++b) {
     unsigned mask = 0;
@@ -208,6 +300,16 @@ inline bool build_model(const void* blob, size_t nbytes, const TaskSpec& task, H
       m.dof_parent[da] = pd;
     }
   }
+  // geoms on moving bodies get a pose slot; static geoms keep their constant world pose in geom_pos / geom_mat
+  m.nmgeom = 0;
+  for (int g = 0; g < ng; ++g) {
+    m.geom_slot[g] = -1;
+    if (m.geom_body[g] != 0) {
+      if (m.nmgeom >= MAXMG) return bad("too many geoms on moving bodies");
+      m.geom_slot[g] = m.nmgeom;
+      m.mgeom[m.nmgeom++] = g;
+    }
+  }
   // candidate collision pairs: contype/conaffinity, same fused body, fused parent-child unless one side is the world
   // (MuJoCo engine_collision_driver.c: filterBodyPair on weld ids, filterBitmask)
   int np = 0;
@@ -218,8 +320,12 @@ inline bool build_model(const void* blob, size_t nbytes, const TaskSpec& task, H
       if (b1 == b2) continue;
       if (b1 != 0 && b2 != 0 && (m.body_parent[b1] == b2 || m.body_parent[b2] == b1)) continue;
       if (np >= MAXPAIR) return bad("too many candidate collision pairs");
-      m.pair_g1[np] = g1;
-      m.pair_g2[np] = g2;
+      const int cd = m.geom_condim[g1] > m.geom_condim[g2] ? m.geom_condim[g1] : m.geom_condim[g2];
+      if (cd != 3 && cd != 4) return bad("only contact dimensions 3 and 4 are built");
+      if (never_touch(m, g1, g2) || never_touch(m, g2, g1)) continue;
+      const bool swap = m.geom_type[g1] > m.geom_type[g2];  // MuJoCo orders a pair by geom type
+      m.pair_g1[np] = swap ? g2 : g1;
+      m.pair_g2[np] = swap ? g1 : g2;
       ++np;
     }
   m.npair = np;

@@ -10,14 +10,24 @@ namespace mj {
 
 // ------------------------------------------------------------------------------------------------ forward + Euler
 template <int NL>
-MJ_HD void substep(const Model& m, const real* hull, Work& w, int lane) {
+MJ_FN void substep(const Model& m, const real* hull, Work& w, int lane) {
   const int nv = m.nv;
+  bsync<NL>();
+  MJ_PHASE_BEGIN(w);
   kinematics<NL>(m, w, lane);
+  MJ_PHASE_END(w, 0);
   mass_matrix<NL>(m, w, lane);
+  bsync<NL>();
+  MJ_PHASE_END(w, 1);
   collide<NL>(m, hull, w, lane);
+  bsync<NL>();
+  MJ_PHASE_END(w, 2);
   make_constraints<NL>(m, w, lane);
   contact_rows<NL>(m, w, lane);
+  bsync<NL>();
+  MJ_PHASE_END(w, 3);
   bias_forces<NL>(m, w, lane);
+  MJ_PHASE_END(w, 4);
   // passive (damping, springs) - bias + actuation
   for (int i = lane; i < nv; i += NL) w.smooth[i] = -m.dof_damping[i] * w.qvel[i] - w.bias[i];
   wsync<NL>();
@@ -34,7 +44,11 @@ MJ_HD void substep(const Model& m, const real* hull, Work& w, int lane) {
     }
   }
   wsync<NL>();
+  bsync<NL>();
+  MJ_PHASE_END(w, 5);
   solve<NL>(m, w, lane);
+  bsync<NL>();
+  MJ_PHASE_END(w, 6);
   if (lane == 0) { w.acc_iter += w.solver_iter; w.acc_rows += w.nefc; w.acc_con += w.ncon; }
   // mj_Euler: implicit in joint damping
   const real h = m.timestep;
@@ -45,8 +59,7 @@ MJ_HD void substep(const Model& m, const real* hull, Work& w, int lane) {
     w.warm[i] = w.acc[i];
   }
   wsync<NL>();
-  if (!chol_factor<NL>(w.H, nv, lane)) w.bad = 1;
-  chol_solve<NL>(w.H, nv, w.tmp, lane);
+  if (!spd_solve<NL>(w.H, nv, w.tmp, lane)) w.bad = 1;
   for (int i = lane; i < nv; i += NL) w.qvel[i] += h * w.tmp[i];
   wsync<NL>();
   for (int j = lane; j < m.njnt; j += NL) {
@@ -67,13 +80,14 @@ MJ_HD void substep(const Model& m, const real* hull, Work& w, int lane) {
     }
   }
   wsync<NL>();
+  MJ_PHASE_END(w, 7);
 }
 
 // ------------------------------------------------------------------------------------------------ task layer
 // metaworld SawyerXYZEnv.step (set_xyz_action + do_simulation) followed by the EARL observation / sparse reward
 // (reference earl_benchmark/envs/sawyer_door.py:86-94,168-177).  `action` has 4 entries.
 template <int NL>
-MJ_HD void env_step(const Model& m, const real* hull, Work& w, const real* action, int lane) {
+MJ_FN void env_step(const Model& m, const real* hull, Work& w, const real* action, int lane) {
   if (lane == 0) {
     for (int k = 0; k < 3; ++k) {
       const double a = (double)clampr(action[k], -1.0f, 1.0f);
@@ -103,7 +117,7 @@ MJ_HD void geom_xpos(const Model& m, const Work& w, int g, real* out) {
   mulmatvec3(t, w.xmat[b], m.geom_pos[g]);
   for (int k = 0; k < 3; ++k) out[k] = w.xpos[b][k] + t[k];
 }
-MJ_HD void observe(const Model& m, const Work& w, real* obs7) {
+MJ_FN void observe(const Model& m, const Work& w, real* obs7) {
   real r[3], l[3];
   site_xpos(m, w, m.obs_hand_site, obs7);
   site_xpos(m, w, m.obs_ree_site, r);

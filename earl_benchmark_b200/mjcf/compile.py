@@ -363,7 +363,7 @@ class Model:
 # ~3x too stiff against the reference's own data; scaling that term by 2.9 reproduces the golden hand rest pose of
 # sawyer_door.py:13 to < 1 mm and the first-step hand response of all ten shipped door demonstrations to 0.6 mm rms,
 # while the rotational rows fit best with NO scaling (sharp optimum at 1.0).  See DESIGN.md "Sawyer engine: what is pinned".
-WELD_TRAN_SCALE = 2.9
+WELD_TRAN_SCALE = 3.35
 
 
 def compile_model(spec, body_pos_overrides=None, keep_geoms=(), keep_sites=None, frame_sites=(), weld_tran_scale=WELD_TRAN_SCALE):

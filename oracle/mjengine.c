@@ -183,6 +183,7 @@ void mje_kinematics(const mjModelF *m, mjDataF *d) {
     mulquat(q, d->xquat[b], m->geom_quat + 4 * g);
     quat2mat(d->geom_xmat[g], q);
   }
+  d->flops += (long long)m->nbody * 130 + (long long)m->ngeom * 40 + (long long)m->nsite * 40;
   for (int s = 0; s < m->nsite; ++s) {
     int b = m->site_body[s];
     double t[3], q[4];
@@ -204,7 +205,7 @@ static void body_inertia_world(const mjModelF *m, const mjDataF *d, int b, doubl
 }
 
 /* Jacobian columns of body b at world point `pt`: jp/jr [3][nv] (zero for dofs that do not move b) */
-static void body_jac(const mjModelF *m, const mjDataF *d, int b, const double *pt, double jp[3][MJ_MAXV], double jr[3][MJ_MAXV]) {
+void mje_body_jac(const mjModelF *m, const mjDataF *d, int b, const double *pt, double jp[3][MJ_MAXV], double jr[3][MJ_MAXV]) {
   for (int k = 0; k < 3; ++k) { memset(jp[k], 0, sizeof(double) * m->nv); memset(jr[k], 0, sizeof(double) * m->nv); }
   for (int c = b; c > 0; c = m->body_parent[c]) {
     int j = m->body_jnt[c], da = m->jnt_dofadr[j], n = m->jnt_type[j] == 0 ? 6 : 1;
@@ -230,7 +231,7 @@ void mje_mass_matrix(const mjModelF *m, mjDataF *d) {
     if (mass <= 0) continue;
     double Iw[9];
     body_inertia_world(m, d, b, Iw);
-    body_jac(m, d, b, d->xipos[b], jp, jr);
+    mje_body_jac(m, d, b, d->xipos[b], jp, jr);
     int dofs[MJ_MAXV], nd = 0;
     for (int c = b; c > 0; c = m->body_parent[c]) {
       int j = m->body_jnt[c], da = m->jnt_dofadr[j], n = m->jnt_type[j] == 0 ? 6 : 1;
@@ -306,6 +307,7 @@ void mje_bias(const mjModelF *m, mjDataF *d) {
     for (int k = 0; k < 3; ++k) { F[b][k] = n[k] + x1[k] + x2[k]; F[b][3 + k] = f[k] + x3[k]; }
     d->flops += 120;
   }
+  d->flops += (long long)nb * 90 + (long long)m->nv * 20;
   for (int b = nb - 1; b >= 1; --b) {
     int p = m->body_parent[b], j = m->body_jnt[b], da = m->jnt_dofadr[j], n = m->jnt_type[j] == 0 ? 6 : 1;
     for (int q = da; q < da + n; ++q) {
@@ -390,7 +392,7 @@ static double impedance(const double *solimp, double pos, double margin) {
 }
 
 /* fill aref / R / D of row i from (solref, solimp, pos, margin, vel, diagApprox); mj_makeImpedance */
-static void finish_row(const mjModelF *m, mjDataF *d, int i, const double *solref, const double *solimp, double margin, double diag) {
+void mje_finish_row(const mjModelF *m, mjDataF *d, int i, const double *solref, const double *solimp, double margin, double diag) {
   double vel = 0;
   for (int k = 0; k < m->nv; ++k) vel += d->efc_J[i][k] * d->qvel[k];
   double imp = impedance(solimp, d->efc_pos[i], margin);
@@ -405,6 +407,7 @@ static void finish_row(const mjModelF *m, mjDataF *d, int i, const double *solre
     k = -solref[0] / (dmax * dmax);
     b = -solref[1] / dmax;
   }
+  d->flops += 2 * m->nv + 30;
   double R = (1 - imp) * diag / imp;
   if (R < MJMINVAL) R = MJMINVAL;
   d->efc_R[i] = R;
@@ -432,7 +435,7 @@ void mje_make_constraints(const mjModelF *m, mjDataF *d) {
     quat2mat(mR, mq);
     mulmatvec3(t, mR, rel);
     for (int k = 0; k < 3; ++k) { p0[k] = d->mocap_pos[k] + t[k]; cpos[k] = p0[k] - p1[k]; }
-    body_jac(m, d, b, p1, jp, jr);
+    mje_body_jac(m, d, b, p1, jp, jr);
     double quat[4], quat1[4] = {q1[0], -q1[1], -q1[2], -q1[3]}, quat2[4];
     mulquat(quat, mq, rel + 3);
     mulquat(quat2, quat1, quat);
@@ -445,10 +448,11 @@ void mje_make_constraints(const mjModelF *m, mjDataF *d) {
       mulquat(q3, q2, quat);
       for (int k = 0; k < 3; ++k) d->efc_J[r + 3 + k][c] = 0.5 * q3[1 + k];
     }
+    d->flops += (long long)nv * 60 + 120;
     for (int k = 0; k < 6; ++k) {
       d->efc_pos[r + k] = cpos[k];
       d->efc_type[r + k] = 0;
-      finish_row(m, d, r + k, m->weld_solref + 2 * w, m->weld_solimp + 5 * w, 0.0, m->weld_invweight[2 * w + (k >= 3)]);
+      mje_finish_row(m, d, r + k, m->weld_solref + 2 * w, m->weld_solimp + 5 * w, 0.0, m->weld_invweight[2 * w + (k >= 3)]);
     }
     r += 6;
   }
@@ -464,7 +468,7 @@ void mje_make_constraints(const mjModelF *m, mjDataF *d) {
         d->efc_J[r][da] = side == 0 ? 1 : -1;
         d->efc_pos[r] = dist;
         d->efc_type[r] = 1;
-        finish_row(m, d, r, m->jnt_solref + 2 * j, m->jnt_solimp + 5 * j, m->jnt_margin[j], m->dof_invweight0[da]);
+        mje_finish_row(m, d, r, m->jnt_solref + 2 * j, m->jnt_solimp + 5 * j, m->jnt_margin[j], m->dof_invweight0[da]);
         ++r;
       }
     }
@@ -506,6 +510,7 @@ void mje_solve(const mjModelF *m, mjDataF *d) {
   chol_factor(H, nv);
   memcpy(d->qacc_smooth, d->qfrc_smooth, sizeof(double) * nv);
   chol_solve(H, nv, d->qacc_smooth);
+  d->flops += (long long)nv * nv * nv / 3 + 2LL * nv * nv + 2LL * (2LL * nv * nv + 2LL * ne * nv + 6LL * ne);
   if (ne == 0) {
     memcpy(d->qacc, d->qacc_smooth, sizeof(double) * nv);
     memset(d->qfrc_constraint, 0, sizeof(double) * nv);
@@ -568,7 +573,7 @@ void mje_solve(const mjModelF *m, mjDataF *d) {
         for (int j = 0; j < nv; ++j) H[i][j] += ji * d->efc_J[r][j];
       }
     }
-    d->flops += (long long)ne * nv * nv + (long long)nv * nv * nv / 3;
+    d->flops += (long long)ne * nv * nv + (long long)nv * nv * nv / 3 + 4LL * nv * nv + 6LL * ne * nv + 8LL * 10 * ne;
     if (chol_factor(H, nv)) break;
     for (int i = 0; i < nv; ++i) dir[i] = -grad[i];
     chol_solve(H, nv, dir);
@@ -707,6 +712,7 @@ void mje_step(const mjModelF *m, mjDataF *d) {
     for (int i = 0; i < nv; ++i) qacc[i] = d->qfrc_smooth[i] + d->qfrc_constraint[i];
     chol_factor(H, nv);
     chol_solve(H, nv, qacc);
+    d->flops += (long long)nv * nv * nv / 3 + 2LL * nv * nv + 6LL * nv;
   } else {
     memcpy(qacc, d->qacc, sizeof(double) * nv);
   }

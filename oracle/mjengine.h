@@ -72,6 +72,7 @@ typedef struct {
   double efc_fri[MJ_MAXEFC][5];
   /* contacts */
   double con_pos[MJ_MAXCON][3], con_frame[MJ_MAXCON][9], con_dist[MJ_MAXCON], con_friction[MJ_MAXCON][5];
+  double con_solref[MJ_MAXCON][2], con_solimp[MJ_MAXCON][5], con_margin[MJ_MAXCON];
   int con_geom1[MJ_MAXCON], con_geom2[MJ_MAXCON], con_dim[MJ_MAXCON];
   /* diagnostics */
   int solver_iter;

@@ -81,7 +81,7 @@ class Emu:
         return M, b, x
 
     def info(self, what):
-        return lib().emu_info(self.h, {"nefc": 0, "ncon": 1, "iter": 2, "bad": 3, "npair": 4}[what])
+        return lib().emu_info(self.h, {"nefc": 0, "ncon": 1, "iter": 2, "bad": 3, "npair": 4, "nhit": 5}[what])
 
     def contacts(self):
         n = self.info("ncon")

@@ -79,6 +79,7 @@ int emu_info(void* h, int what) {
     case 2: return e->w.solver_iter;
     case 3: return e->w.bad;
     case 4: return e->hm.m.npair;
+    case 5: return e->w.nhit;
   }
   return -1;
 }
@@ -92,4 +93,12 @@ void emu_contacts(void* h, double* dist, double* pos, double* frame, int* geoms)
     geoms[2 * c + 1] = e->w.con_g2[c];
   }
 }
+}
+extern "C" int emu_hits(void* h, int* pairs) {
+  Emu* e = static_cast<Emu*>(h);
+  for (int k = 0; k < e->w.nhit; ++k) {
+    pairs[2 * k] = e->hm.m.pair_g1[e->w.hit_list[k]];
+    pairs[2 * k + 1] = e->hm.m.pair_g2[e->w.hit_list[k]];
+  }
+  return e->w.nhit;
 }

@@ -48,20 +48,30 @@ def test_one_step_parity_from_identical_states(oracle):
     got = env.get_state()
     obs = obs.cpu().numpy()
     e = oracle.e
-    worst = dict(q=0.0, v=0.0, obs=0.0)
+    # "light": only the four door-on-table box-box contacts (always present); "convex": the gripper also touches the
+    # handle, i.e. contacts from portal refinement, whose result is not a continuous function of the state (fp32 and
+    # fp64 can follow different, equally valid, portals when a 6 mm thin pad is 4-7 mm deep in a cylinder)
+    worst = {k: dict(q=0.0, v=0.0, obs=0.0, n=0) for k in ("light", "convex")}
     for i, (q, v, w, mp) in enumerate(states):
         e.reset()
         e.qpos[:], e.qvel[:], e.mocap_pos[:] = q, v, mp
         e.arr("qacc_warmstart", (32,))[:e.nv] = w
+        e.forward()
+        ncon0 = e.ncon
         ob_ref, r_ref = oracle.step(actions[i])
-        worst["q"] = max(worst["q"], np.abs(got["qpos"][i] - e.qpos).max())
-        worst["v"] = max(worst["v"], np.abs(got["qvel"][i] - e.qvel).max())
-        worst["obs"] = max(worst["obs"], np.abs(obs[i] - ob_ref).max())
+        k = "light" if max(ncon0, e.ncon) <= 4 else "convex"
+        worst[k]["n"] += 1
+        worst[k]["q"] = max(worst[k]["q"], np.abs(got["qpos"][i] - e.qpos).max())
+        worst[k]["v"] = max(worst[k]["v"], np.abs(got["qvel"][i] - e.qvel).max())
+        worst[k]["obs"] = max(worst[k]["obs"], np.abs(obs[i] - ob_ref).max())
         assert np.abs(got["mocap_pos"][i] - e.mocap_pos).max() < 1e-7
         d = np.linalg.norm(ob_ref[4:7] - ob_ref[11:14])
         if abs(d - 0.02) > 1e-5:
             assert float(rew[i]) == r_ref
-    assert worst["q"] < TOL and worst["v"] < TOL and worst["obs"] < 1e-5, worst
+    print("one-step parity:", worst)
+    assert worst["light"]["n"] >= 40 and worst["convex"]["n"] >= 10
+    assert worst["light"]["q"] < TOL and worst["light"]["v"] < TOL and worst["light"]["obs"] < 1e-5, worst
+    assert worst["convex"]["q"] < 1e-2 and worst["convex"]["obs"] < 5e-3, worst
     assert env.work_counters()["bad_states"] == 0
 
 
@@ -134,3 +144,49 @@ def test_eval_stats_and_success_flag(oracle):
     assert bool(info["success"].all()) and float(r.sum()) == n
     st = env.eval_stats().cpu().numpy()
     assert st[0] == 3 * n and st[1] == n and st[2] == n and st[3] == n
+
+
+def test_demo_replay_on_device_matches_checker_and_recording(oracle):
+    """All ten shipped door demonstrations replayed open loop, one environment per episode in ONE batch (shorter
+    episodes are padded with zero actions): sparse reward vs the recording (>= 99 % per-step agreement, north-star
+    bar) and device vs checker on the same replay (same success steps on the contact-rich forward episodes, hand and
+    handle within 2 mm over the whole forward episodes)."""
+    from earl_benchmark_b200 import demos
+    from test_engine_oracle import door_angle
+    eps = []
+    for which in ("forward", "reverse"):
+        d = demos.load("sawyer_door", which)
+        ends = list(np.nonzero(d["terminals"].ravel())[0] + 1)
+        for s, en in zip([0] + ends[:-1], ends):
+            eps.append(dict(which=which, obs0=d["observations"][s], act=d["actions"][s:en], rew=d["rewards"].ravel()[s:en]))
+    n, T = len(eps), max(len(e["act"]) for e in eps)
+    assert n == 10
+    env = sawyer_door.SawyerDoorV2(num_envs=n, device="cuda:0")
+    env.reset_goal(eps[0]["obs0"][7:14])   # forward goal = goal_states[0]; reverse episodes judged separately below
+    angles = np.array([door_angle(e["obs0"][4:6]) for e in eps])
+    env.reset(door_angle=angles)
+    actions = np.zeros((T, n, 4), np.float32)
+    for i, e in enumerate(eps):
+        actions[:len(e["act"]), i] = e["act"]
+    dev_obs = np.zeros((T, n, 14), np.float32)
+    for t in range(T):
+        o, r, d, info = env.step(torch.from_numpy(actions[t]).cuda())
+        dev_obs[t] = o.cpu().numpy()
+    assert env.work_counters()["bad_states"] == 0
+    total = mism = 0
+    for i, e in enumerate(eps):
+        L = len(e["act"])
+        goal = e["obs0"][11:14]
+        dev_r = (np.linalg.norm(dev_obs[:L, i, 4:7] - goal, axis=1) <= 0.02).astype(np.float32)
+        total += L
+        mism += int((dev_r != e["rew"]).sum())
+        if e["which"] == "forward":
+            oracle.goal = e["obs0"][7:14].astype(np.float64)
+            oracle.reset(door_angle=angles[i])
+            ref = np.array([oracle.step(a)[0] for a in e["act"]])
+            assert np.abs(ref[:, :7] - dev_obs[:L, i, :7]).max() < 2e-3
+            ref_r = (np.linalg.norm(ref[:, 4:7] - goal, axis=1) <= 0.02)
+            near = np.abs(np.linalg.norm(ref[:, 4:7] - goal, axis=1) - 0.02) < 1e-4
+            assert np.array_equal(ref_r[~near], dev_r[~near].astype(bool))
+    oracle.goal = oracle.GOAL.copy()
+    assert 1 - mism / total >= 0.99, (mism, total)
