@@ -16,6 +16,9 @@ One JSON line on stdout (rank 0):
   roofline     HBM roofline of the step kernel: 113 algorithmic bytes per env-step
   cpu_baseline the CPU oracle (C port of the reference arithmetic, OpenMP, all host threads) on a bounded
                sample of the same workload (rank 0, N=1 only)
+  sawyer_door  second section (BASELINE.json configs[2]): batched Sawyer door step, 65,536 envs per GPU, random
+               actions; env-steps/s, e2e with host buffers, FP32-issue roofline from the checker's flop count, CPU
+               baseline (fp64 C restatement of the engine, one process per host core)
 `--impl reference` times that CPU port alone on the same config (the reference itself is Python over
 mujoco-py and cannot run on the GPU box).
 """
@@ -130,6 +133,99 @@ def cpu_port_rate(num_envs, steps, threads, budget_s=20.0):
         n_sample = min(num_envs, n_sample)
     el = run(n_sample, steps)
     return n_sample * steps / el, n_sample, el
+
+
+# ----------------------------------------------------------------------------------------------- Sawyer door (config 3)
+
+DOOR_ENVS, DOOR_STEPS, DOOR_WARMUP, DOOR_RING = 1 << 16, 30, 5, 16
+
+
+def door_cpu_rate(procs, steps_per_proc=20000):
+    """env-steps/s of the fp64 checker on `procs` host processes (oracle/door_cpu_bench.py, one checker instance each:
+    oracle/mjengine.c keeps static scratch, so it is not thread-safe), and its flop count per env step -- the
+    ALGORITHMIC flops of SURVEY.md 8d, counted inside the checker on the same random-action workload."""
+    script = os.path.join(REPO, "oracle", "door_cpu_bench.py")
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    subprocess.check_call([sys.executable, script, "0", "5"], stdout=subprocess.DEVNULL, env=env)  # builds the checker once
+    t0 = time.perf_counter()
+    ps = [subprocess.Popen([sys.executable, script, str(100 + k), str(steps_per_proc)], stdout=subprocess.PIPE, text=True, env=env)
+          for k in range(procs)]
+    res = [json.loads(p.communicate()[0].strip().splitlines()[-1]) for p in ps]
+    wall = time.perf_counter() - t0
+    loop = max(r["seconds"] for r in res)
+    flops = sum(r["flops_per_env_step"] for r in res) / len(res)
+    return procs * steps_per_proc / loop, flops, wall
+
+
+def run_door(dev, rank, world, sm_max_mhz, sm_count, with_cpu):
+    """Second bench section: batched sawyer_door step (BASELINE.json configs[2]), 65,536 envs per GPU, random actions."""
+    import torch
+    import torch.distributed as dist
+
+    from earl_benchmark_b200.distributed import max_over_ranks
+    from earl_benchmark_b200.envs import sawyer_door
+
+    n = DOOR_ENVS
+    env = sawyer_door.SawyerDoorV2(num_envs=n, device=dev, seed=rank)
+    env.reset()
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(4321 + rank)
+    actions = torch.rand((DOOR_RING, n, 4), generator=gen, device=dev, dtype=torch.float32) * 2 - 1
+    for t in range(DOOR_WARMUP):
+        env.step(actions[t % DOOR_RING])
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    w0 = env.work_counters()
+    l0 = env.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for t in range(DOOR_STEPS):
+        env.step(actions[t % DOOR_RING])
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = max_over_ranks(e0.elapsed_time(e1), dev)
+    w1 = env.work_counters()
+    launches = env.launch_count - l0
+    # end to end with host buffers
+    host_a = (torch.rand((n, 4), dtype=torch.float32) * 2 - 1).pin_memory()
+    env.step(host_a)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(5):
+        env.step(host_a)
+    e2e_s = max_over_ranks(time.perf_counter() - t0, dev)
+    out = None
+    if rank == 0:
+        sub = max(1, w1["substeps"] - w0["substeps"])
+        value = n * world * DOOR_STEPS / (ms * 1e-3)
+        out = {"metric": "batched env-steps/sec (sawyer_door, sparse, 5 substeps per env step)", "value": value, "unit": UNIT,
+               "envs_per_gpu": n, "steps": DOOR_STEPS, "warmup": DOOR_WARMUP, "ms_per_step": ms / DOOR_STEPS,
+               "dtype": "f32", "gpu_launches": launches,
+               "e2e": {"value": n * world * 5 / e2e_s, "unit": UNIT, "h2d_bytes_per_step": n * 16 * world,
+                       "d2h_bytes_per_step": n * (14 * 4 + 4 + 1 + 1) * world, "steps": 5},
+               "work": {"newton_iterations_per_substep": (w1["newton_iterations"] - w0["newton_iterations"]) / sub,
+                        "constraint_rows_per_substep": (w1["constraint_rows"] - w0["constraint_rows"]) / sub,
+                        "contacts_per_substep": (w1["contacts"] - w0["contacts"]) / sub,
+                        "bad_states": w1["bad_states"] - w0["bad_states"]},
+               "kernel": "mj_step_kernel (one warp per env, 16 envs per SM in flight)"}
+        if with_cpu:
+            procs = os.cpu_count() or 1
+            rate, flops, wall = door_cpu_rate(procs)
+            peak = sm_count * 128 * 2 * (sm_max_mhz or 1965.0) * 1e6 / 1e12
+            ach = flops * (value / world) / 1e12
+            out["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": procs, "kind": "port",
+                                   "sample": f"{procs} processes x 20000 env steps of the same random-action workload, fp64 "
+                                             f"C restatement of the engine (not MuJoCo), {wall:.1f} s"}
+            out["roofline"] = {"bound": "fp32", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+                               "traffic": None, "algorithmic_flops_per_env_step": flops,
+                               "peak_source": f"{sm_count} SMs x 128 lanes x 2 x {sm_max_mhz or 1965.0:.0f} MHz (nominal FP32 FMA issue)",
+                               "note": "algorithmic flops = the checker's own flop counter on the same workload; the kernel is "
+                                       "latency / instruction-issue bound on per-env serial chains, not FMA bound"}
+    del env
+    return out
 
 
 def run_reference(args):
@@ -265,6 +361,12 @@ def run_ours(args):
                "kernel": "earl::tabletop_step_tma_kernel<3,256>  (cp.async.bulk pipeline)"}
         del a_b, o_b, r_b, d_b, tb, lb
 
+    door = None
+    if not args.profile and not args.no_door:
+        props = torch.cuda.get_device_properties(dev)
+        door = run_door(dev, rank, world, (clocks or {}).get("sm_max_mhz"), props.multi_processor_count,
+                        with_cpu=(world == 1 and not args.no_cpu_baseline))
+
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
         if big is not None:
@@ -289,6 +391,8 @@ def run_ours(args):
                 "clocks": clocks}
         if big is not None:
             line["hbm_bound_check"] = big
+        if door is not None:
+            line["sawyer_door"] = door
         if world == 1 and not args.no_cpu_baseline and not args.profile:
             threads = os.cpu_count() or 1
             rate, n_sample, el = cpu_port_rate(n, min(args.steps, 200), threads, budget_s=15.0)
@@ -312,6 +416,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-hbm-check", action="store_true", help="skip the 8M-env all-HBM operating point")
+    ap.add_argument("--no-door", action="store_true", help="skip the sawyer_door section")
     ap.add_argument("--profile", action="store_true", help="under ncu: no sustained warm-up, 1 e2e step, no CPU leg")
     ap.add_argument("--traffic-bytes", type=float, default=None,
                     help="dram bytes per launch from the committed ncu capture; default: profiles/r01 value for the "

@@ -462,6 +462,38 @@ MJ_HD real point_box_dist2(const real* c, const real* p, const real* R, const re
   return d2;
 }
 
+// Conservative cull: true when the bounding boxes of the two geoms (centres ca / cb, axes = columns of Ra / Rb, half
+// sizes sa / sb) are separated by more than `margin` along one of the 15 candidate axes.  The boxes contain the
+// geoms, so a separated pair cannot produce a contact.
+MJ_FN int obb_separated(const real* ca, const real* Ra, const real* sa, const real* cb, const real* Rb, const real* sb, real margin) {
+  real pp[3], Rm[3][3], Q[3][3], pA[3];
+  sub3(pp, cb, ca);
+  for (int i = 0; i < 3; ++i) {
+    pA[i] = pp[0] * Ra[i] + pp[1] * Ra[3 + i] + pp[2] * Ra[6 + i];
+    for (int j = 0; j < 3; ++j) {
+      Rm[i][j] = Ra[i] * Rb[j] + Ra[3 + i] * Rb[3 + j] + Ra[6 + i] * Rb[6 + j];
+      Q[i][j] = fabsf(Rm[i][j]) + 1e-6f;
+    }
+  }
+  for (int i = 0; i < 3; ++i)
+    if (fabsf(pA[i]) - (sa[i] + sb[0] * Q[i][0] + sb[1] * Q[i][1] + sb[2] * Q[i][2]) > margin) return 1;
+  for (int j = 0; j < 3; ++j) {
+    const real pB = pA[0] * Rm[0][j] + pA[1] * Rm[1][j] + pA[2] * Rm[2][j];
+    if (fabsf(pB) - (sb[j] + sa[0] * Q[0][j] + sa[1] * Q[1][j] + sa[2] * Q[2][j]) > margin) return 1;
+  }
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) {
+      const int i1 = (i + 1) % 3, i2 = (i + 2) % 3, j1 = (j + 1) % 3, j2 = (j + 2) % 3;
+      // axis A_i x B_j (unnormalised, length l): separation test scaled by l, skipped for near-parallel axes
+      const real l2 = 1.0f - Rm[i][j] * Rm[i][j];
+      if (l2 < 1e-4f) continue;
+      const real d = fabsf(pA[i2] * Rm[i1][j] - pA[i1] * Rm[i2][j]);
+      const real r = sa[i1] * Q[i2][j] + sa[i2] * Q[i1][j] + sb[j1] * Q[i][j2] + sb[j2] * Q[i][j1];
+      if (d - r > margin * sqrtf(l2) + 1e-6f) return 1;
+    }
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------------------ driver
 // append `flag`-ed items of one lane-strided pass to a compact list, in item order (deterministic on every path)
 template <int NL>
@@ -513,6 +545,15 @@ MJ_FN void collide(const Model& m, const real* hull, Work& w, int lane) {
         if (hit && t2 == GEOM_BOX) {
           const real r = m.geom_rbound[ga] + margin;
           hit = point_box_dist2(pa, pb, gmat(m, w, gb), m.geom_size[gb]) <= r * r;
+        }
+        if (hit) {  // bounding-box cull
+          const real* Ra = gmat(m, w, ga);
+          const real* Rb = gmat(m, w, gb);
+          real ca[3], cb[3];
+          mulmatvec3(ca, Ra, m.geom_obb_off[ga]);
+          mulmatvec3(cb, Rb, m.geom_obb_off[gb]);
+          for (int k = 0; k < 3; ++k) { ca[k] += pa[k]; cb[k] += pb[k]; }
+          hit = !obb_separated(ca, Ra, m.geom_obb_size[ga], cb, Rb, m.geom_obb_size[gb], margin);
         }
       }
     }

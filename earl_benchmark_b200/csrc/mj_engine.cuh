@@ -94,6 +94,7 @@ struct Model {
   int nmgeom, mgeom[MAXMG];
   real geom_size[MAXG][3], geom_pos[MAXG][3], geom_mat[MAXG][9], geom_friction[MAXG][3], geom_margin[MAXG], geom_gap[MAXG];
   real geom_solref[MAXG][2], geom_solimp[MAXG][5], geom_solmix[MAXG], geom_invweight0[MAXG][2], geom_rbound[MAXG];
+  real geom_obb_size[MAXG][3], geom_obb_off[MAXG][3];  // bounding box in the geom frame (box: itself; cylinder: r,r,h; mesh: hull AABB)
   // candidate collision pairs (compile-time filtered: contype/conaffinity, same body, parent-child)
   int pair_g1[MAXPAIR], pair_g2[MAXPAIR];
   // task constants

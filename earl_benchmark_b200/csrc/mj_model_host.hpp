@@ -168,13 +168,10 @@ inline bool build_model(const void* blob, size_t nbytes, const TaskSpec& task, H
 #define RI(dst) do { if (rd.field(&I, 4) != 1) return bad("model blob: scalar int field"); dst = I[0]; } while (0)
 #define RD(dst) do { if (rd.field(&D, 8) != 1) return bad("model blob: scalar double field"); dst = (real)D[0]; } while (0)
   int nhullvert = 0, cone_elliptic = 0;
-  double tolerance = 0;
   RI(m.nbody); RI(m.nq); RI(m.nv); RI(m.ngeom); RI(m.nsite); RI(m.nu); RI(m.nweld); RI(nhullvert); RI(m.iterations);
   RI(cone_elliptic);
   RD(m.timestep);
-  if (rd.field(&D, 8) != 1) return bad("tolerance");
-  tolerance = D[0];
-  (void)tolerance;
+  if (rd.field(&D, 8) != 1) return bad("tolerance");  // <option tolerance>: the fp32 solver uses its own termination rule
   RD(m.impratio);
   if (!cone_elliptic) return bad("model blob: only elliptic friction cones are built");
   if (m.nbody > MAXB || m.nv > MAXV || m.nq > MAXQ || m.ngeom > MAXG || m.nsite > MAXS || m.nu > MAXU || m.nweld > MAXW)
@@ -299,6 +296,24 @@ inline bool build_model(const void* blob, size_t nbytes, const TaskSpec& task, H
       m.dof_rot[da] = m.jnt_type[j] == 3;
       m.dof_parent[da] = pd;
     }
+  }
+  // bounding boxes in the geom frames (broad-phase cull)
+  for (int g = 0; g < ng; ++g) {
+    real* sz = m.geom_obb_size[g];
+    real* off = m.geom_obb_off[g];
+    off[0] = off[1] = off[2] = 0;
+    if (m.geom_type[g] == GEOM_BOX) { for (int k = 0; k < 3; ++k) sz[k] = m.geom_size[g][k]; }
+    else if (m.geom_type[g] == GEOM_CYLINDER) { sz[0] = sz[1] = m.geom_size[g][0]; sz[2] = m.geom_size[g][1]; }
+    else if (m.geom_type[g] == GEOM_MESH && m.geom_hullnum[g] > 0) {
+      real lo[3] = {1e30f, 1e30f, 1e30f}, hi[3] = {-1e30f, -1e30f, -1e30f};
+      for (int v = 0; v < m.geom_hullnum[g]; ++v)
+        for (int k = 0; k < 3; ++k) {
+          const real x = out->hull_vert[3 * (m.geom_hulladr[g] + v) + k];
+          lo[k] = x < lo[k] ? x : lo[k];
+          hi[k] = x > hi[k] ? x : hi[k];
+        }
+      for (int k = 0; k < 3; ++k) { sz[k] = 0.5f * (hi[k] - lo[k]); off[k] = 0.5f * (hi[k] + lo[k]); }
+    } else { sz[0] = sz[1] = sz[2] = m.geom_rbound[g]; }
   }
   // geoms on moving bodies get a pose slot; static geoms keep their constant world pose in geom_pos / geom_mat
   m.nmgeom = 0;
