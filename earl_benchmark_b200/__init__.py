@@ -27,7 +27,7 @@ continuing_eval_config = {
     'minitaur': {'num_initial_state_samples': 1, 'num_goals': 4, 'train_horizon': int(1e5), 'goal_change_frequency': 2000},
 }
 
-_BUILT = ("tabletop_manipulation", "sawyer_door")
+_BUILT = ("tabletop_manipulation", "sawyer_door", "sawyer_peg")
 
 
 def shard_range(num_envs, rank, world_size):
@@ -100,6 +100,11 @@ class EARLEnvs(object):
             train_env = sawyer_door.SawyerDoorV2(reward_type=self._reward_type,
                                                  reset_at_goal=self._reset_train_env_at_goal,
                                                  eval_stats=False, **self._shard_kwargs(0))
+        elif self._env_name == 'sawyer_peg':
+            from .envs import sawyer_peg
+            train_env = sawyer_peg.SawyerPegV2(reward_type=self._reward_type,
+                                               reset_at_goal=self._reset_train_env_at_goal,
+                                               eval_stats=False, **self._shard_kwargs(0))
         else:
             deployment_eval_config[self._env_name]  # KeyError for unknown names
             self._not_built()
@@ -122,6 +127,10 @@ class EARLEnvs(object):
             from .envs import sawyer_door
             eval_env = sawyer_door.SawyerDoorV2(reward_type=self._reward_type,
                                                 eval_stats=self._kwargs.get('eval_stats', True), **self._shard_kwargs(1))
+        elif self._env_name == 'sawyer_peg':
+            from .envs import sawyer_peg
+            eval_env = sawyer_peg.SawyerPegV2(reward_type=self._reward_type,
+                                              eval_stats=self._kwargs.get('eval_stats', True), **self._shard_kwargs(1))
         else:
             self._not_built()
         return persistent_state_wrapper.PersistentStateWrapper(eval_env, episode_horizon=self._eval_horizon)
@@ -142,6 +151,9 @@ class EARLEnvs(object):
         if self._env_name == 'sawyer_door':
             from .envs import sawyer_door
             return sawyer_door.initial_states
+        if self._env_name == 'sawyer_peg':
+            from .envs import sawyer_peg
+            return sawyer_peg.initial_states
         self._not_built()
 
     def get_goal_states(self):
@@ -151,6 +163,9 @@ class EARLEnvs(object):
         if self._env_name == 'sawyer_door':
             from .envs import sawyer_door
             return sawyer_door.goal_states
+        if self._env_name == 'sawyer_peg':
+            from .envs import sawyer_peg
+            return sawyer_peg.goal_states
         self._not_built()
 
     def get_demonstrations(self):

@@ -68,7 +68,7 @@ struct StepArgs {
   const uint8_t* mask;
   const double* obj_qpos;
   const int* goal_idx;
-  int obj_qadr, obj_dadr;
+  int obj_qadr, obj_dadr, obj_nq_set, obj_nv;
   // settle
   double hand_init[3];
   float ctrl[2];
@@ -185,7 +185,10 @@ __global__ void __launch_bounds__(kWPB * 32, 1) mj_reset_kernel(const StepArgs a
     float* rec = a.state + (size_t)env * REC_FLOATS;
     load_env(w, mode == 0 ? a.tmpl : rec, lane);
     if (mode == 0 && lane == 0) {
-      if (a.obj_qpos) { w.qpos[a.obj_qadr] = (float)a.obj_qpos[env]; w.qvel[a.obj_dadr] = 0.0f; }  // _set_obj_xyz
+      if (a.obj_qpos) {  // _set_obj_xyz: leading qpos entries of the object joint, zero velocity on all its dofs
+        for (int k = 0; k < a.obj_nq_set; ++k) w.qpos[a.obj_qadr + k] = (float)a.obj_qpos[(size_t)env * a.obj_nq_set + k];
+        for (int k = 0; k < a.obj_nv; ++k) w.qvel[a.obj_dadr + k] = 0.0f;
+      }
       w.goalrow = a.goal_idx ? (unsigned)a.goal_idx[env] : 0u;
       w.steps = 0;
       w.flags = 0;
@@ -252,7 +255,7 @@ struct earl_mj_handle {
   earl_mj_config cfg{};
   HostModel hm;
   int device = 0, sm_count = 0, grid = 0;
-  int obj_qadr = -1, obj_dadr = -1;
+  int obj_qadr = -1, obj_dadr = -1, obj_nv = 0;
   bool have_template = false;
   int64_t total_steps = 0, launches = 0;
   std::vector<void*> owned;
@@ -299,8 +302,8 @@ int earl_mj_create(const earl_mj_config* cfg, const void* model_blob, size_t mod
                    earl_mj_handle** out) {
   if (!cfg || !out || !task || !model_blob) return failf(EARL_ERR_INVALID, "null argument");
   *out = nullptr;
-  if (cfg->env_kind != EARL_ENV_SAWYER_DOOR)
-    return failf(EARL_ERR_UNSUPPORTED, "env_kind %d is not built yet on the articulated-body engine (only sawyer_door)", cfg->env_kind);
+  if (cfg->env_kind != EARL_ENV_SAWYER_DOOR && cfg->env_kind != EARL_ENV_SAWYER_PEG)
+    return failf(EARL_ERR_UNSUPPORTED, "env_kind %d is not built on the articulated-body engine (sawyer_door, sawyer_peg)", cfg->env_kind);
   if (cfg->num_envs < 1) return failf(EARL_ERR_INVALID, "num_envs must be >= 1");
   if (cfg->episode_horizon < 1) return failf(EARL_ERR_INVALID, "episode_horizon must be >= 1");
   if (cfg->flags & ~(uint32_t)(EARL_FLAG_EVAL_STATS)) return failf(EARL_ERR_UNSUPPORTED, "unsupported flags %#x", cfg->flags);
@@ -328,6 +331,9 @@ int earl_mj_create(const earl_mj_config* cfg, const void* model_blob, size_t mod
     const int j = m.body_jnt[b];
     h->obj_qadr = m.jnt_qposadr[j];
     h->obj_dadr = m.jnt_dofadr[j];
+    h->obj_nv = m.jnt_type[j] == 0 ? 6 : 1;
+    const int nq_j = m.jnt_type[j] == 0 ? 7 : 1;
+    if (ts.obj_qpos_count < 1 || ts.obj_qpos_count > nq_j) { delete h; return failf(EARL_ERR_INVALID, "obj_qpos_count %d does not fit the object joint", ts.obj_qpos_count); }
   }
   cudaDeviceProp prop;
   cudaError_t e = cudaGetDeviceProperties(&prop, cfg->device);
@@ -366,6 +372,8 @@ int earl_mj_create(const earl_mj_config* cfg, const void* model_blob, size_t mod
   a.flags = cfg->flags;
   a.obj_qadr = h->obj_qadr;
   a.obj_dadr = h->obj_dadr;
+  a.obj_nq_set = ts.obj_qpos_count;
+  a.obj_nv = h->obj_nv;
   *out = h;
   return 0;
 }

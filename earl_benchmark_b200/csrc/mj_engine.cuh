@@ -45,7 +45,7 @@ constexpr int MAXG = 32;    // geoms kept on the device
 constexpr int MAXS = 8;     // sites kept on the device
 constexpr int MAXU = 2;     // actuators
 constexpr int MAXW = 1;     // welds
-constexpr int MAXEFC = 48;  // constraint rows
+constexpr int MAXEFC = 64;  // constraint rows
 constexpr int MAXCON = 12;  // contacts
 constexpr int MAXPAIR = 192; // candidate geom pairs
 constexpr int MAXMG = 16;    // geoms on moving bodies (their world poses are recomputed every substep)
@@ -123,18 +123,24 @@ struct Work {
   // kinematics
   real xpos[MAXB][3], xquat[MAXB][4], xmat[MAXB][9], xipos[MAXB][3];
   real dof_axis[MAXV][3], dof_anchor[MAXV][3];
-  // composite inertias (about the composite CoM, world axes)
-  real c_mass[MAXB], c_com[MAXB][3], c_I[MAXB][6];
-  // Newton-Euler scratch: angular velocity / acceleration, linear velocity / acceleration of the body origin,
-  // wrench (force, torque about the body origin)
-  real b_w[MAXB][3], b_v[MAXB][3], b_al[MAXB][3], b_a[MAXB][3], b_F[MAXB][3], b_N[MAXB][3];
-  // dense matrices
-  real M[MAXV][LDM], H[MAXV][LDM];
+  // dense matrices.  H doubles as scratch while it is idle: narrow-phase scratch during collision (mj_collide.cuh) and
+  // the Newton-Euler pass (angular velocity / acceleration, linear velocity / acceleration of the body origin, wrench
+  // about the body origin) between the constraint rows and the solve.
+  real M[MAXV][LDM];
+  union {
+    real H[MAXV][LDM];
+    struct { real b_w[MAXB][3], b_v[MAXB][3], b_al[MAXB][3], b_a[MAXB][3], b_F[MAXB][3], b_N[MAXB][3]; } rne;
+  };
   // dof vectors
   real bias[MAXV], smooth[MAXV], acc[MAXV], Ma[MAXV], grad[MAXV], dir[MAXV], fcon[MAXV], tmp[MAXV];
   // constraint rows
   int nefc, ncon;
-  real J[MAXEFC][MAXV];
+  // the Jacobian is written after collision; before that its storage holds the composite inertias of the mass-matrix
+  // pass (about the composite CoM, world axes)
+  union {
+    real J[MAXEFC][MAXV];
+    struct { real c_mass[MAXB], c_com[MAXB][3], c_I[MAXB][6]; } crb;
+  };
   real e_pos[MAXEFC], e_aref[MAXEFC], e_D[MAXEFC], e_R[MAXEFC], e_jar[MAXEFC], e_jv[MAXEFC], e_force[MAXEFC];
   int e_type[MAXEFC], e_state[MAXEFC];
   // collision
@@ -334,10 +340,10 @@ template <int NL>
 MJ_FN void mass_matrix(const Model& m, Work& w, int lane) {
   const int nb = m.nbody, nv = m.nv;
   for (int b = 1 + lane; b < nb; b += NL) {
-    w.c_mass[b] = m.body_mass[b];
-    for (int k = 0; k < 3; ++k) w.c_com[b][k] = w.xipos[b][k];
-    if (m.body_mass[b] > 0) body_inertia_world(m, w, b, w.c_I[b]);
-    else for (int k = 0; k < 6; ++k) w.c_I[b][k] = 0;
+    w.crb.c_mass[b] = m.body_mass[b];
+    for (int k = 0; k < 3; ++k) w.crb.c_com[b][k] = w.xipos[b][k];
+    if (m.body_mass[b] > 0) body_inertia_world(m, w, b, w.crb.c_I[b]);
+    else for (int k = 0; k < 6; ++k) w.crb.c_I[b][k] = 0;
   }
   for (int i = lane; i < nv; i += NL)
     for (int j = 0; j < nv; ++j) w.M[i][j] = 0;
@@ -346,45 +352,45 @@ MJ_FN void mass_matrix(const Model& m, Work& w, int lane) {
   for (int b = nb - 1; b >= 1; --b) {
     const int p = m.body_parent[b];
     if (p <= 0) continue;
-    const real m1 = w.c_mass[p], m2 = w.c_mass[b], mt = m1 + m2;
+    const real m1 = w.crb.c_mass[p], m2 = w.crb.c_mass[b], mt = m1 + m2;
     if (m2 <= 0) continue;
     real c[3], d1[3], d2[3];
     for (int k = 0; k < 3; ++k) {
-      c[k] = (m1 * w.c_com[p][k] + m2 * w.c_com[b][k]) / mt;
-      d1[k] = w.c_com[p][k] - c[k];
-      d2[k] = w.c_com[b][k] - c[k];
+      c[k] = (m1 * w.crb.c_com[p][k] + m2 * w.crb.c_com[b][k]) / mt;
+      d1[k] = w.crb.c_com[p][k] - c[k];
+      d2[k] = w.crb.c_com[b][k] - c[k];
     }
     const real s1 = dot3(d1, d1), s2 = dot3(d2, d2);
     real I[6];
-    I[0] = w.c_I[p][0] + w.c_I[b][0] + m1 * (s1 - d1[0] * d1[0]) + m2 * (s2 - d2[0] * d2[0]);
-    I[1] = w.c_I[p][1] + w.c_I[b][1] + m1 * (s1 - d1[1] * d1[1]) + m2 * (s2 - d2[1] * d2[1]);
-    I[2] = w.c_I[p][2] + w.c_I[b][2] + m1 * (s1 - d1[2] * d1[2]) + m2 * (s2 - d2[2] * d2[2]);
-    I[3] = w.c_I[p][3] + w.c_I[b][3] - m1 * d1[0] * d1[1] - m2 * d2[0] * d2[1];
-    I[4] = w.c_I[p][4] + w.c_I[b][4] - m1 * d1[0] * d1[2] - m2 * d2[0] * d2[2];
-    I[5] = w.c_I[p][5] + w.c_I[b][5] - m1 * d1[1] * d1[2] - m2 * d2[1] * d2[2];
+    I[0] = w.crb.c_I[p][0] + w.crb.c_I[b][0] + m1 * (s1 - d1[0] * d1[0]) + m2 * (s2 - d2[0] * d2[0]);
+    I[1] = w.crb.c_I[p][1] + w.crb.c_I[b][1] + m1 * (s1 - d1[1] * d1[1]) + m2 * (s2 - d2[1] * d2[1]);
+    I[2] = w.crb.c_I[p][2] + w.crb.c_I[b][2] + m1 * (s1 - d1[2] * d1[2]) + m2 * (s2 - d2[2] * d2[2]);
+    I[3] = w.crb.c_I[p][3] + w.crb.c_I[b][3] - m1 * d1[0] * d1[1] - m2 * d2[0] * d2[1];
+    I[4] = w.crb.c_I[p][4] + w.crb.c_I[b][4] - m1 * d1[0] * d1[2] - m2 * d2[0] * d2[2];
+    I[5] = w.crb.c_I[p][5] + w.crb.c_I[b][5] - m1 * d1[1] * d1[2] - m2 * d2[1] * d2[2];
     wsync<NL>();
-    w.c_mass[p] = mt;
-    for (int k = 0; k < 3; ++k) w.c_com[p][k] = c[k];
-    for (int k = 0; k < 6; ++k) w.c_I[p][k] = I[k];
+    w.crb.c_mass[p] = mt;
+    for (int k = 0; k < 3; ++k) w.crb.c_com[p][k] = c[k];
+    for (int k = 0; k < 6; ++k) w.crb.c_I[p][k] = I[k];
     wsync<NL>();
   }
   // one lane per dof i: wrench of a unit acceleration of dof i on its composite body, projected on ancestor dofs
   for (int i = lane; i < nv; i += NL) {
     const int b = m.dof_body[i];
-    const real mass = w.c_mass[b];
+    const real mass = w.crb.c_mass[b];
     real F[3], N[3];  // force, torque about the composite CoM
     if (m.dof_rot[i]) {
-      real r[3] = {w.c_com[b][0] - w.dof_anchor[i][0], w.c_com[b][1] - w.dof_anchor[i][1], w.c_com[b][2] - w.dof_anchor[i][2]};
+      real r[3] = {w.crb.c_com[b][0] - w.dof_anchor[i][0], w.crb.c_com[b][1] - w.dof_anchor[i][1], w.crb.c_com[b][2] - w.dof_anchor[i][2]};
       cross3(F, w.dof_axis[i], r);
       F[0] *= mass; F[1] *= mass; F[2] *= mass;
-      sym6_mulvec(N, w.c_I[b], w.dof_axis[i]);
+      sym6_mulvec(N, w.crb.c_I[b], w.dof_axis[i]);
     } else {
       for (int k = 0; k < 3; ++k) { F[k] = mass * w.dof_axis[i][k]; N[k] = 0; }
     }
     for (int j = i; j >= 0; j = m.dof_parent[j]) {
       real v;
       if (m.dof_rot[j]) {
-        real r[3] = {w.c_com[b][0] - w.dof_anchor[j][0], w.c_com[b][1] - w.dof_anchor[j][1], w.c_com[b][2] - w.dof_anchor[j][2]};
+        real r[3] = {w.crb.c_com[b][0] - w.dof_anchor[j][0], w.crb.c_com[b][1] - w.dof_anchor[j][1], w.crb.c_com[b][2] - w.dof_anchor[j][2]};
         real t[3];
         cross3(t, r, F);
         v = dot3(w.dof_axis[j], N) + dot3(w.dof_axis[j], t);
@@ -405,13 +411,13 @@ template <int NL>
 MJ_FN void bias_forces(const Model& m, Work& w, int lane) {
   const int nb = m.nbody, nv = m.nv;
   for (int k = 0; k < 3; ++k) {
-    w.b_w[0][k] = 0; w.b_v[0][k] = 0; w.b_al[0][k] = 0; w.b_a[0][k] = -m.gravity[k];
+    w.rne.b_w[0][k] = 0; w.rne.b_v[0][k] = 0; w.rne.b_al[0][k] = 0; w.rne.b_a[0][k] = -m.gravity[k];
   }
   wsync<NL>();
   for (int b = 1; b < nb; ++b) {  // forward pass (serial chain, redundant across lanes)
     const int p = m.body_parent[b], j = m.body_jnt[b], da = m.jnt_dofadr[j], jt = m.jnt_type[j];
     real om[3], al[3], v[3], a[3];
-    for (int k = 0; k < 3; ++k) { om[k] = w.b_w[p][k]; al[k] = w.b_al[p][k]; }
+    for (int k = 0; k < 3; ++k) { om[k] = w.rne.b_w[p][k]; al[k] = w.rne.b_al[p][k]; }
     if (jt == 3) {
       const real qd = w.qvel[da];
       const real* ax = w.dof_axis[da];
@@ -419,10 +425,10 @@ MJ_FN void bias_forces(const Model& m, Work& w, int lane) {
       // anchor as a point of the parent
       real r[3] = {an[0] - w.xpos[p][0], an[1] - w.xpos[p][1], an[2] - w.xpos[p][2]}, t[3], t2[3], vP[3], aP[3];
       cross3(t, om, r);
-      for (int k = 0; k < 3; ++k) vP[k] = w.b_v[p][k] + t[k];
+      for (int k = 0; k < 3; ++k) vP[k] = w.rne.b_v[p][k] + t[k];
       cross3(t2, om, t);
       cross3(t, al, r);
-      for (int k = 0; k < 3; ++k) aP[k] = w.b_a[p][k] + t[k] + t2[k];
+      for (int k = 0; k < 3; ++k) aP[k] = w.rne.b_a[p][k] + t[k] + t2[k];
       // joint
       cross3(t, om, ax);
       for (int k = 0; k < 3; ++k) { al[k] += t[k] * qd; om[k] += ax[k] * qd; }
@@ -437,18 +443,18 @@ MJ_FN void bias_forces(const Model& m, Work& w, int lane) {
       const real* ax = w.dof_axis[da];
       real r[3] = {w.xpos[b][0] - w.xpos[p][0], w.xpos[b][1] - w.xpos[p][1], w.xpos[b][2] - w.xpos[p][2]}, t[3], t2[3], t3[3];
       cross3(t, om, r);
-      for (int k = 0; k < 3; ++k) v[k] = w.b_v[p][k] + t[k] + ax[k] * qd;
+      for (int k = 0; k < 3; ++k) v[k] = w.rne.b_v[p][k] + t[k] + ax[k] * qd;
       cross3(t2, om, t);
       cross3(t, al, r);
       cross3(t3, om, ax);
-      for (int k = 0; k < 3; ++k) a[k] = w.b_a[p][k] + t[k] + t2[k] + 2 * t3[k] * qd;
+      for (int k = 0; k < 3; ++k) a[k] = w.rne.b_a[p][k] + t[k] + t2[k] + 2 * t3[k] * qd;
     } else {  // free joint: velocities are given in the world (translation) and body (rotation) frames
       real wl[3] = {w.qvel[da + 3], w.qvel[da + 4], w.qvel[da + 5]};
       mulmatvec3(om, w.xmat[b], wl);  // world angular velocity
       for (int k = 0; k < 3; ++k) { v[k] = w.qvel[da + k]; al[k] = 0; a[k] = -m.gravity[k]; }
       // body-axis rotational dofs: axis_k_dot = om x axis_k, summed over k with qd_k gives om x om = 0
     }
-    for (int k = 0; k < 3; ++k) { w.b_w[b][k] = om[k]; w.b_al[b][k] = al[k]; w.b_v[b][k] = v[k]; w.b_a[b][k] = a[k]; }
+    for (int k = 0; k < 3; ++k) { w.rne.b_w[b][k] = om[k]; w.rne.b_al[b][k] = al[k]; w.rne.b_v[b][k] = v[k]; w.rne.b_a[b][k] = a[k]; }
     wsync<NL>();
   }
   // wrench of each body about its own origin (parallel over bodies)
@@ -459,18 +465,18 @@ MJ_FN void bias_forces(const Model& m, Work& w, int lane) {
       real I6[6], c[3] = {w.xipos[b][0] - w.xpos[b][0], w.xipos[b][1] - w.xpos[b][1], w.xipos[b][2] - w.xpos[b][2]};
       body_inertia_world(m, w, b, I6);
       real t[3], t2[3], ac[3], Iw[3], Ial[3];
-      cross3(t, w.b_w[b], c);
-      cross3(t2, w.b_w[b], t);
-      cross3(t, w.b_al[b], c);
-      for (int k = 0; k < 3; ++k) ac[k] = w.b_a[b][k] + t[k] + t2[k];
+      cross3(t, w.rne.b_w[b], c);
+      cross3(t2, w.rne.b_w[b], t);
+      cross3(t, w.rne.b_al[b], c);
+      for (int k = 0; k < 3; ++k) ac[k] = w.rne.b_a[b][k] + t[k] + t2[k];
       for (int k = 0; k < 3; ++k) F[k] = mass * ac[k];
-      sym6_mulvec(Iw, I6, w.b_w[b]);
-      sym6_mulvec(Ial, I6, w.b_al[b]);
-      cross3(t, w.b_w[b], Iw);
+      sym6_mulvec(Iw, I6, w.rne.b_w[b]);
+      sym6_mulvec(Ial, I6, w.rne.b_al[b]);
+      cross3(t, w.rne.b_w[b], Iw);
       cross3(t2, c, F);
       for (int k = 0; k < 3; ++k) N[k] = Ial[k] + t[k] + t2[k];
     }
-    for (int k = 0; k < 3; ++k) { w.b_F[b][k] = F[k]; w.b_N[b][k] = N[k]; }
+    for (int k = 0; k < 3; ++k) { w.rne.b_F[b][k] = F[k]; w.rne.b_N[b][k] = N[k]; }
   }
   wsync<NL>();
   // project: dof i collects the wrenches of every body in its subtree (parallel over dofs)
@@ -481,8 +487,8 @@ MJ_FN void bias_forces(const Model& m, Work& w, int lane) {
     for (int c = bi; c < nb; ++c) {
       if (!((m.body_anc[c] >> bi) & 1u)) continue;
       real r[3] = {w.xpos[c][0] - an[0], w.xpos[c][1] - an[1], w.xpos[c][2] - an[2]}, t[3];
-      cross3(t, r, w.b_F[c]);
-      for (int k = 0; k < 3; ++k) { F[k] += w.b_F[c][k]; N[k] += w.b_N[c][k] + t[k]; }
+      cross3(t, r, w.rne.b_F[c]);
+      for (int k = 0; k < 3; ++k) { F[k] += w.rne.b_F[c][k]; N[k] += w.rne.b_N[c][k] + t[k]; }
     }
     w.bias[i] = m.dof_rot[i] ? dot3(w.dof_axis[i], N) : dot3(w.dof_axis[i], F);
   }

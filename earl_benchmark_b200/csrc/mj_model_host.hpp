@@ -26,7 +26,7 @@ struct TaskSpec {
   int32_t obj_geom;        // door: geom 'handle' (sawyer_door._get_pos_objects); -1 if the object is a site
   int32_t obj_site;        // peg: site 'pegHead' (sawyer_peg.py:186-187); -1 otherwise
   int32_t max_newton;      // device cap on Newton iterations per substep
-  int32_t reserved;
+  int32_t obj_qpos_count;  // qpos entries of the object joint written by a reset (door angle: 1, peg xyz: 3)
   float mocap_low[3];      // hand_low  (sawyer_peg.py:66 / metaworld SawyerDoorEnvV2)
   float mocap_high[3];     // hand_high
   float action_scale;      // 1/100

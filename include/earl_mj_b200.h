@@ -1,6 +1,6 @@
 /*
  * earl_mj_b200.h -- C ABI of the articulated-body half of libearl_b200.so: batched, device-resident step of the
- * reference's MuJoCo-backed Sawyer tasks (sawyer_door now; sawyer_peg next), one warp per environment instance.
+ * reference's MuJoCo-backed Sawyer tasks (sawyer_door, sawyer_peg), one warp per environment instance.
  *
  * The reference has no FFI on this path: `SawyerDoorV2` / `SawyerPegV2` (earl_benchmark/envs/sawyer_door.py,
  * sawyer_peg.py) inherit metaworld's SawyerXYZEnv.step, which drives MuJoCo 2.1.0 through mujoco-py
@@ -20,7 +20,7 @@ extern "C" {
 typedef struct earl_mj_handle earl_mj_handle;
 
 typedef struct {
-  int32_t env_kind;         /* EARL_ENV_SAWYER_DOOR (EARL_ENV_SAWYER_PEG: not built yet) */
+  int32_t env_kind;         /* EARL_ENV_SAWYER_DOOR or EARL_ENV_SAWYER_PEG */
   int32_t num_envs;
   int32_t device;
   uint32_t flags;           /* EARL_FLAG_AUTO_RESET | EARL_FLAG_EVAL_STATS */
@@ -36,7 +36,7 @@ typedef struct {
   int32_t obj_geom;         /* door: geom 'handle' (sawyer_door.py:113 get_geom_xpos); -1 when the object is a site */
   int32_t obj_site;         /* peg: site 'pegHead' (sawyer_peg.py:186-187); -1 otherwise */
   int32_t max_newton;       /* cap on Newton iterations per substep (0 = the model's <option iterations>) */
-  int32_t reserved;
+  int32_t obj_qpos_count;   /* leading qpos entries of the object joint written by a reset: 1 door angle, 3 peg xyz (_set_obj_xyz) */
   float mocap_low[3];       /* hand_low */
   float mocap_high[3];      /* hand_high */
   float action_scale;       /* 1/100 (SawyerXYZEnv.action_scale) */
@@ -64,10 +64,10 @@ EARL_API int earl_mj_build_reset_template(earl_mj_handle* h, const double* hand_
                                           int32_t steps);
 
 /* PersistentStateWrapper.reset + reset_model (persistent_state_wrapper.py:17-20, sawyer_door.py:111-125) for every env
- * with mask[i] != 0 (NULL = all): state <- reset template, object joint <- obj_qpos[i] with zero velocity
+ * with mask[i] != 0 (NULL = all): state <- reset template, object joint <- obj_qpos[i,:] with zero velocity
  * (_set_obj_xyz), goal <- goal_idx[i] (NULL = row 0), num_interventions += 1, steps_since_reset = 0, then a fresh
- * forward-kinematics pass and the observation (obs_out may be NULL).  obj_qpos is f64 [N]: the host draws it from
- * the bit-exact replica of the reference's np.random stream (earl_rng_np_uniform). */
+ * forward-kinematics pass and the observation (obs_out may be NULL).  obj_qpos is f64 [N, obj_qpos_count] (door angle /
+ * peg xyz; sawyer_peg.py:192-229): the host draws it from the bit-exact replica of the reference's np.random stream. */
 EARL_API int earl_mj_reset(earl_mj_handle* h, const uint8_t* mask_dev, const double* obj_qpos_dev, const int32_t* goal_idx_dev,
                            float* obs_out_dev, void* stream);
 

@@ -146,3 +146,51 @@ class SawyerDoorOracle:
         o = self.obs()
         reward = float(np.linalg.norm(o[4:7] - o[11:14]) <= 0.02)
         return o, reward
+
+
+class SawyerPegOracle:
+    """metaworld SawyerXYZEnv.step / reset semantics + EARL SawyerPegV2 observation and sparse reward
+    (reference earl_benchmark/envs/sawyer_peg.py:134-142,192-229,296-305)."""
+    MOCAP_LOW = np.array([-0.5, 0.40, 0.05])
+    MOCAP_HIGH = np.array([0.5, 1.0, 0.5])
+    HAND_INIT = np.array([0, 0.6, 0.2], dtype=np.float64)
+    GOAL = np.array([0.0, 0.6, 0.2, 1.0, -0.3 + 0.03, 0.6, 0.0 + 0.13])
+    OBJ_INIT = np.array([0, 0.6, 0.02])
+    FRAME_SKIP, ACTION_SCALE, TARGET_RADIUS = 5, 1.0 / 100, 0.05
+
+    def __init__(self, model):
+        self.e = Engine(model)
+        self.goal = self.GOAL.copy()
+        j = [k for k in range(len(model.jnt_type)) if model.jnt_type[k] == 0][0]
+        self.peg_qadr, self.peg_dadr = int(model.jnt_qposadr[j]), int(model.jnt_dofadr[j])
+
+    def reset_hand(self, steps=50):
+        for _ in range(steps):
+            self.e.mocap_pos[:] = self.HAND_INIT
+            self.e.mocap_quat[:] = [1, 0, 1, 0]
+            self.e.ctrl[:] = [-1, 1]
+            self.e.step(self.FRAME_SKIP)
+
+    def reset(self, peg_pos=None):
+        self.e.reset()
+        self.reset_hand()
+        p = self.OBJ_INIT if peg_pos is None else np.asarray(peg_pos, np.float64)
+        self.e.qpos[self.peg_qadr:self.peg_qadr + 3] = p          # _set_obj_xyz: qpos[9:12] = pos, qvel[9:15] = 0
+        self.e.qvel[self.peg_dadr:self.peg_dadr + 6] = 0
+        self.e.forward()
+        return self.obs()
+
+    def obs(self):
+        e = self.e
+        hand = e.site_xpos("body:hand")
+        grip = np.clip(np.linalg.norm(e.site_xpos("rightEndEffector") - e.site_xpos("leftEndEffector")) / 0.1, 0.0, 1.0)
+        return np.concatenate([hand, [grip], e.site_xpos("pegHead"), self.goal])
+
+    def step(self, action):
+        a = np.clip(np.asarray(action, np.float64), -1, 1)
+        self.e.mocap_pos[:] = np.clip(self.e.mocap_pos + a[:3] * self.ACTION_SCALE, self.MOCAP_LOW, self.MOCAP_HIGH)
+        self.e.mocap_quat[:] = [1, 0, 1, 0]
+        self.e.ctrl[:] = [a[3], -a[3]]
+        self.e.step(self.FRAME_SKIP)
+        o = self.obs()  # stale by one substep, as in the reference (see SawyerDoorOracle.step)
+        return o, float(np.linalg.norm(o[4:7] - o[11:14]) <= self.TARGET_RADIUS)

@@ -13,7 +13,7 @@ _LIB = None
 
 class TaskSpec(C.Structure):
     _fields_ = [("frame_skip", C.c_int32), ("hand_site", C.c_int32), ("ree_site", C.c_int32), ("lee_site", C.c_int32),
-                ("obj_geom", C.c_int32), ("obj_site", C.c_int32), ("max_newton", C.c_int32), ("reserved", C.c_int32),
+                ("obj_geom", C.c_int32), ("obj_site", C.c_int32), ("max_newton", C.c_int32), ("obj_qpos_count", C.c_int32),
                 ("mocap_low", C.c_float * 3), ("mocap_high", C.c_float * 3), ("action_scale", C.c_float),
                 ("success_radius", C.c_float)]
 
@@ -92,10 +92,21 @@ class Emu:
 
 def door_task(model, max_newton=0):
     t = TaskSpec()
-    t.frame_skip, t.max_newton = 5, max_newton
+    t.frame_skip, t.max_newton, t.obj_qpos_count = 5, max_newton, 1
     t.hand_site, t.ree_site, t.lee_site = model.site_id("body:hand"), model.site_id("rightEndEffector"), model.site_id("leftEndEffector")
     t.obj_geom, t.obj_site = model.geom_id("handle"), -1
     t.mocap_low[:] = [-0.5, 0.40, 0.05]
     t.mocap_high[:] = [0.5, 1.0, 0.5]
     t.action_scale, t.success_radius = 0.01, 0.02
+    return t
+
+
+def peg_task(model, max_newton=0):
+    t = TaskSpec()
+    t.frame_skip, t.max_newton, t.obj_qpos_count = 5, max_newton, 3
+    t.hand_site, t.ree_site, t.lee_site = model.site_id("body:hand"), model.site_id("rightEndEffector"), model.site_id("leftEndEffector")
+    t.obj_geom, t.obj_site = -1, model.site_id("pegHead")
+    t.mocap_low[:] = [-0.5, 0.40, 0.05]
+    t.mocap_high[:] = [0.5, 1.0, 0.5]
+    t.action_scale, t.success_radius = 0.01, 0.05
     return t

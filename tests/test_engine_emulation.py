@@ -118,3 +118,46 @@ def test_contact_rich_demo_replay_one_step_parity(door):
     assert same >= steps - 2
     assert worst_q < 1e-4 and worst_v < 2e-2, (worst_q, worst_v)
     assert light_ok >= 15
+
+
+# ------------------------------------------------------------------------------------------------ sawyer_peg scene
+@pytest.fixture(scope="module")
+def peg():
+    from earl_benchmark_b200.envs.sawyer_peg import MODEL_PATH as PEG_MODEL
+    from host_emulation.emu import peg_task
+    from oracle.engine import SawyerPegOracle
+    m = Model.load(PEG_MODEL)
+    return m, SawyerPegOracle(m), Emu(m, peg_task(m))
+
+
+def test_peg_scene_one_step_parity(peg):
+    """Free-joint peg (nq 16, nv 15): sim.reset() + _reset_hand() (the peg drops 1.5 cm onto the table: 4 box-box
+    contacts) and 80 env steps of the hand pressing down on the peg (up to 12 contacts, condim-4 pads), re-synchronised
+    before every env step.  Only box-box contacts occur, so fp32 stays within 1e-4 everywhere."""
+    m, o, em = peg
+    e, nv = o.e, int(m.nv)
+    e.reset()
+    worst_q = worst_v = 0.0
+    for _ in range(50):
+        e.mocap_pos[:], e.mocap_quat[:], e.ctrl[:] = o.HAND_INIT, [1, 0, 1, 0], [-1, 1]
+        em.set_state(e.qpos, e.qvel, e.arr("qacc_warmstart", (32,))[:nv], o.HAND_INIT, ctrl=(-1, 1))
+        e.step(5)
+        em.substeps(5)
+        q, v, _, _ = em.get_state()
+        worst_q, worst_v = max(worst_q, np.abs(q - e.qpos).max()), max(worst_v, np.abs(v - e.qvel).max())
+    assert e.ncon == 4 and em.info("ncon") == 4
+    o.reset(peg_pos=[0.05, 0.6, 0.02])
+    rs = np.random.RandomState(0)
+    max_con = 0
+    for _ in range(80):
+        a = np.clip(rs.uniform(-1, 1, 4) + [0, 0, -0.6, 0], -1, 1).astype(np.float32)
+        em.set_state(e.qpos, e.qvel, e.arr("qacc_warmstart", (32,))[:nv], e.mocap_pos)
+        ob_ref, _ = o.step(a)
+        ob = em.env_step(a)
+        q, v, _, _ = em.get_state()
+        worst_q, worst_v = max(worst_q, np.abs(q - e.qpos).max()), max(worst_v, np.abs(v - e.qvel).max())
+        assert e.ncon == em.info("ncon") and e.nefc == em.info("nefc")
+        assert np.abs(ob_ref[:7] - ob).max() < 1e-5 and em.info("bad") == 0
+        max_con = max(max_con, e.ncon)
+    assert max_con >= 10
+    assert worst_q < TOL and worst_v < TOL, (worst_q, worst_v)

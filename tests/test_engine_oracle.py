@@ -84,3 +84,47 @@ def test_sparse_reward_agreement_over_all_demonstrations(oracle):
     assert 1 - mism / total >= 0.99, (mism, total)
     for ep in eps[5:]:  # reverse episodes: free-space approach (first 45 steps) tracks the recording
         assert ep["hand"][:45].max() < 0.03
+
+
+# ------------------------------------------------------------------------------------------------ sawyer_peg
+@pytest.fixture(scope="module")
+def peg_oracle():
+    from earl_benchmark_b200.envs import sawyer_peg
+    from oracle.engine import SawyerPegOracle
+    return SawyerPegOracle(Model.load(sawyer_peg.MODEL_PATH))
+
+
+def test_peg_reset_known_answers(peg_oracle):
+    """initial_states of sawyer_peg.py:18-50: pegHead = peg position - (0.1, 0, 0) at z = 0.02 (exact: FK of the free
+    joint + site), hand rest pose [0.00615235, 0.6001898, 0.19430117] after sim.reset() + _reset_hand().
+    KNOWN GAP: the hand rest pose (a snapshot of a moving arm with joint j1 on its limit) is reproduced to 1.2 cm only."""
+    from earl_benchmark_b200.envs import sawyer_peg
+    for row in sawyer_peg.initial_states[:4]:
+        ob = peg_oracle.reset(peg_pos=row[4:7] + np.array([0.1, 0, 0]))
+        assert np.abs(ob[4:7] - row[4:7]).max() < 1e-6
+        assert np.abs(ob[:3] - row[:3]).max() < 0.012
+        assert ob[3] == 1.0
+
+
+def test_peg_demonstrations_are_not_reproduced(peg_oracle):
+    """Documents the state of the peg checker honestly: the open-loop replay of the shipped forward demonstrations
+    tracks the recorded HAND within 7 cm, but the grasp-lift-insert sequence is not reproduced (the peg is left behind),
+    so no episode reaches the goal and the per-step sparse agreement (98.4 %) is below the 99 % north-star bar."""
+    d = demos.load("sawyer_peg", "forward")
+    obs, nobs, act = d["observations"], d["next_observations"], d["actions"]
+    term, rew = d["terminals"].ravel(), d["rewards"].ravel()
+    ends = list(np.nonzero(term)[0] + 1)
+    total = mism = 0
+    for s, en in zip([0] + ends[:-1], ends):
+        peg_oracle.goal = obs[s][7:14].astype(np.float64)
+        peg_oracle.reset(peg_pos=obs[s][4:7].astype(np.float64) + np.array([0.1, 0, 0]))
+        r, hand = [], []
+        for t in range(s, en):
+            ob, rr = peg_oracle.step(act[t])
+            r.append(rr)
+            hand.append(np.abs(ob[:3] - nobs[t][:3]).max())
+        assert max(hand) < 0.07
+        total += en - s
+        mism += int((np.array(r) != rew[s:en]).sum())
+    peg_oracle.goal = peg_oracle.GOAL.copy()
+    assert 0.98 <= 1 - mism / total < 0.99

@@ -75,3 +75,43 @@ def test_goal_table_and_custom_goals():
         TabletopManipulation(task_list="bc_r")
     with pytest.raises(ValueError):
         TabletopManipulation(reward_type="banana")
+
+
+def test_peg_reset_draws_replicate_the_reference_numpy_stream():
+    """reset_model() of sawyer_peg.py:192-229 against numpy's own legacy generator, for the three variants."""
+    from earl_benchmark_b200.envs import sawyer_peg as sp
+    low, high = sp._RESET_LOW, sp._RESET_HIGH
+    pos_box = sp.goal_states[0][4:] - np.array([0.03, 0.0, 0.13])
+
+    def ref_draws(seed, count, reset_at_goal, wide_init):
+        rs = np.random.RandomState(seed)
+        out = []
+        for _ in range(count):
+            if not reset_at_goal:
+                rs.randint(0, 1)
+                row, pos = 0, np.array([0, 0.6, 0.02])
+                sample = lambda: np.split(rs.uniform(low, high, size=6), 2)[0]  # noqa: E731
+                if wide_init:
+                    if rs.uniform() < 0.5:
+                        pos = sample()
+                        while np.linalg.norm(pos[:2] - pos_box[:2]) < 0.1:
+                            pos = sample()
+                    else:
+                        pos = sp.wide_initial_states[rs.randint(0, sp.wide_initial_states.shape[0])] - np.array([-0.1, 0., 0.])
+                        pos = pos + rs.uniform(-0.02, 0.02, size=3)
+                else:
+                    pos = sample()
+                    while np.linalg.norm(pos[:2] - pos_box[:2]) < 0.1:
+                        pos = sample()
+            else:
+                row = 1 + rs.randint(0, sp.initial_states.shape[0])
+                pos = sp.goal_states[0][4:] - np.array([-0.1, 0., 0.]) + rs.uniform(-0.02, 0.02, size=3)
+            out.append((row, pos))
+        return out
+
+    for kw in (dict(), dict(wide_init=True), dict(reset_at_goal=True)):
+        env = sp.SawyerPegV2(reward_type="sparse", num_envs=1, seed=7, **kw)
+        want = ref_draws(7, 40, kw.get("reset_at_goal", False), kw.get("wide_init", False))
+        for row, pos in want:
+            r, p = env._draw_one()
+            assert r == row and np.array_equal(p, pos)

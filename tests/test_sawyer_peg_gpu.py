@@ -1,0 +1,95 @@
+"""GPU parity tests of the batched Sawyer peg step (free-joint peg, box-box contacts, condim-4 pads) against the fp64
+checker, through the C ABI of include/earl_mj_b200.h.  The checker itself is only weakly pinned for this task (see
+tests/test_engine_oracle.py::test_peg_demonstrations_are_not_reproduced)."""
+import numpy as np
+import pytest
+import torch
+
+import earl_benchmark_b200 as eb
+from earl_benchmark_b200.envs import sawyer_peg
+from earl_benchmark_b200.mjcf.compile import Model
+from oracle.engine import SawyerPegOracle
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def oracle():
+    return SawyerPegOracle(Model.load(sawyer_peg.MODEL_PATH))
+
+
+def test_one_step_parity_from_identical_states(oracle):
+    """States sampled along checker rollouts in which the hand descends onto the peg (peg-on-table, pad-on-peg box-box
+    contacts): one env step on the device from the same (qpos, qvel, warm start, mocap) and action."""
+    e, nv = oracle.e, oracle.e.nv
+    rs = np.random.RandomState(11)
+    states = []
+    while len(states) < 64:
+        oracle.reset(peg_pos=[rs.uniform(0, 0.1), rs.uniform(0.55, 0.65), 0.02])
+        bias = np.array([rs.uniform(-0.3, 0.3), rs.uniform(-0.3, 0.3), -0.7, rs.uniform(-1, 1)])
+        for t in range(48):
+            oracle.step(np.clip(bias + rs.uniform(-0.5, 0.5, 4), -1, 1))
+            if t % 6 == 5:
+                states.append((e.qpos.copy(), e.qvel.copy(), e.arr("qacc_warmstart", (32,))[:nv].copy(), e.mocap_pos.copy()))
+    n = len(states)
+    env = sawyer_peg.SawyerPegV2(reward_type="sparse", num_envs=n, device="cuda:0")
+    env.reset()
+    env.set_state(qpos=np.stack([s[0] for s in states]), qvel=np.stack([s[1] for s in states]),
+                  qacc_warmstart=np.stack([s[2] for s in states]), mocap_pos=np.stack([s[3] for s in states]))
+    actions = rs.uniform(-1, 1, (n, 4)).astype(np.float32)
+    obs, rew, done, info = env.step(torch.from_numpy(actions).cuda())
+    got, obs = env.get_state(), obs.cpu().numpy()
+    worst = dict(q=0.0, v=0.0, obs=0.0)
+    contacts = 0
+    for i, (q, v, w, mp) in enumerate(states):
+        e.reset()
+        e.qpos[:], e.qvel[:], e.mocap_pos[:] = q, v, mp
+        e.arr("qacc_warmstart", (32,))[:nv] = w
+        ob_ref, r_ref = oracle.step(actions[i])
+        contacts = max(contacts, e.ncon)
+        worst["q"] = max(worst["q"], np.abs(got["qpos"][i] - e.qpos).max())
+        worst["v"] = max(worst["v"], np.abs(got["qvel"][i] - e.qvel).max())
+        worst["obs"] = max(worst["obs"], np.abs(obs[i] - ob_ref).max())
+        assert float(rew[i]) == r_ref
+    print("peg one-step parity:", worst, "max contacts", contacts)
+    assert contacts >= 8
+    assert worst["q"] < TOL and worst["v"] < 5e-4 and worst["obs"] < 1e-5, worst
+    assert env.work_counters()["bad_states"] == 0
+
+
+def test_reset_and_rollout_against_checker(oracle):
+    n = 4
+    pegs = np.array([[0.0, 0.6, 0.02], [0.1, 0.55, 0.02], [0.15, 0.68, 0.02], [0.05, 0.62, 0.02]])
+    env = sawyer_peg.SawyerPegV2(reward_type="sparse", num_envs=n, device="cuda:0")
+    obs0 = env.reset(peg_pos=pegs).cpu().numpy()
+    rs = np.random.RandomState(5)
+    actions = rs.uniform(-1, 1, (30, n, 4)).astype(np.float32)
+    dev = [env.step(torch.from_numpy(a).cuda())[0].cpu().numpy().copy() for a in actions]
+    for i in (0, n - 1):
+        ob = oracle.reset(peg_pos=pegs[i])
+        assert np.abs(ob - obs0[i]).max() < 2e-5
+        for t in range(30):
+            ob, _ = oracle.step(actions[t, i])
+            assert np.abs(ob - dev[t][i]).max() < 5e-5, (t, np.abs(ob - dev[t][i]).max())
+
+
+def test_loader_surface_and_reset_draws():
+    n = 9
+    loader = eb.EARLEnvs("sawyer_peg", reward_type="sparse", num_envs=n, train_horizon=4, device="cuda:0", seed=3)
+    train, ev = loader.get_envs()
+    assert loader.get_initial_states().shape == (15, 7) and loader.get_goal_states().shape == (1, 7)
+    obs = train.reset()
+    assert obs.shape == (n, 14)
+    # peg xyz of every env = np.random.seed(3) stream: 6 uniforms per env over the reset box, first 3 kept
+    rs = np.random.RandomState(3)
+    want = np.stack([np.split(rs.uniform(sawyer_peg._RESET_LOW, sawyer_peg._RESET_HIGH, size=6), 2)[0] for _ in range(n)])
+    got = train.env.get_state()["qpos"][:, 9:12]
+    assert np.array_equal(got, want.astype(np.float32))
+    assert np.allclose(obs.cpu().numpy()[:, 4:7], want - [0.1, 0, 0], atol=2e-6)
+    a = torch.zeros((n, 4), device="cuda")
+    for t in range(5):
+        o, r, d, _ = train.step(a)
+        assert bool(d.all()) == (t + 1 >= 4)
+    assert train.total_steps == 5 and int(train.num_interventions[0]) == 1
+    assert ev.env._episode_horizon == 200

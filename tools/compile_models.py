@@ -26,8 +26,18 @@ def sawyer_door():
                            keep_sites=("rightEndEffector", "leftEndEffector"))
 
 
+def sawyer_peg():
+    spec = parser.load(os.path.join(MW, "sawyer_peg_insertion_side.xml"))
+    # reset_model() moves the block to goal_states[0][4:] - (0.03, 0, 0.13) (reference envs/sawyer_peg.py:195-197)
+    box_pos = np.array([-0.3 + 0.03, 0.6, 0.0 + 0.13]) - np.array([0.03, 0.0, 0.13])
+    return C.compile_model(spec, body_pos_overrides={"box": box_pos}, frame_sites=("hand",),
+                           keep_sites=("rightEndEffector", "leftEndEffector", "pegHead", "pegGrasp"))
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    m = sawyer_door()
-    m.save(os.path.join(OUT, "sawyer_door.npz"))
-    print("sawyer_door: bodies", int(m.nbody), "nv", int(m.nv), "geoms", int(m.ngeom), "blob", len(m.to_blob()), "B")
+    for name, fn in (("sawyer_door", sawyer_door), ("sawyer_peg", sawyer_peg)):
+        m = fn()
+        m.save(os.path.join(OUT, name + ".npz"))
+        print(name, ": bodies", int(m.nbody), "nq", int(m.nq), "nv", int(m.nv), "geoms", int(m.ngeom), "sites", int(m.nsite),
+              "blob", len(m.to_blob()), "B")
