@@ -37,7 +37,7 @@ class TabletopModel(C.Structure):
 class MjConfig(C.Structure):
     """earl_mj_config (include/earl_mj_b200.h)"""
     _fields_ = [("env_kind", C.c_int32), ("num_envs", C.c_int32), ("device", C.c_int32), ("flags", C.c_uint32),
-                ("episode_horizon", C.c_int64)]
+                ("episode_horizon", C.c_int64), ("goal_change_frequency", C.c_int64)]
 
 
 class MjTask(C.Structure):
@@ -97,7 +97,7 @@ SIGNATURES = [
     ("earl_mj_get_obs", C.c_int, [_VP, _VP, _VP]),
     ("earl_mj_get_state", C.c_int, [_VP, _VP, _VP, _VP, _VP]),
     ("earl_mj_set_state", C.c_int, [_VP, _VP, _VP, _VP, _VP]),
-    ("earl_mj_counters", C.c_int, [_VP, C.POINTER(_I64), _VP, _VP, _VP]),
+    ("earl_mj_counters", C.c_int, [_VP, C.POINTER(_I64), _VP, _VP, _VP, _VP]),
     ("earl_mj_eval_stats", C.c_int, [_VP, _VP, _VP]),
     ("earl_mj_work_counters", C.c_int, [_VP, _VP]),
     ("earl_mj_launch_count", _I64, [_VP]),

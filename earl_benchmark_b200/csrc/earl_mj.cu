@@ -53,6 +53,9 @@ struct StepArgs {
   const float* goals;        // [kMaxGoals][8]
   long long* interventions;  // [N]
   double* ep_return;         // [N] or null
+  double* ll_return;         // [N] or null (lifelong handles)
+  unsigned* ll_steps;        // [N] steps_since_goal_change
+  unsigned goal_freq;
   unsigned long long* work;  // 6 counters
   int n;
   unsigned horizon;
@@ -116,14 +119,22 @@ __device__ __forceinline__ void store_env(const Work& w, float* rec, int lane) {
   rec[lane + 32] = gather_rec(w, lane + 32);
 }
 
-// observation row [hand(3), gripper(1), object(3), goal(7)] + sparse success (sawyer_door.py:86-94,168-177)
+// sparse success of the current observation against the current goal (sawyer_door.py:173-177, sawyer_peg.py:301-305)
+__device__ __forceinline__ bool obs_success(const Model& m, const Work& w, const float* goals) {
+  const float* g = goals + 8 * w.goalrow;
+  const float dx = w.obs7[4] - g[4], dy = w.obs7[5] - g[5], dz = w.obs7[6] - g[6];
+  return sqrtf(dx * dx + dy * dy + dz * dz) <= m.success_radius;
+}
+// observation row [hand(3), gripper(1), object(3), goal(7)] (sawyer_door.py:86-94)
+__device__ __forceinline__ void write_obs_row(const Work& w, const float* goals, float* obs_row, int lane) {
+  const float* g = goals + 8 * w.goalrow;
+  if (obs_row && lane < kObs) obs_row[lane] = lane < 7 ? w.obs7[lane] : g[lane - 7];
+}
 __device__ __forceinline__ bool write_obs(const Model& m, Work& w, const float* goals, float* obs_row, int lane) {
   if (lane == 0) observe(m, w, w.obs7);
   __syncwarp();
-  const float* g = goals + 8 * w.goalrow;
-  if (obs_row && lane < kObs) obs_row[lane] = lane < 7 ? w.obs7[lane] : g[lane - 7];
-  const float dx = w.obs7[4] - g[4], dy = w.obs7[5] - g[5], dz = w.obs7[6] - g[6];
-  return sqrtf(dx * dx + dy * dy + dz * dz) <= m.success_radius;
+  write_obs_row(w, goals, obs_row, lane);
+  return obs_success(m, w, goals);
 }
 
 __global__ void __launch_bounds__(kWPB * 32, 1) mj_step_kernel(const StepArgs a) {
@@ -144,7 +155,18 @@ __global__ void __launch_bounds__(kWPB * 32, 1) mj_step_kernel(const StepArgs a)
     __syncwarp();
     env_step<32>(*sm, a.hull, w, w.action, lane);
     if (!live) continue;
-    const bool ok = write_obs(*sm, w, a.goals, a.obs + (size_t)env * kObs, lane);
+    if (lane == 0) observe(*sm, w, w.obs7);
+    __syncwarp();
+    const bool ok = obs_success(*sm, w, a.goals);  // reward / success against the goal the step was taken with
+    if (lane == 0 && a.ll_return) {
+      // LifelongWrapper.step: lifetime return, periodic reset_goal() (single-goal tasks: goal_states[0] = row 0)
+      a.ll_return[env] += ok ? 1.0 : 0.0;
+      unsigned s = a.ll_steps[env] + 1;
+      if (s >= a.goal_freq) { s = 0; w.goalrow = 0; }
+      a.ll_steps[env] = s;
+    }
+    __syncwarp();
+    write_obs_row(w, a.goals, a.obs + (size_t)env * kObs, lane);
     if (lane == 0) {
       // PersistentStateWrapper.step: counters, horizon `done` (persistent_state_wrapper.py:22-31)
       const unsigned steps = w.steps == 0xffffffffu ? w.steps : w.steps + 1;
@@ -194,6 +216,7 @@ __global__ void __launch_bounds__(kWPB * 32, 1) mj_reset_kernel(const StepArgs a
       w.flags = 0;
       a.interventions[env] += 1;  // PersistentStateWrapper.reset (persistent_state_wrapper.py:17-20)
       if (a.ep_return) a.ep_return[env] = 0.0;
+      if (a.ll_steps) a.ll_steps[env] = 0;  // LifelongWrapper.reset (lifelong_wrapper.py:25-28); the return is kept
     }
     __syncwarp();
     kinematics<32>(*sm, w, lane);
@@ -306,7 +329,9 @@ int earl_mj_create(const earl_mj_config* cfg, const void* model_blob, size_t mod
     return failf(EARL_ERR_UNSUPPORTED, "env_kind %d is not built on the articulated-body engine (sawyer_door, sawyer_peg)", cfg->env_kind);
   if (cfg->num_envs < 1) return failf(EARL_ERR_INVALID, "num_envs must be >= 1");
   if (cfg->episode_horizon < 1) return failf(EARL_ERR_INVALID, "episode_horizon must be >= 1");
-  if (cfg->flags & ~(uint32_t)(EARL_FLAG_EVAL_STATS)) return failf(EARL_ERR_UNSUPPORTED, "unsupported flags %#x", cfg->flags);
+  if (cfg->flags & ~(uint32_t)(EARL_FLAG_EVAL_STATS | EARL_FLAG_LIFELONG)) return failf(EARL_ERR_UNSUPPORTED, "unsupported flags %#x", cfg->flags);
+  if ((cfg->flags & EARL_FLAG_LIFELONG) && cfg->goal_change_frequency < 1)
+    return failf(EARL_ERR_INVALID, "lifelong handles need goal_change_frequency >= 1");
   static_assert(sizeof(earl_mj_task) == sizeof(TaskSpec), "earl_mj_task must mirror earl::mj::TaskSpec");
   int ndev = 0;
   CU(cudaGetDeviceCount(&ndev));
@@ -349,6 +374,7 @@ int earl_mj_create(const earl_mj_config* cfg, const void* model_blob, size_t mod
   if (!rc) rc = h->alloc(&h->d_goals, kMaxGoals * 8);
   if (!rc) rc = h->alloc(&a.interventions, n);
   if (!rc && (cfg->flags & EARL_FLAG_EVAL_STATS)) rc = h->alloc(&a.ep_return, n);
+  if (!rc && (cfg->flags & EARL_FLAG_LIFELONG)) { rc = h->alloc(&a.ll_return, n); if (!rc) rc = h->alloc(&a.ll_steps, n); }
   if (!rc) rc = h->alloc(&a.work, 16);
   if (!rc) rc = h->alloc(&h->d_tmpl, REC_FLOATS);
   if (rc) { earl_mj_destroy(h); return rc; }
@@ -370,6 +396,7 @@ int earl_mj_create(const earl_mj_config* cfg, const void* model_blob, size_t mod
   a.n = cfg->num_envs;
   a.horizon = cfg->episode_horizon > 0xffffffffLL ? 0xffffffffu : (unsigned)cfg->episode_horizon;
   a.flags = cfg->flags;
+  a.goal_freq = cfg->goal_change_frequency > 0xffffffffLL ? 0xffffffffu : (unsigned)(cfg->goal_change_frequency > 0 ? cfg->goal_change_frequency : 1);
   a.obj_qadr = h->obj_qadr;
   a.obj_dadr = h->obj_dadr;
   a.obj_nq_set = ts.obj_qpos_count;
@@ -525,7 +552,7 @@ int earl_mj_set_state(earl_mj_handle* h, const double* qpos_host, const double* 
 }
 
 int earl_mj_counters(earl_mj_handle* h, int64_t* total_steps_host, int64_t* num_interventions_dev, uint32_t* steps_since_reset_dev,
-                     void* stream) {
+                     double* lifelong_return_dev, void* stream) {
   if (int rc = check_handle(h)) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const size_t n = (size_t)h->a.n;
@@ -535,6 +562,10 @@ int earl_mj_counters(earl_mj_handle* h, int64_t* total_steps_host, int64_t* num_
   if (steps_since_reset_dev)
     CU(cudaMemcpy2DAsync(steps_since_reset_dev, sizeof(uint32_t), h->a.state + REC_STEPS, REC_FLOATS * sizeof(float),
                          sizeof(uint32_t), n, cudaMemcpyDeviceToDevice, s));
+  if (lifelong_return_dev) {
+    if (!h->a.ll_return) return failf(EARL_ERR_INVALID, "lifelong_return needs EARL_FLAG_LIFELONG");
+    CU(cudaMemcpyAsync(lifelong_return_dev, h->a.ll_return, n * sizeof(double), cudaMemcpyDeviceToDevice, s));
+  }
   return 0;
 }
 

@@ -57,6 +57,8 @@ class SawyerBatchedEnv:
         self.observation_space = Box(-np.inf, np.inf, (OBS_DIM,), np.float32)
         self._goal_table = []
         self._episode_horizon = _NEVER
+        self._lifelong = False
+        self._goal_change_frequency = 0
         self._handle = None
         self._np_random = rng.NumpyLegacyRandom(self._seed & 0xFFFFFFFF)
         self._obs = self._reward = self._done = self._success = None
@@ -76,15 +78,20 @@ class SawyerBatchedEnv:
             raise RuntimeError("wrappers must be applied before the env is first reset/stepped")
         if episode_horizon is not None:
             self._episode_horizon = int(episode_horizon)
-        if lifelong:
-            raise NotImplementedError(f"{type(self).__name__}: LifelongWrapper is not built on the articulated-body engine yet")
+        if lifelong is not None:
+            if lifelong and self._reset_at_goal and type(self).__name__ == "SawyerPegV2":
+                raise NotImplementedError("SawyerPegV2: lifelong goal swaps with reset_at_goal (random goals) are not built")
+            self._lifelong = bool(lifelong)
+        if goal_change_frequency is not None:
+            self._goal_change_frequency = int(goal_change_frequency)
 
     def _ensure(self):
         if self._handle is not None:
             return
         L = _lib.lib()
-        cfg = _lib.MjConfig(self.ENV_KIND, self.num_envs, self.device.index or 0,
-                            _lib.FLAG_EVAL_STATS if self._eval_stats else 0, self._episode_horizon)
+        flags = (_lib.FLAG_EVAL_STATS if self._eval_stats else 0) | (_lib.FLAG_LIFELONG if self._lifelong else 0)
+        cfg = _lib.MjConfig(self.ENV_KIND, self.num_envs, self.device.index or 0, flags, self._episode_horizon,
+                            self._goal_change_frequency)
         blob = self.model.to_blob()
         task = self._task_spec()
         h = C.c_void_p()
@@ -213,14 +220,15 @@ class SawyerBatchedEnv:
         return s.to(torch.float32) if isinstance(s, torch.Tensor) else s.astype(np.float32)
 
     # ------------------------------------------------------------------ counters / stats / state
-    def _counters(self):
+    def _counters(self, want_ll=False):
         self._ensure()
         total = C.c_int64()
         n = self.num_envs
         interv = torch.empty((n,), dtype=torch.int64, device=self.device)
         since = torch.empty((n,), dtype=torch.int32, device=self.device)
-        _lib.check(_lib.lib().earl_mj_counters(self._handle, C.byref(total), interv.data_ptr(), since.data_ptr(), _stream()))
-        return total.value, interv, since, None
+        ll = torch.empty((n,), dtype=torch.float64, device=self.device) if want_ll else None
+        _lib.check(_lib.lib().earl_mj_counters(self._handle, C.byref(total), interv.data_ptr(), since.data_ptr(), _ptr(ll), _stream()))
+        return total.value, interv, since, ll
 
     def eval_stats(self):
         self._ensure()

@@ -23,8 +23,9 @@ typedef struct {
   int32_t env_kind;         /* EARL_ENV_SAWYER_DOOR or EARL_ENV_SAWYER_PEG */
   int32_t num_envs;
   int32_t device;
-  uint32_t flags;           /* EARL_FLAG_AUTO_RESET | EARL_FLAG_EVAL_STATS */
+  uint32_t flags;           /* EARL_FLAG_EVAL_STATS | EARL_FLAG_LIFELONG */
   int64_t episode_horizon;  /* PersistentStateWrapper(episode_horizon), persistent_state_wrapper.py:10-12 */
+  int64_t goal_change_frequency; /* LifelongWrapper(goal_change_frequency), lifelong_wrapper.py:19-24; 0 = unused */
 } earl_mj_config;
 
 /* Task constants that live in the metaworld / EARL Python classes rather than in the MJCF. */
@@ -73,8 +74,10 @@ EARL_API int earl_mj_reset(earl_mj_handle* h, const uint8_t* mask_dev, const dou
 
 /* One PersistentStateWrapper.step of every env: SawyerXYZEnv.step (set_xyz_action, do_simulation = frame_skip x
  * mj_step), EARL observation + sparse reward (sawyer_door.py:86-94,168-177), counters and horizon `done`
- * (persistent_state_wrapper.py:22-31).  actions [N,4] f32; obs [N,14] f32; reward [N] f32; done [N] u8;
- * success [N] u8 or NULL. */
+ * (persistent_state_wrapper.py:22-31).  With EARL_FLAG_LIFELONG also LifelongWrapper.step (lifelong_wrapper.py:30-44):
+ * lifelong_return += reward and, every goal_change_frequency steps, reset_goal() -- the observation of that step then
+ * carries the new goal while the reward is the pre-swap one.  actions [N,4] f32; obs [N,14] f32; reward [N] f32;
+ * done [N] u8; success [N] u8 or NULL. */
 EARL_API int earl_mj_step(earl_mj_handle* h, const float* actions_dev, float* obs_dev, float* reward_dev, uint8_t* done_dev,
                           uint8_t* success_dev, void* stream);
 /* Same with HOST buffers (copies inside the call, synchronous). */
@@ -90,9 +93,10 @@ EARL_API int earl_mj_get_state(earl_mj_handle* h, double* qpos_host, double* qve
 EARL_API int earl_mj_set_state(earl_mj_handle* h, const double* qpos_host, const double* qvel_host, const double* warm_host,
                                const double* mocap_host);
 
-/* total_steps (host scalar), num_interventions i64 [N], steps_since_reset u32 [N]; arrays may be NULL. */
+/* total_steps (host scalar), num_interventions i64 [N], steps_since_reset u32 [N], lifelong_return f64 [N]
+ * (lifelong_wrapper.py:46-48; EARL_FLAG_LIFELONG handles only); arrays may be NULL. */
 EARL_API int earl_mj_counters(earl_mj_handle* h, int64_t* total_steps_host, int64_t* num_interventions_dev,
-                              uint32_t* steps_since_reset_dev, void* stream);
+                              uint32_t* steps_since_reset_dev, double* lifelong_return_dev, void* stream);
 /* out4 = { sum of episode returns, #envs successful at their last step, #envs successful at any step since reset, N } */
 EARL_API int earl_mj_eval_stats(earl_mj_handle* h, double* out4_dev, void* stream);
 /* Work counters accumulated by the step kernel since creation (host): { env_steps, substeps, newton_iterations,

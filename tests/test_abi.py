@@ -41,7 +41,7 @@ def test_struct_layouts_match_header():
     # sizes the C side checks against (earl_create rejects blobs of any other size)
     assert ctypes.sizeof(_lib.EarlConfig) == 40
     assert ctypes.sizeof(_lib.TabletopModel) == 8 + 4 * 8 + 6 * 8 + 256 * 6 * 8
-    assert ctypes.sizeof(_lib.MjConfig) == 24
+    assert ctypes.sizeof(_lib.MjConfig) == 32
     assert ctypes.sizeof(_lib.MjTask) == 8 * 4 + 8 * 4
 
 

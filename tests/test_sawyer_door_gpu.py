@@ -190,3 +190,42 @@ def test_demo_replay_on_device_matches_checker_and_recording(oracle):
             assert np.array_equal(ref_r[~near], dev_r[~near].astype(bool))
     oracle.goal = oracle.GOAL.copy()
     assert 1 - mism / total >= 0.99, (mism, total)
+
+
+def test_lifelong_wrapper_on_the_door():
+    """LifelongWrapper semantics (lifelong_wrapper.py:25-48) on the engine: lifetime return accumulates the sparse reward,
+    survives reset(), the goal swap every `goal_change_frequency` steps re-selects goal_states[0] while the reward of
+    that step is the pre-swap one."""
+    n, freq = 5, 3
+    env = eb.EARLEnvs("sawyer_door", reward_type="sparse", setup_as_lifelong_learning=True, num_envs=n, device="cuda:0",
+                      goal_change_frequency=freq, train_horizon=100).get_envs()
+    base = env.env.env
+    base.reset_goal(sawyer_door.initial_states[0])           # custom goal: the OPEN-door state (row 1 of the table)
+    env.reset(door_angle=np.full(n, -np.pi / 3))
+    a = torch.zeros((n, 4), device="cuda")
+    rewards, goals = [], []
+    for t in range(2 * freq):
+        o, r, d, _ = env.step(a)
+        rewards.append(r.cpu().numpy().copy())
+        goals.append(o[:, 11:14].cpu().numpy().copy())
+    rewards = np.array(rewards)
+    # steps 0..freq-1 are judged against the custom goal (door open -> success); the observation of step freq-1 already
+    # carries goal_states[0]; later steps are judged against goal_states[0] (door closed -> no success)
+    assert rewards[:freq].min() == 1.0 and rewards[freq:].max() == 0.0
+    assert np.allclose(goals[freq - 2], sawyer_door.initial_states[0][4:7], atol=1e-6)
+    assert np.allclose(goals[freq - 1], sawyer_door.goal_states[0][4:7], atol=1e-6)
+    assert np.array_equal(env.lifelong_return.cpu().numpy(), np.full(n, float(freq)))
+    env.reset(door_angle=np.full(n, -np.pi / 3))
+    assert np.array_equal(env.lifelong_return.cpu().numpy(), np.full(n, float(freq)))
+    assert int(env.num_interventions[0]) == 2
+
+
+def test_eval_stats_all_reduce_single_rank():
+    """The one collective of the system on the Sawyer envs (world_size 1 path of distributed.all_reduce_eval_stats)."""
+    from earl_benchmark_b200 import distributed as D
+    env = sawyer_door.SawyerDoorV2(num_envs=6, device="cuda:0", eval_stats=True)
+    env.reset(door_angle=np.array([0, 0, 0, -1.0, -1.0, -1.0]))
+    for _ in range(2):
+        env.step(torch.zeros((6, 4), device="cuda"))
+    st = D.all_reduce_eval_stats(env.eval_stats())
+    assert st == {"mean_return": 1.0, "success_rate": 0.5, "success_any_rate": 0.5, "num_envs": 6}
