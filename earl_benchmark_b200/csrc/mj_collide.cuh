@@ -29,7 +29,17 @@ struct Supp { real v[3], v1[3], v2[3]; };
 // the warp runs the same narrow-phase code and writes identical values to identical addresses, so no lane ever reads a
 // value it did not also write itself; keeping these dynamically indexed arrays out of local memory keeps the kernel
 // off the L1/L2 path.
+// a convex geom as the support function sees it: pose / size pointers resolved once per pair
+struct CObj {
+  int type, nvert;
+  real margin;
+  const real* pos;   // world position of the geom frame
+  const real* R;     // world rotation (row-major)
+  const real* size;
+  const real* hv;    // hull vertices (mesh geoms)
+};
 struct NarrowScratch {
+  CObj o1, o2;
   real A[3][3], B[3][3];
   real poly[16][3], tmp[16][3];
   RawCon rc[8];
@@ -214,27 +224,33 @@ MJ_FN int box_box(const real* p1, const real* R1, const real* s1, const real* p2
 }
 
 // ------------------------------------------------------------------------------------------------ support functions
-struct CObj { int g; real margin; };
+MJ_HD void make_cobj(CObj& o, const Model& m, const real* hull, const Work& w, int g, real margin) {
+  o.type = m.geom_type[g];
+  o.nvert = m.geom_hullnum[g];
+  o.margin = margin;
+  o.pos = gpos(m, w, g);
+  o.R = gmat(m, w, g);
+  o.size = m.geom_size[g];
+  o.hv = hull + 3 * m.geom_hulladr[g];
+}
 
 template <int NL>
-MJ_FN void support_geom(const Model& m, const real* hull, Work& w, const CObj& o, const real* dir, real* res, int lane) {
-  const int g = o.g;
-  const real* R = gmat(m, w, g);
-  const real* sz = m.geom_size[g];
+MJ_HD void support_geom(const CObj& o, const real* dir, real* res, int lane) {
+  const real* R = o.R;
+  const real* sz = o.size;
   const real dl[3] = {R[0] * dir[0] + R[3] * dir[1] + R[6] * dir[2], R[1] * dir[0] + R[4] * dir[1] + R[7] * dir[2],
                       R[2] * dir[0] + R[5] * dir[1] + R[8] * dir[2]};
   real loc[3] = {0, 0, 0};
-  const int tp = m.geom_type[g];
-  if (tp == GEOM_BOX) {
+  if (o.type == GEOM_BOX) {
     for (int k = 0; k < 3; ++k) loc[k] = dl[k] >= 0 ? sz[k] : -sz[k];
-  } else if (tp == GEOM_CYLINDER) {
-    const real t = sqrtf(dl[0] * dl[0] + dl[1] * dl[1]);
-    if (t > MINVAL) { loc[0] = dl[0] / t * sz[0]; loc[1] = dl[1] / t * sz[0]; }
+  } else if (o.type == GEOM_CYLINDER) {
+    const real t2 = dl[0] * dl[0] + dl[1] * dl[1];
+    if (t2 > MINVAL * MINVAL) { const real it = sz[0] / sqrtf(t2); loc[0] = dl[0] * it; loc[1] = dl[1] * it; }
     loc[2] = dl[2] >= 0 ? sz[1] : -sz[1];
-  } else if (tp == GEOM_MESH) {
+  } else if (o.type == GEOM_MESH) {
     // lane-parallel argmax over the hull vertices; the first vertex reaching the maximum wins
-    const real* hv = hull + 3 * m.geom_hulladr[g];
-    const int nvert = m.geom_hullnum[g];
+    const real* hv = o.hv;
+    const int nvert = o.nvert;
     real bd = -1e30f;
     int bi = nvert;
     for (int v = lane; v < nvert; v += NL) {
@@ -247,14 +263,20 @@ MJ_FN void support_geom(const Model& m, const real* hull, Work& w, const CObj& o
     loc[0] = hv[3 * best]; loc[1] = hv[3 * best + 1]; loc[2] = hv[3 * best + 2];
   }
   for (int k = 0; k < 3; ++k)
-    res[k] = gpos(m, w, g)[k] + R[3 * k] * loc[0] + R[3 * k + 1] * loc[1] + R[3 * k + 2] * loc[2] + dir[k] * o.margin;
+    res[k] = o.pos[k] + R[3 * k] * loc[0] + R[3 * k + 1] * loc[1] + R[3 * k + 2] * loc[2] + dir[k] * o.margin;
 }
 
+#if defined(MJ_DEBUG) && !defined(__CUDA_ARCH__)
+static long g_support_calls = 0, g_mpr_calls = 0, g_mpr_hits = 0;
+#endif
 template <int NL>
-MJ_FN void mpr_support(const Model& m, const real* hull, Work& w, const CObj& o1, const CObj& o2, const real* dir, Supp* s, int lane) {
+MJ_FN void mpr_support(const CObj& o1, const CObj& o2, const real* dir, Supp* s, int lane) {
+#if defined(MJ_DEBUG) && !defined(__CUDA_ARCH__)
+  ++g_support_calls;
+#endif
   const real nd[3] = {-dir[0], -dir[1], -dir[2]};
-  support_geom<NL>(m, hull, w, o1, dir, s->v1, lane);
-  support_geom<NL>(m, hull, w, o2, nd, s->v2, lane);
+  support_geom<NL>(o1, dir, s->v1, lane);
+  support_geom<NL>(o2, nd, s->v2, lane);
   sub3(s->v, s->v1, s->v2);
 }
 MJ_HD int is_zero(real x) { return fabsf(x) < CCD_EPS; }
@@ -322,17 +344,16 @@ MJ_FN real tri_dist2(const real* Pt, const real* x0, const real* B, const real* 
 
 // returns 1 with (depth, dir, pos) when the (inflated) geoms penetrate; all lanes take the same path
 template <int NL>
-MJ_FN int mpr_penetration(const Model& m, const real* hull, Work& w, const CObj& o1, const CObj& o2, real* depth, real* dir,
-                          real* pos, NarrowScratch* S, int lane) {
+MJ_FN int mpr_penetration(const CObj& o1, const CObj& o2, real* depth, real* dir, real* pos, NarrowScratch* S, int lane) {
   Supp* P = S->P;
   Supp& v4 = S->v4;
   const real origin[3] = {0, 0, 0};
-  for (int k = 0; k < 3; ++k) { P[0].v1[k] = gpos(m, w, o1.g)[k]; P[0].v2[k] = gpos(m, w, o2.g)[k]; }
+  for (int k = 0; k < 3; ++k) { P[0].v1[k] = o1.pos[k]; P[0].v2[k] = o2.pos[k]; }
   sub3(P[0].v, P[0].v1, P[0].v2);
   if (is_zero(P[0].v[0]) && is_zero(P[0].v[1]) && is_zero(P[0].v[2])) P[0].v[0] = 0.00001f;
   real d[3] = {-P[0].v[0], -P[0].v[1], -P[0].v[2]}, va[3], vb[3], dt;
   normalize3(d);
-  mpr_support<NL>(m, hull, w, o1, o2, d, &P[1], lane);
+  mpr_support<NL>(o1, o2, d, &P[1], lane);
   dt = dot3(P[1].v, d);
   if (is_zero(dt) || dt < 0) return 0;
   cross3(d, P[0].v, P[1].v);
@@ -345,7 +366,7 @@ MJ_FN int mpr_penetration(const Model& m, const real* hull, Work& w, const CObj&
     return 1;
   }
   normalize3(d);
-  mpr_support<NL>(m, hull, w, o1, o2, d, &P[2], lane);
+  mpr_support<NL>(o1, o2, d, &P[2], lane);
   dt = dot3(P[2].v, d);
   if (is_zero(dt) || dt < 0) return 0;
   sub3(va, P[1].v, P[0].v);
@@ -357,7 +378,7 @@ MJ_FN int mpr_penetration(const Model& m, const real* hull, Work& w, const CObj&
     for (int k = 0; k < 3; ++k) d[k] = -d[k];
   }
   for (int guard = 0; guard < 100; ++guard) {
-    mpr_support<NL>(m, hull, w, o1, o2, d, &P[3], lane);
+    mpr_support<NL>(o1, o2, d, &P[3], lane);
     dt = dot3(P[3].v, d);
     if (is_zero(dt) || dt < 0) return 0;
     int cont = 0;
@@ -379,14 +400,14 @@ MJ_FN int mpr_penetration(const Model& m, const real* hull, Work& w, const CObj&
     portal_dir(P, d);
     dt = dot3(d, P[1].v);
     if (is_zero(dt) || dt > 0) break;
-    mpr_support<NL>(m, hull, w, o1, o2, d, &v4, lane);
+    mpr_support<NL>(o1, o2, d, &v4, lane);
     dt = dot3(v4.v, d);
     if (!(is_zero(dt) || dt > 0) || reach_tolerance(P, &v4, d) || guard > 200) return 0;
     expand_portal(P, &v4);
   }
   for (int it = 0;; ++it) {  // findPenetr
     portal_dir(P, d);
-    mpr_support<NL>(m, hull, w, o1, o2, d, &v4, lane);
+    mpr_support<NL>(o1, o2, d, &v4, lane);
     if (reach_tolerance(P, &v4, d) || it > MPR_ITER) {
       real wit[3];
       *depth = sqrtf(tri_dist2(origin, P[1].v, P[2].v, P[3].v, wit));
@@ -441,8 +462,9 @@ MJ_FN int plane_convex(const Model& m, const real* hull, Work& w, int gp, int g,
     }
     return nc;
   }
-  const CObj o = {g, 0.0f};
-  support_geom<NL>(m, hull, w, o, nd, pt, lane);
+  CObj& o = reinterpret_cast<NarrowScratch*>(&w.H[0][0])->o1;
+  make_cobj(o, m, hull, w, g, 0.0f);
+  support_geom<NL>(o, nd, pt, lane);
   sub3(rel, pt, gpos(m, w, gp));
   const real dist = dot3(rel, n);
   if (dist >= margin) return 0;
@@ -575,9 +597,21 @@ MJ_FN void collide(const Model& m, const real* hull, Work& w, int lane) {
     } else if (t1 == GEOM_BOX && t2 == GEOM_BOX) {
       n = box_box(gpos(m, w, ga), gmat(m, w, ga), m.geom_size[ga], gpos(m, w, gb), gmat(m, w, gb), m.geom_size[gb], margin, rc, S);
     } else {
-      const CObj o1 = {ga, 0.5f * margin}, o2 = {gb, 0.5f * margin};
+      make_cobj(S->o1, m, hull, w, ga, 0.5f * margin);
+      make_cobj(S->o2, m, hull, w, gb, 0.5f * margin);
+      const CObj& o1 = S->o1;
+      const CObj& o2 = S->o2;
       real depth, dir[3], pos[3];
-      if (mpr_penetration<NL>(m, hull, w, o1, o2, &depth, dir, pos, S, lane)) {
+#if defined(MJ_DEBUG) && !defined(__CUDA_ARCH__)
+      ++g_mpr_calls;
+      const long before = g_support_calls;
+#endif
+      const int pen = mpr_penetration<NL>(o1, o2, &depth, dir, pos, S, lane);
+#if defined(MJ_DEBUG) && !defined(__CUDA_ARCH__)
+      g_mpr_hits += pen;
+      if (g_support_calls - before > 12) printf("  mpr pair (%d,%d) types %d %d: %ld supports, pen %d depth %g\n", ga, gb, t1, t2, g_support_calls - before, pen, pen ? (double)depth : 0.0);
+#endif
+      if (pen) {
         for (int k = 0; k < 3; ++k) { rc[0].pos[k] = pos[k]; rc[0].normal[k] = dir[k]; }
         rc[0].dist = margin - depth;
         n = 1;

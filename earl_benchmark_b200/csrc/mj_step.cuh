@@ -17,14 +17,12 @@ MJ_FN void substep(const Model& m, const real* hull, Work& w, int lane) {
   kinematics<NL>(m, w, lane);
   MJ_PHASE_END(w, 0);
   mass_matrix<NL>(m, w, lane);
-  bsync<NL>();
   MJ_PHASE_END(w, 1);
   collide<NL>(m, hull, w, lane);
   bsync<NL>();
   MJ_PHASE_END(w, 2);
   make_constraints<NL>(m, w, lane);
   contact_rows<NL>(m, w, lane);
-  bsync<NL>();
   MJ_PHASE_END(w, 3);
   bias_forces<NL>(m, w, lane);
   MJ_PHASE_END(w, 4);

@@ -102,3 +102,6 @@ extern "C" int emu_hits(void* h, int* pairs) {
   }
   return e->w.nhit;
 }
+#if defined(MJ_DEBUG)
+extern "C" void emu_mpr_stats(long* out) { out[0] = earl::mj::g_support_calls; out[1] = earl::mj::g_mpr_calls; out[2] = earl::mj::g_mpr_hits; }
+#endif
