@@ -57,6 +57,11 @@ struct StepArgs {
   unsigned* ll_steps;        // [N] steps_since_goal_change
   unsigned goal_freq;
   unsigned long long* work;  // 6 counters
+  // cost-sorted scheduling: environments are visited in the order of `order_cur` in chunks of kWPB grabbed from an
+  // atomic counter; every env appends itself to the front (expensive last step) or the back (cheap) of `order_next`
+  const int* order_cur;
+  int* order_next;
+  unsigned* sched;           // {next chunk, #expensive, #cheap}
   int n;
   unsigned horizon;
   unsigned flags;
@@ -107,7 +112,7 @@ __device__ __forceinline__ float gather_rec(const Work& w, int idx) {
 __device__ __forceinline__ void load_env(Work& w, const float* rec, int lane) {
   scatter_rec(w, lane, rec[lane]);
   scatter_rec(w, lane + 32, rec[lane + 32]);
-  if (lane == 0) { w.bad = 0; w.acc_iter = w.acc_rows = w.acc_con = 0; }
+  if (lane == 0) { w.bad = 0; w.acc_iter = w.acc_rows = w.acc_con = w.acc_mpr = 0; }
 #ifdef MJ_PHASE_TIMING
   if (lane < 8) w.phase[lane] = 0;
 #endif
@@ -144,11 +149,21 @@ __global__ void __launch_bounds__(kWPB * 32, 1) mj_step_kernel(const StepArgs a)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   Work& w = *reinterpret_cast<Work*>(smem + kModelBytes + warp * kWorkStride);
   unsigned long long it = 0, rows = 0, cons = 0, bad = 0, envs = 0;
-  // every warp of a block makes the same number of trips (the substep has block-wide phase barriers); a warp without
-  // an environment in the last trip re-runs the last environment and discards the result
-  for (int base = blockIdx.x * kWPB; base < a.n; base += gridDim.x * kWPB) {
+  // Every warp of a block makes the same trips (the substep has block-wide phase barriers); a warp without an
+  // environment in the last chunk re-runs another environment and discards the result.  Chunks of kWPB consecutive
+  // entries of the cost-sorted order are handed out dynamically, so blocks that draw expensive chunks (gripper on
+  // the handle: MPR solves, more Newton iterations) take fewer of them and cheap environments are not held back at
+  // the phase barriers by an expensive neighbour.
+  __shared__ int s_chunk;
+  const int nchunks = (a.n + kWPB - 1) / kWPB;
+  for (;;) {
+    __syncthreads();
+    if (threadIdx.x == 0) s_chunk = (int)atomicAdd(&a.sched[0], 1u);
+    __syncthreads();
+    const int base = s_chunk * kWPB;
+    if (s_chunk >= nchunks) break;
     const bool live = base + warp < a.n;
-    const int env = live ? base + warp : a.n - 1;
+    const int env = a.order_cur[live ? base + warp : base];  // idle warps shadow the chunk's first env (same barriers, no store)
     float* rec = a.state + (size_t)env * REC_FLOATS;
     load_env(w, rec, lane);
     if (lane < kAct) w.action[lane] = a.actions[(size_t)env * kAct + lane];
@@ -178,6 +193,10 @@ __global__ void __launch_bounds__(kWPB * 32, 1) mj_step_kernel(const StepArgs a)
       if (a.success) a.success[env] = ok ? 1 : 0;
       if (a.ep_return) a.ep_return[env] += (double)r;
       it += w.acc_iter; rows += w.acc_rows; cons += w.acc_con; bad += w.bad ? 1 : 0; envs += 1;
+      // next step's visiting order: expensive environments first and together
+      const bool heavy = w.acc_mpr > 0 || w.acc_iter > 2 * sm->frame_skip;
+      const unsigned slot = heavy ? atomicAdd(&a.sched[1], 1u) : (unsigned)a.n - 1u - atomicAdd(&a.sched[2], 1u);
+      a.order_next[slot] = env;
 #ifdef MJ_PHASE_TIMING
       for (int k = 0; k < 8; ++k) atomicAdd(&a.work[8 + k], (unsigned long long)w.phase[k]);
 #endif
@@ -285,6 +304,9 @@ struct earl_mj_handle {
   StepArgs a{};
   float* d_tmpl = nullptr;
   float* d_goals = nullptr;
+  int* d_order[2] = {nullptr, nullptr};
+  unsigned* d_sched = nullptr;
+  int order_sel = 0;
   // host-path staging
   float* d_act = nullptr;
   float* d_obs = nullptr;
@@ -377,7 +399,16 @@ int earl_mj_create(const earl_mj_config* cfg, const void* model_blob, size_t mod
   if (!rc && (cfg->flags & EARL_FLAG_LIFELONG)) { rc = h->alloc(&a.ll_return, n); if (!rc) rc = h->alloc(&a.ll_steps, n); }
   if (!rc) rc = h->alloc(&a.work, 16);
   if (!rc) rc = h->alloc(&h->d_tmpl, REC_FLOATS);
+  if (!rc) rc = h->alloc(&h->d_order[0], n);
+  if (!rc) rc = h->alloc(&h->d_order[1], n);
+  if (!rc) rc = h->alloc(&h->d_sched, 4);
   if (rc) { earl_mj_destroy(h); return rc; }
+  {
+    std::vector<int> ident(n);
+    for (size_t k = 0; k < n; ++k) ident[k] = (int)k;
+    e = cudaMemcpy(h->d_order[0], ident.data(), n * sizeof(int), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { earl_mj_destroy(h); return failf(EARL_ERR_CUDA, "order upload: %s", cudaGetErrorString(e)); }
+  }
   e = cudaMemcpy(d_model, &m, sizeof(Model), cudaMemcpyHostToDevice);
   if (e == cudaSuccess && !h->hm.hull_vert.empty())
     e = cudaMemcpy(d_hull, h->hm.hull_vert.data(), h->hm.hull_vert.size() * sizeof(float), cudaMemcpyHostToDevice);
@@ -484,6 +515,11 @@ int earl_mj_step(earl_mj_handle* h, const float* actions_dev, float* obs_dev, fl
   a.reward = reward_dev;
   a.done = done_dev;
   a.success = success_dev;
+  a.order_cur = h->d_order[h->order_sel];
+  a.order_next = h->d_order[h->order_sel ^ 1];
+  a.sched = h->d_sched;
+  h->order_sel ^= 1;
+  CU(cudaMemsetAsync(h->d_sched, 0, 4 * sizeof(unsigned), static_cast<cudaStream_t>(stream)));
   mj_step_kernel<<<grid_for(h, a.n), kWPB * 32, kSmemBytes, static_cast<cudaStream_t>(stream)>>>(a);
   CU(cudaGetLastError());
   h->launches += 1;

@@ -597,6 +597,7 @@ MJ_FN void collide(const Model& m, const real* hull, Work& w, int lane) {
     } else if (t1 == GEOM_BOX && t2 == GEOM_BOX) {
       n = box_box(gpos(m, w, ga), gmat(m, w, ga), m.geom_size[ga], gpos(m, w, gb), gmat(m, w, gb), m.geom_size[gb], margin, rc, S);
     } else {
+      if (lane == 0) w.acc_mpr += 1;
       make_cobj(S->o1, m, hull, w, ga, 0.5f * margin);
       make_cobj(S->o2, m, hull, w, gb, 0.5f * margin);
       const CObj& o1 = S->o1;

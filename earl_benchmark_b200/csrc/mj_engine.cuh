@@ -157,7 +157,7 @@ struct Work {
   // diagnostics
   int solver_iter;
   int bad;
-  int acc_iter, acc_rows, acc_con;  // summed over the substeps of one env step
+  int acc_iter, acc_rows, acc_con, acc_mpr;  // summed over the substeps of one env step
 #ifdef MJ_PHASE_TIMING
   long long phase[8], phase_t0;     // SM cycles per engine phase (profiling builds only)
 #endif
