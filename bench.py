@@ -209,7 +209,8 @@ def run_door(dev, rank, world, sm_max_mhz, sm_count, with_cpu):
                "work": {"newton_iterations_per_substep": (w1["newton_iterations"] - w0["newton_iterations"]) / sub,
                         "constraint_rows_per_substep": (w1["constraint_rows"] - w0["constraint_rows"]) / sub,
                         "contacts_per_substep": (w1["contacts"] - w0["contacts"]) / sub,
-                        "bad_states": w1["bad_states"] - w0["bad_states"]},
+                        "bad_states": w1["bad_states"] - w0["bad_states"],
+                        "overflow_states": w1["overflow_states"] - w0["overflow_states"]},
                "kernel": "mj_step_kernel (one warp per env, 16 envs per SM in flight)"}
         if with_cpu:
             procs = os.cpu_count() or 1

@@ -148,7 +148,7 @@ __global__ void __launch_bounds__(kWPB * 32, 1) mj_step_kernel(const StepArgs a)
   load_model(sm, a.model);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   Work& w = *reinterpret_cast<Work*>(smem + kModelBytes + warp * kWorkStride);
-  unsigned long long it = 0, rows = 0, cons = 0, bad = 0, envs = 0;
+  unsigned long long it = 0, rows = 0, cons = 0, bad = 0, over = 0, envs = 0;
   // Every warp of a block makes the same trips (the substep has block-wide phase barriers); a warp without an
   // environment in the last chunk re-runs another environment and discards the result.  Chunks of kWPB consecutive
   // entries of the cost-sorted order are handed out dynamically, so blocks that draw expensive chunks (gripper on
@@ -186,13 +186,13 @@ __global__ void __launch_bounds__(kWPB * 32, 1) mj_step_kernel(const StepArgs a)
       // PersistentStateWrapper.step: counters, horizon `done` (persistent_state_wrapper.py:22-31)
       const unsigned steps = w.steps == 0xffffffffu ? w.steps : w.steps + 1;
       w.steps = steps;
-      w.flags = (w.flags & ~2u) | (ok ? 3u : 0u) | (w.bad ? 4u : 0u);
+      w.flags = (w.flags & ~2u) | (ok ? 3u : 0u) | ((w.bad & 1) ? 4u : 0u) | ((w.bad & 2) ? 8u : 0u);
       const float r = ok ? 1.0f : 0.0f;
       a.reward[env] = r;
       a.done[env] = steps >= a.horizon ? 1 : 0;
       if (a.success) a.success[env] = ok ? 1 : 0;
       if (a.ep_return) a.ep_return[env] += (double)r;
-      it += w.acc_iter; rows += w.acc_rows; cons += w.acc_con; bad += w.bad ? 1 : 0; envs += 1;
+      it += w.acc_iter; rows += w.acc_rows; cons += w.acc_con; bad += (w.bad & 1) ? 1 : 0; over += (w.bad & 2) ? 1 : 0; envs += 1;
       // next step's visiting order: expensive environments first and together
       const bool heavy = w.acc_mpr > 0 || w.acc_iter > 2 * sm->frame_skip;
       const unsigned slot = heavy ? atomicAdd(&a.sched[1], 1u) : (unsigned)a.n - 1u - atomicAdd(&a.sched[2], 1u);
@@ -211,6 +211,7 @@ __global__ void __launch_bounds__(kWPB * 32, 1) mj_step_kernel(const StepArgs a)
     atomicAdd(&a.work[3], rows);
     atomicAdd(&a.work[4], cons);
     atomicAdd(&a.work[5], bad);
+    atomicAdd(&a.work[6], over);
   }
 }
 
@@ -619,18 +620,18 @@ int earl_mj_eval_stats(earl_mj_handle* h, double* out4_dev, void* stream) {
   return 0;
 }
 
-int earl_mj_work_counters(earl_mj_handle* h, uint64_t* out6_host) {
+int earl_mj_work_counters(earl_mj_handle* h, uint64_t* out7_host) {
   if (int rc = check_handle(h)) return rc;
-  if (!out6_host) return failf(EARL_ERR_INVALID, "null out");
+  if (!out7_host) return failf(EARL_ERR_INVALID, "null out");
   CU(cudaDeviceSynchronize());
-  CU(cudaMemcpy(out6_host, h->a.work, 6 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(out7_host, h->a.work, 7 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
 #ifdef MJ_PHASE_TIMING
   uint64_t ph[8];
   CU(cudaMemcpy(ph, h->a.work + 8, sizeof(ph), cudaMemcpyDeviceToHost));
   static const char* names[8] = {"kinematics", "mass_matrix", "collide", "constraint_rows", "bias", "smooth", "solve", "euler"};
   uint64_t tot = 0;
   for (int k = 0; k < 8; ++k) tot += ph[k];
-  for (int k = 0; k < 8; ++k) fprintf(stderr, "[mj phase] %-16s %6.2f %%  %10.0f cycles/env-step\n", names[k], 100.0 * ph[k] / (tot ? tot : 1), (double)ph[k] / (out6_host[0] ? out6_host[0] : 1));
+  for (int k = 0; k < 8; ++k) fprintf(stderr, "[mj phase] %-16s %6.2f %%  %10.0f cycles/env-step\n", names[k], 100.0 * ph[k] / (tot ? tot : 1), (double)ph[k] / (out7_host[0] ? out7_host[0] : 1));
 #endif
   return 0;
 }

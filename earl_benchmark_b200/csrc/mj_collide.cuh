@@ -527,12 +527,15 @@ MJ_FN void compact_append(Work& w, int item, int flag, int lane) {
     const int pos = base + __popc(mask & ((1u << lane) - 1u));
     if (flag && pos < MAXHIT) w.hit_list[pos] = (unsigned char)item;
     __syncwarp();
-    if (lane == 0) { const int n = base + __popc(mask); w.nhit = n < MAXHIT ? n : MAXHIT; }
+    if (lane == 0) { const int n = base + __popc(mask); w.nhit = n < MAXHIT ? n : MAXHIT; if (n > MAXHIT) w.bad |= 2; }
     __syncwarp();
     return;
   }
 #endif
-  if (flag && w.nhit < MAXHIT) w.hit_list[w.nhit++] = (unsigned char)item;
+  if (flag) {
+    if (w.nhit < MAXHIT) w.hit_list[w.nhit++] = (unsigned char)item;
+    else w.bad |= 2;  // capacity overflow: a candidate pair was dropped
+  }
 }
 
 template <int NL>
@@ -621,7 +624,8 @@ MJ_FN void collide(const Model& m, const real* hull, Work& w, int lane) {
     const int base = w.ncon;
     int added = 0;
     for (int c = 0; c < n; ++c) {
-      if (rc[c].dist >= margin || base + added >= MAXCON) continue;
+      if (rc[c].dist >= margin) continue;
+      if (base + added >= MAXCON) { if (lane == 0) w.bad |= 2; continue; }
       const int k = base + added;
       ++added;
       if (lane == 0) {
@@ -648,7 +652,7 @@ MJ_FN void contact_rows(const Model& m, Work& w, int lane) {
   for (int c = 0; c < w.ncon; ++c) {
     const int g1 = w.con_g1[c], g2 = w.con_g2[c];
     const int dim = m.geom_condim[g1] > m.geom_condim[g2] ? m.geom_condim[g1] : m.geom_condim[g2];
-    if (row + dim > MAXEFC) break;
+    if (row + dim > MAXEFC) { if (lane == 0) w.bad |= 2; break; }
     if (lane == 0) { w.con_row[c] = row; w.con_dim[c] = dim; }
     row += dim;
     ++used;

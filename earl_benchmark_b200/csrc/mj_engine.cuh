@@ -110,7 +110,7 @@ constexpr int REC_QVEL = 20;    // [20,36)
 constexpr int REC_WARM = 36;    // [36,52)  qacc_warmstart
 constexpr int REC_MOCAP = 52;   // 3 doubles = 6 floats [52,58)
 constexpr int REC_STEPS = 58;   // u32 steps_since_reset
-constexpr int REC_FLAGS = 59;   // u32: bit0 success-any, bit1 success-last, bit2 bad_state
+constexpr int REC_FLAGS = 59;   // u32: bit0 success-any, bit1 success-last, bit2 bad_state, bit3 capacity overflow
 constexpr int REC_GOALROW = 60; // u32 goal row
 constexpr int REC_SPARE = 61;
 
@@ -156,7 +156,7 @@ struct Work {
   unsigned steps, flags, goalrow;
   // diagnostics
   int solver_iter;
-  int bad;
+  int bad;  // bit 0: numerical failure (non-positive pivot), bit 1: a fixed capacity (pairs / contacts / rows) overflowed
   int acc_iter, acc_rows, acc_con, acc_mpr;  // summed over the substeps of one env step
 #ifdef MJ_PHASE_TIMING
   long long phase[8], phase_t0;     // SM cycles per engine phase (profiling builds only)
@@ -690,6 +690,7 @@ MJ_FN void make_constraints(const Model& m, Work& w, int lane) {
     const int qa = m.jnt_qposadr[j], da = m.jnt_dofadr[j];
     for (int side = 0; side < 2; ++side) {
       const real dist = side == 0 ? w.qpos[qa] - m.jnt_range[j][0] : m.jnt_range[j][1] - w.qpos[qa];
+      if (dist < m.jnt_margin[j] && r >= MAXEFC && lane == 0) w.bad |= 2;
       if (dist < m.jnt_margin[j] && r < MAXEFC) {
         for (int c = lane; c < nv; c += NL) w.J[r][c] = (c == da) ? (side == 0 ? 1.0f : -1.0f) : 0.0f;
         if (lane == 0) { w.e_pos[r] = dist; w.e_type[r] = ROW_LIMIT; }
@@ -844,7 +845,7 @@ MJ_FN void solve(const Model& m, Work& w, int lane) {
       w.fcon[i] = 0;
     }
     wsync<NL>();
-    if (!spd_solve<NL>(w.H, nv, w.acc, lane)) w.bad = 1;
+    if (!spd_solve<NL>(w.H, nv, w.acc, lane)) w.bad |= 1;
     w.solver_iter = 0;
     return;
   }
@@ -877,7 +878,7 @@ MJ_FN void solve(const Model& m, Work& w, int lane) {
     }
     for (int i = lane; i < nv; i += NL) w.dir[i] = -w.grad[i];
     wsync<NL>();
-    if (!spd_solve<NL>(w.H, nv, w.dir, lane)) { w.bad = 1; break; }
+    if (!spd_solve<NL>(w.H, nv, w.dir, lane)) { w.bad |= 1; break; }
     // line search along dir
     for (int r = lane; r < ne; r += NL) {
       real s = 0;

@@ -57,7 +57,7 @@ MJ_FN void substep(const Model& m, const real* hull, Work& w, int lane) {
     w.warm[i] = w.acc[i];
   }
   wsync<NL>();
-  if (!spd_solve<NL>(w.H, nv, w.tmp, lane)) w.bad = 1;
+  if (!spd_solve<NL>(w.H, nv, w.tmp, lane)) w.bad |= 1;
   for (int i = lane; i < nv; i += NL) w.qvel[i] += h * w.tmp[i];
   wsync<NL>();
   for (int j = lane; j < m.njnt; j += NL) {

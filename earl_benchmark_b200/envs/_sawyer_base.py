@@ -239,9 +239,10 @@ class SawyerBatchedEnv:
     def work_counters(self):
         """dict of work done by the step kernel since creation (env_steps, substeps, newton_iterations, ...)."""
         self._ensure()
-        out = np.zeros(6, np.uint64)
+        out = np.zeros(7, np.uint64)
         _lib.check(_lib.lib().earl_mj_work_counters(self._handle, out.ctypes.data))
-        return dict(zip(("env_steps", "substeps", "newton_iterations", "constraint_rows", "contacts", "bad_states"),
+        return dict(zip(("env_steps", "substeps", "newton_iterations", "constraint_rows", "contacts", "bad_states",
+                         "overflow_states"),
                         (int(x) for x in out)))
 
     @property
