@@ -168,7 +168,11 @@ class EARLEnvs(object):
             return sawyer_peg.goal_states
         self._not_built()
 
-    def get_demonstrations(self):
+    def get_demonstrations(self, device=None):
+        """(forward, reverse) demonstration dicts (reference :238-247); `device` (batched extra) returns the numeric
+        arrays as tensors on that device."""
         if demos.available(self._env_name):
+            if device is not None:
+                return demos.load_to_device(self._env_name, 'forward', device), demos.load_to_device(self._env_name, 'reverse', device)
             return demos.load(self._env_name, 'forward'), demos.load(self._env_name, 'reverse')
         print('please download the demonstrations corresponding to ', self._env_name)

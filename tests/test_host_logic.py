@@ -115,3 +115,16 @@ def test_peg_reset_draws_replicate_the_reference_numpy_stream():
         for row, pos in want:
             r, p = env._draw_one()
             assert r == row and np.array_equal(p, pos)
+
+
+def test_demo_utilities():
+    fwd = demos.load("sawyer_door", "forward")
+    eps = demos.episodes(fwd)
+    assert [b - a for a, b in eps] == [78, 79, 75, 78, 85]
+    ang = demos.door_angle_from_obs(fwd["observations"][[a for a, _ in eps]])
+    assert np.all(ang > -np.pi / 3 - 1e-3) and np.all(ang < -np.pi / 3 + np.pi / 20 + 1e-3)   # reset_model's draw range
+    dev = demos.load_to_device("sawyer_door", "forward", "cpu")
+    assert dev["observations"].shape == (395, 14) and str(dev["actions"].dtype) == "torch.float32"
+    peg = demos.load("sawyer_peg", "forward")
+    p = demos.peg_position_from_obs(peg["observations"][0])
+    assert 0.0 <= p[0] <= 0.2 and 0.5 <= p[1] <= 0.7 and abs(p[2] - 0.02) < 1e-6                # obj_low / obj_high
