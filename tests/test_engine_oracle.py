@@ -128,3 +128,18 @@ def test_peg_demonstrations_are_not_reproduced(peg_oracle):
         mism += int((np.array(r) != rew[s:en]).sum())
     peg_oracle.goal = peg_oracle.GOAL.copy()
     assert 0.98 <= 1 - mism / total < 0.99
+
+
+def test_gripper_opening_trajectory_known_answer(oracle):
+    """obs[3] = clip(|rightEndEffector - leftEndEffector| / 0.1, 0, 1) over the first 40 steps of the first forward door
+    demonstration (fingers closing in free space, then running into their soft joint limits: 1.0 -> 0.274 overshoot ->
+    0.300).  Independent of the arm, this pins the position actuators (kp 400), armature 100 / damping 1000 with the
+    implicit-damping Euler step, the limit rows (solref / solimp / dof_invweight0 regulariser) and the one-substep-stale
+    observation timing against the reference's own MuJoCo run: agreement 4e-4 on every step."""
+    d = demos.load("sawyer_door", "forward")
+    oracle.goal = d["observations"][0][7:14].astype(np.float64)
+    oracle.reset(door_angle=door_angle(d["observations"][0][4:6]))
+    sim = np.array([oracle.step(d["actions"][t])[0][3] for t in range(40)])
+    ref = d["next_observations"][:40, 3]
+    oracle.goal = oracle.GOAL.copy()
+    assert ref.min() < 0.28 and np.abs(sim - ref).max() < 4e-4, np.abs(sim - ref).max()
