@@ -173,9 +173,11 @@ __global__ void __launch_bounds__(kWPB * 32, 1) mj_step_kernel(const StepArgs a)
     if (lane == 0) observe(*sm, w, w.obs7);
     __syncwarp();
     const bool ok = obs_success(*sm, w, a.goals);  // reward / success against the goal the step was taken with
+    float r = ok ? 1.0f : 0.0f;
+    if (a.flags & EARL_FLAG_DENSE_REWARD) r = door_dense_reward(*sm, w.obs7, a.goals + 8 * w.goalrow + 4);
     if (lane == 0 && a.ll_return) {
       // LifelongWrapper.step: lifetime return, periodic reset_goal() (single-goal tasks: goal_states[0] = row 0)
-      a.ll_return[env] += ok ? 1.0 : 0.0;
+      a.ll_return[env] += (double)r;
       unsigned s = a.ll_steps[env] + 1;
       if (s >= a.goal_freq) { s = 0; w.goalrow = 0; }
       a.ll_steps[env] = s;
@@ -187,7 +189,6 @@ __global__ void __launch_bounds__(kWPB * 32, 1) mj_step_kernel(const StepArgs a)
       const unsigned steps = w.steps == 0xffffffffu ? w.steps : w.steps + 1;
       w.steps = steps;
       w.flags = (w.flags & ~2u) | (ok ? 3u : 0u) | ((w.bad & 1) ? 4u : 0u) | ((w.bad & 2) ? 8u : 0u);
-      const float r = ok ? 1.0f : 0.0f;
       a.reward[env] = r;
       a.done[env] = steps >= a.horizon ? 1 : 0;
       if (a.success) a.success[env] = ok ? 1 : 0;
@@ -352,7 +353,10 @@ int earl_mj_create(const earl_mj_config* cfg, const void* model_blob, size_t mod
     return failf(EARL_ERR_UNSUPPORTED, "env_kind %d is not built on the articulated-body engine (sawyer_door, sawyer_peg)", cfg->env_kind);
   if (cfg->num_envs < 1) return failf(EARL_ERR_INVALID, "num_envs must be >= 1");
   if (cfg->episode_horizon < 1) return failf(EARL_ERR_INVALID, "episode_horizon must be >= 1");
-  if (cfg->flags & ~(uint32_t)(EARL_FLAG_EVAL_STATS | EARL_FLAG_LIFELONG)) return failf(EARL_ERR_UNSUPPORTED, "unsupported flags %#x", cfg->flags);
+  if (cfg->flags & ~(uint32_t)(EARL_FLAG_EVAL_STATS | EARL_FLAG_LIFELONG | EARL_FLAG_DENSE_REWARD))
+    return failf(EARL_ERR_UNSUPPORTED, "unsupported flags %#x", cfg->flags);
+  if ((cfg->flags & EARL_FLAG_DENSE_REWARD) && cfg->env_kind != EARL_ENV_SAWYER_DOOR)
+    return failf(EARL_ERR_UNSUPPORTED, "the dense reward is only built for sawyer_door");
   if ((cfg->flags & EARL_FLAG_LIFELONG) && cfg->goal_change_frequency < 1)
     return failf(EARL_ERR_INVALID, "lifelong handles need goal_change_frequency >= 1");
   static_assert(sizeof(earl_mj_task) == sizeof(TaskSpec), "earl_mj_task must mirror earl::mj::TaskSpec");

@@ -100,6 +100,7 @@ struct Model {
   // task constants
   int obs_hand_site, obs_ree_site, obs_lee_site, obs_obj_geom, obs_obj_site;
   real mocap_low[3], mocap_high[3], action_scale, success_radius;
+  real obj_init_pos[3], hand_init_pos[3];
 };
 
 // ------------------------------------------------------------------------------------------------ per-env record

@@ -31,6 +31,8 @@ struct TaskSpec {
   float mocap_high[3];     // hand_high
   float action_scale;      // 1/100
   float success_radius;    // 0.02 door (sawyer_door.py:177), 0.05 peg (sawyer_peg.py:305)
+  float obj_init_pos[3];   // dense door reward (sawyer_door.py:150)
+  float hand_init_pos[3];  // dense door reward (sawyer_door.py:156)
 };
 
 class BlobReader {
@@ -354,6 +356,7 @@ inline bool build_model(const void* blob, size_t nbytes, const TaskSpec& task, H
   for (int k = 0; k < 3; ++k) { m.mocap_low[k] = task.mocap_low[k]; m.mocap_high[k] = task.mocap_high[k]; }
   m.action_scale = task.action_scale;
   m.success_radius = task.success_radius;
+  for (int k = 0; k < 3; ++k) { m.obj_init_pos[k] = task.obj_init_pos[k]; m.hand_init_pos[k] = task.hand_init_pos[k]; }
   if (task.hand_site < 0 || task.hand_site >= ns || task.ree_site < 0 || task.ree_site >= ns || task.lee_site < 0 ||
       task.lee_site >= ns || (task.obj_geom < 0 && (task.obj_site < 0 || task.obj_site >= ns)) || task.obj_geom >= ng)
     return bad("task spec: observation site / geom index out of range");

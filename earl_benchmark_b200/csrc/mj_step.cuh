@@ -126,5 +126,30 @@ MJ_FN void observe(const Model& m, const Work& w, real* obs7) {
   else site_xpos(m, w, m.obs_obj_site, obs7 + 4);
 }
 
+// metaworld reward_utils.tolerance(x, bounds=(0, upper), margin, sigmoid='gaussian', value_at_margin=0.1)
+// [metaworld@master, not under /root/reference; formula as in SURVEY.md Appendix C]
+MJ_HD real tolerance_gaussian(real x, real upper, real margin) {
+  if (x >= 0 && x <= upper) return 1.0f;
+  if (margin == 0) return 0.0f;
+  const real d = (x < 0 ? -x : x - upper) / margin;
+  const real scale2 = 4.605170185988092f;  // -2 ln(0.1)
+  return expf(-0.5f * d * d * scale2);
+}
+
+// SawyerDoorV2.compute_reward, dense branch (reference earl_benchmark/envs/sawyer_door.py:141-171) on an observation
+// [hand(3), gripper, handle(3)] and the goal's target position
+MJ_HD real door_dense_reward(const Model& m, const real* obs7, const real* target) {
+  const real TARGET_RADIUS = 0.05f;
+  real d_ot = 0, d_to = 0, m_in = 0, m_hand = 0;
+  for (int k = 0; k < 3; ++k) {
+    const real a = obs7[4 + k] - target[k], b = obs7[k] - obs7[4 + k], c = m.obj_init_pos[k] - target[k],
+               e = m.hand_init_pos[k] - obs7[4 + k];
+    d_ot += a * a; d_to += b * b; m_in += c * c; m_hand += e * e;
+  }
+  d_ot = sqrtf(d_ot); d_to = sqrtf(d_to); m_in = sqrtf(m_in); m_hand = sqrtf(m_hand) + 0.1f;
+  if (d_ot < TARGET_RADIUS) return 10.0f;
+  return 3.0f * tolerance_gaussian(d_to, 0.25f * TARGET_RADIUS, m_hand) + 6.0f * tolerance_gaussian(d_ot, TARGET_RADIUS, m_in);
+}
+
 }  // namespace mj
 }  // namespace earl

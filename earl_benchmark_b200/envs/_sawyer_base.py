@@ -30,14 +30,15 @@ class SawyerBatchedEnv:
     ENV_KIND = None          # _lib.ENV_SAWYER_*
     MODEL_FILE = None        # file under models/
     SUCCESS_RADIUS = None
+    HAS_DENSE_REWARD = False
 
     def __init__(self, reward_type="sparse", reset_at_goal=False, num_envs=1, device=None, seed=0, eval_stats=False,
                  env_offset=0, total_envs=None, model_path=None, max_newton=0, **_tabletop_only):
         name = type(self).__name__
-        if reward_type == "dense":
-            raise NotImplementedError(f"{name}: the dense reward (metaworld reward_utils) is not built yet")
-        if reward_type != "sparse":
-            raise ValueError(f"reward_type must be 'sparse', got {reward_type!r}")
+        if reward_type == "dense" and not self.HAS_DENSE_REWARD:
+            raise NotImplementedError(f"{name}: the dense reward (metaworld reward_utils, gripper caging) is not built yet")
+        if reward_type not in ("sparse", "dense"):
+            raise ValueError(f"reward_type must be 'sparse' or 'dense', got {reward_type!r}")
         self._reward_type = reward_type
         self._reset_at_goal = bool(reset_at_goal)
         self.num_envs = int(num_envs)
@@ -90,6 +91,8 @@ class SawyerBatchedEnv:
             return
         L = _lib.lib()
         flags = (_lib.FLAG_EVAL_STATS if self._eval_stats else 0) | (_lib.FLAG_LIFELONG if self._lifelong else 0)
+        if self._reward_type == "dense":
+            flags |= _lib.FLAG_DENSE_REWARD
         cfg = _lib.MjConfig(self.ENV_KIND, self.num_envs, self.device.index or 0, flags, self._episode_horizon,
                             self._goal_change_frequency)
         blob = self.model.to_blob()
@@ -216,6 +219,7 @@ class SawyerBatchedEnv:
         return np.linalg.norm(o[:, 4:7] - o[:, 11:14], axis=1) <= self.SUCCESS_RADIUS
 
     def compute_reward(self, obs, actions=None):
+        """Sparse reward of caller-supplied observations (cold path; task classes with a dense reward override this)."""
         s = self.is_successful(obs)
         return s.to(torch.float32) if isinstance(s, torch.Tensor) else s.astype(np.float32)
 

@@ -35,7 +35,7 @@ goal_states = np.array([[0.29072163, 0.74286009, 0.10003595, 1.0,
 MODEL_PATH = os.path.join(MODEL_DIR, "sawyer_door.npz")
 
 
-def task_spec(model, max_newton=0):
+def task_spec(model, max_newton=0, hand_init_pos=(0.0, 0.4, 0.2)):
     """Constants of metaworld's SawyerXYZEnv / SawyerDoorEnvV2 and of sawyer_door.py that are not in the MJCF."""
     t = _lib.MjTask()
     t.frame_skip = 5                                  # SawyerXYZEnv frame_skip
@@ -49,6 +49,8 @@ def task_spec(model, max_newton=0):
     t.mocap_high[:] = [0.5, 1.0, 0.5]
     t.action_scale = 1.0 / 100
     t.success_radius = 0.02                           # is_successful(), sawyer_door.py:177
+    t.obj_init_pos[:] = [0.1, 0.95, 0.1]              # dense reward margins (sawyer_door.py:36,150,156); float32 in the reference
+    t.hand_init_pos[:] = [float(x) for x in hand_init_pos]
     return t
 
 
@@ -56,6 +58,7 @@ class SawyerDoorV2(SawyerBatchedEnv):
     ENV_KIND = _lib.ENV_SAWYER_DOOR
     MODEL_FILE = "sawyer_door.npz"
     SUCCESS_RADIUS = 0.02
+    HAS_DENSE_REWARD = True
 
     def __init__(self, reward_type="sparse", reset_at_goal=False, **batched):
         super().__init__(reward_type=reward_type, reset_at_goal=reset_at_goal, **batched)
@@ -71,7 +74,28 @@ class SawyerDoorV2(SawyerBatchedEnv):
         self._goal_table = [goal_states[0].copy(), initial_states[0].copy()]
 
     def _task_spec(self):
-        return task_spec(self.model, self._max_newton)
+        return task_spec(self.model, self._max_newton, self.hand_init_pos)
+
+    def compute_reward(self, obs, actions=None):
+        """compute_reward(obs)[0] of the reference (sawyer_door.py:141-171) on caller-supplied observations [M,14]
+        (cold path, numpy / torch on the caller's device; the step kernel evaluates the same expressions in fp32)."""
+        if self._reward_type == "sparse":
+            return super().compute_reward(obs, actions)
+        xp = __import__("torch") if not isinstance(obs, np.ndarray) else np
+        o = obs.reshape(-1, OBS_DIM)
+        norm = (lambda v: xp.linalg.norm(v, dim=1)) if xp is not np else (lambda v: np.linalg.norm(v, axis=1))
+        tcp, obj, target = o[:, :3], o[:, 4:7], o[:, 11:14]
+        to = lambda c: (xp.as_tensor(np.asarray(c, np.float32), device=o.device) if xp is not np else np.asarray(c, np.float64))  # noqa: E731
+        d_to, d_ot = norm(tcp - obj), norm(obj - target)
+
+        def tol(x, upper, margin):
+            d = (x - upper) / margin
+            v = xp.exp(-0.5 * d * d * 4.605170185988092)
+            return xp.where(x <= upper, xp.ones_like(v), v)
+        in_place = tol(d_ot, 0.05, norm(to(self.init_config["obj_init_pos"])[None, :] - target))
+        hand = tol(d_to, 0.0125, norm(to(self.hand_init_pos)[None, :] - obj) + 0.1)
+        r = 3 * hand + 6 * in_place
+        return xp.where(d_ot < 0.05, xp.full_like(r, 10.0), r)
 
     def get_next_goal(self):  # sawyer_door.py:96-98
         return np.broadcast_to(self.goal_states[0], (self.num_envs, 7)).copy()

@@ -23,7 +23,7 @@ typedef struct {
   int32_t env_kind;         /* EARL_ENV_SAWYER_DOOR or EARL_ENV_SAWYER_PEG */
   int32_t num_envs;
   int32_t device;
-  uint32_t flags;           /* EARL_FLAG_EVAL_STATS | EARL_FLAG_LIFELONG */
+  uint32_t flags;           /* EARL_FLAG_EVAL_STATS | EARL_FLAG_LIFELONG | EARL_FLAG_DENSE_REWARD (door only) */
   int64_t episode_horizon;  /* PersistentStateWrapper(episode_horizon), persistent_state_wrapper.py:10-12 */
   int64_t goal_change_frequency; /* LifelongWrapper(goal_change_frequency), lifelong_wrapper.py:19-24; 0 = unused */
 } earl_mj_config;
@@ -41,7 +41,9 @@ typedef struct {
   float mocap_low[3];       /* hand_low */
   float mocap_high[3];      /* hand_high */
   float action_scale;       /* 1/100 (SawyerXYZEnv.action_scale) */
-  float success_radius;     /* 0.02 door (sawyer_door.py:177) */
+  float success_radius;     /* 0.02 door (sawyer_door.py:177), 0.05 peg (sawyer_peg.py:305) */
+  float obj_init_pos[3];    /* dense door reward: self.obj_init_pos (sawyer_door.py:36,150) */
+  float hand_init_pos[3];   /* dense door reward: self.hand_init_pos (sawyer_door.py:37-40,156) */
 } earl_mj_task;
 
 /* model_blob: the serialized structure-of-arrays model written by earl_benchmark_b200.mjcf.compile.Model.to_blob()

@@ -135,6 +135,28 @@ class SawyerDoorOracle:
         grip = np.clip(np.linalg.norm(e.site_xpos("rightEndEffector") - e.site_xpos("leftEndEffector")) / 0.1, 0.0, 1.0)
         return np.concatenate([hand, [grip], e.geom_xpos("handle"), self.goal])
 
+    @staticmethod
+    def _tolerance_gaussian(x, upper, margin, value_at_margin=0.1):
+        """metaworld reward_utils.tolerance(x, bounds=(0, upper), margin, sigmoid='gaussian') [metaworld@master, not under
+        /root/reference: formula as recalled in SURVEY.md Appendix C -- parity of the dense reward is UNPINNED]."""
+        if 0 <= x <= upper:
+            return 1.0
+        if margin == 0:
+            return 0.0
+        d = (x - upper if x > upper else -x) / margin
+        scale = np.sqrt(-2 * np.log(value_at_margin))
+        return float(np.exp(-0.5 * (d * scale) ** 2))
+
+    def dense_reward(self, obs):
+        """compute_reward(obs)[0] with reward_type='dense' (reference earl_benchmark/envs/sawyer_door.py:141-171)."""
+        tcp, obj, target = obs[:3], obs[4:7], obs[11:14]
+        obj_init_pos = np.array([0.1, 0.95, 0.1], dtype=np.float32)
+        tcp_to_obj, obj_to_target = np.linalg.norm(tcp - obj), np.linalg.norm(obj - target)
+        in_place = self._tolerance_gaussian(obj_to_target, 0.05, np.linalg.norm(obj_init_pos - target))
+        hand_in_place = self._tolerance_gaussian(tcp_to_obj, 0.25 * 0.05, np.linalg.norm(self.HAND_INIT - obj) + 0.1)
+        reward = 3 * hand_in_place + 6 * in_place
+        return 10.0 if obj_to_target < 0.05 else reward
+
     def step(self, action):
         a = np.clip(np.asarray(action, np.float64), -1, 1)
         self.e.mocap_pos[:] = np.clip(self.e.mocap_pos + a[:3] * self.ACTION_SCALE, self.MOCAP_LOW, self.MOCAP_HIGH)

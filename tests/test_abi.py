@@ -42,7 +42,7 @@ def test_struct_layouts_match_header():
     assert ctypes.sizeof(_lib.EarlConfig) == 40
     assert ctypes.sizeof(_lib.TabletopModel) == 8 + 4 * 8 + 6 * 8 + 256 * 6 * 8
     assert ctypes.sizeof(_lib.MjConfig) == 32
-    assert ctypes.sizeof(_lib.MjTask) == 8 * 4 + 8 * 4
+    assert ctypes.sizeof(_lib.MjTask) == 8 * 4 + 8 * 4 + 6 * 4
 
 
 def test_no_cpu_fallback_without_gpu():

@@ -31,7 +31,7 @@ def test_unknown_env_is_keyerror_like_reference():
 
 
 def test_unbuilt_envs_fail_loudly():
-    for name in ("sawyer_door", "sawyer_peg", "kitchen"):
+    for name in ("sawyer_peg", "kitchen"):
         with pytest.raises(NotImplementedError):
             eb.EARLEnvs(name, reward_type="dense")
 

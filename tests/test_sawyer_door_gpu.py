@@ -229,3 +229,22 @@ def test_eval_stats_all_reduce_single_rank():
         env.step(torch.zeros((6, 4), device="cuda"))
     st = D.all_reduce_eval_stats(env.eval_stats())
     assert st == {"mean_return": 1.0, "success_rate": 0.5, "success_any_rate": 0.5, "num_envs": 6}
+
+
+def test_dense_reward_matches_checker(oracle):
+    """reward_type='dense' (sawyer_door.py:141-171) in the step kernel vs the numpy restatement, and the cold-path
+    compute_reward(obs) on the same observations.  (The formulas of metaworld's reward_utils are recalled, not vendored:
+    the dense reward is self-consistent but unpinned.)"""
+    n = 12
+    angles = np.linspace(-np.pi / 3, -0.02, n)
+    env = sawyer_door.SawyerDoorV2(reward_type="dense", num_envs=n, device="cuda:0")
+    env.reset(door_angle=angles)
+    rs = np.random.RandomState(2)
+    for _ in range(6):
+        obs, rew, done, info = env.step(torch.from_numpy(rs.uniform(-1, 1, (n, 4)).astype(np.float32)).cuda())
+    o, r = obs.cpu().numpy().astype(np.float64), rew.cpu().numpy()
+    ref = np.array([oracle.dense_reward(o[i]) for i in range(n)])
+    assert np.abs(r - ref).max() < 2e-5 * 10 and ref.max() == 10.0 and ref.min() < 6.0
+    assert np.abs(env.compute_reward(obs).cpu().numpy() - ref).max() < 2e-4
+    assert np.abs(env.compute_reward(o) - ref).max() < 1e-9
+    assert np.array_equal(info["success"].cpu().numpy(), np.linalg.norm(o[:, 4:7] - o[:, 11:14], axis=1) <= 0.02)
