@@ -569,3 +569,33 @@ int mje_contact_rows(const mjModelF *m, mjDataF *d, int row) {
   }
   return row;
 }
+
+/* direct entry points for the geometry unit tests (tests/test_collision_geometry.py) */
+int mje_test_box_box(const double *p1, const double *R1, const double *s1, const double *p2, const double *R2, const double *s2,
+                     double margin, double *out /* [8][7]: pos, normal, dist */) {
+  RawCon rc[8];
+  int n = box_box(p1, R1, s1, p2, R2, s2, margin, rc);
+  for (int c = 0; c < n; ++c) {
+    memcpy(out + 7 * c, rc[c].pos, 3 * sizeof(double));
+    memcpy(out + 7 * c + 3, rc[c].normal, 3 * sizeof(double));
+    out[7 * c + 6] = rc[c].dist;
+  }
+  return n;
+}
+
+int mje_test_mpr(int t1, const double *size1, const double *p1, const double *R1, int t2, const double *size2, const double *p2,
+                 const double *R2, double margin, double *out /* depth, dir[3], pos[3] */) {
+  static mjModelF m;
+  static mjDataF d;
+  static int types[2];
+  static double sizes[6];
+  types[0] = t1; types[1] = t2;
+  memcpy(sizes, size1, 3 * sizeof(double));
+  memcpy(sizes + 3, size2, 3 * sizeof(double));
+  m.geom_type = types;
+  m.geom_size = sizes;
+  memcpy(d.geom_xpos[0], p1, 3 * sizeof(double)); memcpy(d.geom_xpos[1], p2, 3 * sizeof(double));
+  memcpy(d.geom_xmat[0], R1, 9 * sizeof(double)); memcpy(d.geom_xmat[1], R2, 9 * sizeof(double));
+  CObj o1 = {&m, &d, 0, 0.5 * margin}, o2 = {&m, &d, 1, 0.5 * margin};
+  return mpr_penetration(&o1, &o2, out, out + 1, out + 4);
+}

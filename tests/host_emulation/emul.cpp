@@ -105,3 +105,21 @@ extern "C" int emu_hits(void* h, int* pairs) {
 #if defined(MJ_DEBUG)
 extern "C" void emu_mpr_stats(long* out) { out[0] = earl::mj::g_support_calls; out[1] = earl::mj::g_mpr_calls; out[2] = earl::mj::g_mpr_hits; }
 #endif
+// direct entry point for the geometry unit tests: the kernel's box-box routine on caller-supplied boxes
+extern "C" int emu_box_box(const float* p1, const float* R1, const float* s1, const float* p2, const float* R2, const float* s2,
+                           float margin, float* out /* [8][7] */) {
+  static NarrowScratch S;
+  const int n = box_box(p1, R1, s1, p2, R2, s2, margin, S.rc, &S);
+  for (int c = 0; c < n; ++c) {
+    for (int k = 0; k < 3; ++k) { out[7 * c + k] = S.rc[c].pos[k]; out[7 * c + 3 + k] = S.rc[c].normal[k]; }
+    out[7 * c + 6] = S.rc[c].dist;
+  }
+  return n;
+}
+extern "C" int emu_mpr(int t1, const float* size1, const float* p1, const float* R1, int t2, const float* size2, const float* p2,
+                       const float* R2, float margin, float* out /* depth, dir[3], pos[3] */) {
+  static NarrowScratch S;
+  S.o1 = CObj{t1, 0, 0.5f * margin, p1, R1, size1, nullptr};
+  S.o2 = CObj{t2, 0, 0.5f * margin, p2, R2, size2, nullptr};
+  return mpr_penetration<1>(S.o1, S.o2, out, out + 1, out + 4, &S, 0);
+}
