@@ -19,12 +19,17 @@ namespace earl {
 namespace mj {
 
 constexpr int GEOM_PLANE = 0, GEOM_CYLINDER = 5, GEOM_BOX = 6, GEOM_MESH = 7;
-constexpr real MPR_TOL = 1e-6f;
+// Portal refinement runs in fp64 (`mreal`) on fp32 poses: its termination tests (libccd: |x| < eps, portal tolerance 1e-6)
+// cannot be resolved in fp32, where the refinement stops at a different portal and contact normals of thin-box-vs-
+// cylinder pairs came out up to 30 degrees away from the fp64 result; rounding the INPUTS to fp32 changes nothing
+// measurable.  B200 issues fp64 at half the fp32 rate and MPR is a minor share of the step.
+typedef double mreal;
+constexpr mreal MPR_TOL = 1e-6;
 constexpr int MPR_ITER = 50;
-constexpr real CCD_EPS = 1.1920929e-07f;
+constexpr mreal CCD_EPS = 2.220446049250313e-16;
 
 struct RawCon { real pos[3], normal[3], dist; };
-struct Supp { real v[3], v1[3], v2[3]; };
+struct Supp { mreal v[3], v1[3], v2[3]; };
 // Narrow-phase scratch.  It lives in SHARED memory (aliased onto Work::H, which is idle during collision): every lane of
 // the warp runs the same narrow-phase code and writes identical values to identical addresses, so no lane ever reads a
 // value it did not also write itself; keeping these dynamically indexed arrays out of local memory keeps the kernel
@@ -40,18 +45,21 @@ struct CObj {
 };
 struct NarrowScratch {
   CObj o1, o2;
-  real A[3][3], B[3][3];
-  real poly[16][3], tmp[16][3];
   RawCon rc[8];
-  Supp P[4], v4;
+  union {
+    struct { real A[3][3], B[3][3], poly[16][3], tmp[16][3]; };  // box-box
+    struct { Supp P[4], v4; };                                   // portal refinement
+  };
 };
 static_assert(sizeof(NarrowScratch) <= sizeof(real) * MAXV * LDM, "narrow-phase scratch must fit in Work::H");
 
-MJ_HD void sub3(real* r, const real* a, const real* b) { r[0] = a[0] - b[0]; r[1] = a[1] - b[1]; r[2] = a[2] - b[2]; }
-MJ_HD real normalize3(real* v) {
-  real n = sqrtf(dot3(v, v));
-  if (n < MINVAL) { v[0] = 1; v[1] = v[2] = 0; return 0; }
-  real s = 1.0f / n;
+template <class T>
+MJ_HD void sub3(T* r, const T* a, const T* b) { r[0] = a[0] - b[0]; r[1] = a[1] - b[1]; r[2] = a[2] - b[2]; }
+template <class T>
+MJ_HD T normalize3(T* v) {
+  T n = msqrt(dot3(v, v));
+  if (n < (T)1e-15) { v[0] = 1; v[1] = v[2] = 0; return 0; }
+  T s = (T)1 / n;
   v[0] *= s; v[1] *= s; v[2] *= s;
   return n;
 }
@@ -235,72 +243,72 @@ MJ_HD void make_cobj(CObj& o, const Model& m, const real* hull, const Work& w, i
 }
 
 template <int NL>
-MJ_HD void support_geom(const CObj& o, const real* dir, real* res, int lane) {
+MJ_HD void support_geom(const CObj& o, const mreal* dir, mreal* res, int lane) {
   const real* R = o.R;
   const real* sz = o.size;
-  const real dl[3] = {R[0] * dir[0] + R[3] * dir[1] + R[6] * dir[2], R[1] * dir[0] + R[4] * dir[1] + R[7] * dir[2],
-                      R[2] * dir[0] + R[5] * dir[1] + R[8] * dir[2]};
-  real loc[3] = {0, 0, 0};
+  const mreal dl[3] = {R[0] * dir[0] + R[3] * dir[1] + R[6] * dir[2], R[1] * dir[0] + R[4] * dir[1] + R[7] * dir[2],
+                       R[2] * dir[0] + R[5] * dir[1] + R[8] * dir[2]};
+  mreal loc[3] = {0, 0, 0};
   if (o.type == GEOM_BOX) {
-    for (int k = 0; k < 3; ++k) loc[k] = dl[k] >= 0 ? sz[k] : -sz[k];
+    for (int k = 0; k < 3; ++k) loc[k] = dl[k] >= 0 ? (mreal)sz[k] : -(mreal)sz[k];
   } else if (o.type == GEOM_CYLINDER) {
-    const real t2 = dl[0] * dl[0] + dl[1] * dl[1];
-    if (t2 > MINVAL * MINVAL) { const real it = sz[0] / sqrtf(t2); loc[0] = dl[0] * it; loc[1] = dl[1] * it; }
-    loc[2] = dl[2] >= 0 ? sz[1] : -sz[1];
+    const mreal t = sqrt(dl[0] * dl[0] + dl[1] * dl[1]);
+    if (t > 1e-15) { loc[0] = dl[0] / t * sz[0]; loc[1] = dl[1] / t * sz[0]; }
+    loc[2] = dl[2] >= 0 ? (mreal)sz[1] : -(mreal)sz[1];
   } else if (o.type == GEOM_MESH) {
     // lane-parallel argmax over the hull vertices; the first vertex reaching the maximum wins
     const real* hv = o.hv;
     const int nvert = o.nvert;
-    real bd = -1e30f;
+    mreal bd = -1e300;
     int bi = nvert;
     for (int v = lane; v < nvert; v += NL) {
-      const real dd = hv[3 * v] * dl[0] + hv[3 * v + 1] * dl[1] + hv[3 * v + 2] * dl[2];
+      const mreal dd = hv[3 * v] * dl[0] + hv[3 * v + 1] * dl[1] + hv[3 * v + 2] * dl[2];
       if (dd > bd) { bd = dd; bi = v; }
     }
-    const real top = wmax<NL>(bd);
+    const mreal top = wmaxd<NL>(bd);
     const int cand = (bd == top) ? bi : nvert;
     const int best = -(int)wmax<NL>(-(real)cand);  // smallest index among the lanes holding the maximum
     loc[0] = hv[3 * best]; loc[1] = hv[3 * best + 1]; loc[2] = hv[3 * best + 2];
   }
   for (int k = 0; k < 3; ++k)
-    res[k] = o.pos[k] + R[3 * k] * loc[0] + R[3 * k + 1] * loc[1] + R[3 * k + 2] * loc[2] + dir[k] * o.margin;
+    res[k] = (mreal)o.pos[k] + R[3 * k] * loc[0] + R[3 * k + 1] * loc[1] + R[3 * k + 2] * loc[2] + dir[k] * (mreal)o.margin;
 }
 
 #if defined(MJ_DEBUG) && !defined(__CUDA_ARCH__)
 static long g_support_calls = 0, g_mpr_calls = 0, g_mpr_hits = 0;
 #endif
 template <int NL>
-MJ_FN void mpr_support(const CObj& o1, const CObj& o2, const real* dir, Supp* s, int lane) {
+MJ_FN void mpr_support(const CObj& o1, const CObj& o2, const mreal* dir, Supp* s, int lane) {
 #if defined(MJ_DEBUG) && !defined(__CUDA_ARCH__)
   ++g_support_calls;
 #endif
-  const real nd[3] = {-dir[0], -dir[1], -dir[2]};
+  const mreal nd[3] = {-dir[0], -dir[1], -dir[2]};
   support_geom<NL>(o1, dir, s->v1, lane);
   support_geom<NL>(o2, nd, s->v2, lane);
   sub3(s->v, s->v1, s->v2);
 }
-MJ_HD int is_zero(real x) { return fabsf(x) < CCD_EPS; }
-MJ_HD int ccd_eq(real a, real b) {
-  const real ab = fabsf(a - b);
+MJ_HD int is_zero(mreal x) { return fabs(x) < CCD_EPS; }
+MJ_HD int ccd_eq(mreal a, mreal b) {
+  const mreal ab = fabs(a - b);
   if (ab < CCD_EPS) return 1;
-  const real fa = fabsf(a), fb = fabsf(b);
+  const mreal fa = fabs(a), fb = fabs(b);
   return ab < CCD_EPS * (fb > fa ? fb : fa);
 }
-MJ_HD void portal_dir(const Supp* P, real* dir) {
-  real a[3], b[3];
+MJ_HD void portal_dir(const Supp* P, mreal* dir) {
+  mreal a[3], b[3];
   sub3(a, P[2].v, P[1].v);
   sub3(b, P[3].v, P[1].v);
   cross3(dir, a, b);
   normalize3(dir);
 }
-MJ_HD int reach_tolerance(const Supp* P, const Supp* v4, const real* dir) {
-  const real dv4 = dot3(v4->v, dir), d1 = dv4 - dot3(P[1].v, dir), d2 = dv4 - dot3(P[2].v, dir), d3 = dv4 - dot3(P[3].v, dir);
-  real d = d1 < d2 ? d1 : d2;
+MJ_HD int reach_tolerance(const Supp* P, const Supp* v4, const mreal* dir) {
+  const mreal dv4 = dot3(v4->v, dir), d1 = dv4 - dot3(P[1].v, dir), d2 = dv4 - dot3(P[2].v, dir), d3 = dv4 - dot3(P[3].v, dir);
+  mreal d = d1 < d2 ? d1 : d2;
   d = d < d3 ? d : d3;
   return ccd_eq(d, MPR_TOL) || d < MPR_TOL;
 }
 MJ_HD void expand_portal(Supp* P, const Supp* v4) {
-  real v4v0[3];
+  mreal v4v0[3];
   cross3(v4v0, v4->v, P[0].v);
   if (dot3(P[1].v, v4v0) > 0) {
     if (dot3(P[2].v, v4v0) > 0) P[1] = *v4; else P[3] = *v4;
@@ -308,34 +316,34 @@ MJ_HD void expand_portal(Supp* P, const Supp* v4) {
     if (dot3(P[3].v, v4v0) > 0) P[2] = *v4; else P[1] = *v4;
   }
 }
-MJ_FN real seg_dist2(const real* Pt, const real* x0, const real* b, real* wit) {
-  real d[3], a[3];
+MJ_FN mreal seg_dist2(const mreal* Pt, const mreal* x0, const mreal* b, mreal* wit) {
+  mreal d[3], a[3];
   sub3(d, b, x0);
   sub3(a, x0, Pt);
-  const real t = -dot3(a, d) / dot3(d, d);
+  const mreal t = -dot3(a, d) / dot3(d, d);
   if (t < 0 || is_zero(t)) { wit[0] = x0[0]; wit[1] = x0[1]; wit[2] = x0[2]; }
   else if (t > 1 || ccd_eq(t, 1)) { wit[0] = b[0]; wit[1] = b[1]; wit[2] = b[2]; }
   else for (int k = 0; k < 3; ++k) wit[k] = x0[k] + t * d[k];
-  real r[3];
+  mreal r[3];
   sub3(r, wit, Pt);
   return dot3(r, r);
 }
-MJ_FN real tri_dist2(const real* Pt, const real* x0, const real* B, const real* C, real* wit) {
-  real d1[3], d2[3], a[3];
+MJ_FN mreal tri_dist2(const mreal* Pt, const mreal* x0, const mreal* B, const mreal* C, mreal* wit) {
+  mreal d1[3], d2[3], a[3];
   sub3(d1, B, x0);
   sub3(d2, C, x0);
   sub3(a, x0, Pt);
-  const real v = dot3(d1, d1), ww = dot3(d2, d2), p = dot3(a, d1), q = dot3(a, d2), r = dot3(d1, d2);
-  const real s = (q * r - ww * p) / (ww * v - r * r), t = (-s * r - q) / ww;
+  const mreal v = dot3(d1, d1), ww = dot3(d2, d2), p = dot3(a, d1), q = dot3(a, d2), r = dot3(d1, d2);
+  const mreal s = (q * r - ww * p) / (ww * v - r * r), t = (-s * r - q) / ww;
   if ((is_zero(s) || s > 0) && (ccd_eq(s, 1) || s < 1) && (is_zero(t) || t > 0) && (ccd_eq(t, 1) || t < 1) &&
       (ccd_eq(t + s, 1) || t + s < 1)) {
     for (int k = 0; k < 3; ++k) wit[k] = x0[k] + s * d1[k] + t * d2[k];
-    real rr[3];
+    mreal rr[3];
     sub3(rr, wit, Pt);
     return dot3(rr, rr);
   }
-  real w2[3];
-  real dist = seg_dist2(Pt, x0, B, wit), d2v = seg_dist2(Pt, x0, C, w2);
+  mreal w2[3];
+  mreal dist = seg_dist2(Pt, x0, B, wit), d2v = seg_dist2(Pt, x0, C, w2);
   if (d2v < dist) { dist = d2v; wit[0] = w2[0]; wit[1] = w2[1]; wit[2] = w2[2]; }
   d2v = seg_dist2(Pt, B, C, w2);
   if (d2v < dist) { dist = d2v; wit[0] = w2[0]; wit[1] = w2[1]; wit[2] = w2[2]; }
@@ -344,14 +352,14 @@ MJ_FN real tri_dist2(const real* Pt, const real* x0, const real* B, const real* 
 
 // returns 1 with (depth, dir, pos) when the (inflated) geoms penetrate; all lanes take the same path
 template <int NL>
-MJ_FN int mpr_penetration(const CObj& o1, const CObj& o2, real* depth, real* dir, real* pos, NarrowScratch* S, int lane) {
+MJ_FN int mpr_penetration(const CObj& o1, const CObj& o2, real* depth_out, real* dir_out, real* pos_out, NarrowScratch* S, int lane) {
   Supp* P = S->P;
   Supp& v4 = S->v4;
-  const real origin[3] = {0, 0, 0};
+  const mreal origin[3] = {0, 0, 0};
   for (int k = 0; k < 3; ++k) { P[0].v1[k] = o1.pos[k]; P[0].v2[k] = o2.pos[k]; }
   sub3(P[0].v, P[0].v1, P[0].v2);
-  if (is_zero(P[0].v[0]) && is_zero(P[0].v[1]) && is_zero(P[0].v[2])) P[0].v[0] = 0.00001f;
-  real d[3] = {-P[0].v[0], -P[0].v[1], -P[0].v[2]}, va[3], vb[3], dt;
+  if (is_zero(P[0].v[0]) && is_zero(P[0].v[1]) && is_zero(P[0].v[2])) P[0].v[0] = 0.00001;
+  mreal d[3] = {-P[0].v[0], -P[0].v[1], -P[0].v[2]}, va[3], vb[3], dt, depth, dir[3], pos[3];
   normalize3(d);
   mpr_support<NL>(o1, o2, d, &P[1], lane);
   dt = dot3(P[1].v, d);
@@ -359,10 +367,11 @@ MJ_FN int mpr_penetration(const CObj& o1, const CObj& o2, real* depth, real* dir
   cross3(d, P[0].v, P[1].v);
   if (is_zero(dot3(d, d))) {
     if (is_zero(P[1].v[0]) && is_zero(P[1].v[1]) && is_zero(P[1].v[2])) return 0;
-    *depth = sqrtf(dot3(P[1].v, P[1].v));
+    depth = sqrt(dot3(P[1].v, P[1].v));
     dir[0] = P[1].v[0]; dir[1] = P[1].v[1]; dir[2] = P[1].v[2];
     normalize3(dir);
-    for (int k = 0; k < 3; ++k) pos[k] = 0.5f * (P[1].v1[k] + P[1].v2[k]);
+    for (int k = 0; k < 3; ++k) { pos_out[k] = (real)(0.5 * (P[1].v1[k] + P[1].v2[k])); dir_out[k] = (real)dir[k]; }
+    *depth_out = (real)depth;
     return 1;
   }
   normalize3(d);
@@ -409,18 +418,18 @@ MJ_FN int mpr_penetration(const CObj& o1, const CObj& o2, real* depth, real* dir
     portal_dir(P, d);
     mpr_support<NL>(o1, o2, d, &v4, lane);
     if (reach_tolerance(P, &v4, d) || it > MPR_ITER) {
-      real wit[3];
-      *depth = sqrtf(tri_dist2(origin, P[1].v, P[2].v, P[3].v, wit));
-      if (is_zero(*depth)) return 0;
+      mreal wit[3];
+      depth = sqrt(tri_dist2(origin, P[1].v, P[2].v, P[3].v, wit));
+      if (is_zero(depth)) return 0;
       dir[0] = wit[0]; dir[1] = wit[1]; dir[2] = wit[2];
       normalize3(dir);
-      real b[4], t[3];
+      mreal b[4], t[3];
       portal_dir(P, d);
       cross3(t, P[1].v, P[2].v); b[0] = dot3(t, P[3].v);
       cross3(t, P[3].v, P[2].v); b[1] = dot3(t, P[0].v);
       cross3(t, P[0].v, P[1].v); b[2] = dot3(t, P[3].v);
       cross3(t, P[2].v, P[1].v); b[3] = dot3(t, P[0].v);
-      real sum = b[0] + b[1] + b[2] + b[3];
+      mreal sum = b[0] + b[1] + b[2] + b[3];
       if (is_zero(sum) || sum < 0) {
         b[0] = 0;
         cross3(t, P[2].v, P[3].v); b[1] = dot3(t, d);
@@ -428,12 +437,14 @@ MJ_FN int mpr_penetration(const CObj& o1, const CObj& o2, real* depth, real* dir
         cross3(t, P[1].v, P[2].v); b[3] = dot3(t, d);
         sum = b[1] + b[2] + b[3];
       }
-      const real inv = 1.0f / sum;
+      const mreal inv = 1.0 / sum;
       for (int k = 0; k < 3; ++k) {
-        real q1 = 0, q2 = 0;
+        mreal q1 = 0, q2 = 0;
         for (int v = 0; v < 4; ++v) { q1 += b[v] * P[v].v1[k]; q2 += b[v] * P[v].v2[k]; }
-        pos[k] = 0.5f * (q1 + q2) * inv;
+        pos[k] = 0.5 * (q1 + q2) * inv;
       }
+      for (int k = 0; k < 3; ++k) { pos_out[k] = (real)pos[k]; dir_out[k] = (real)dir[k]; }
+      *depth_out = (real)depth;
       return 1;
     }
     expand_portal(P, &v4);
@@ -464,7 +475,10 @@ MJ_FN int plane_convex(const Model& m, const real* hull, Work& w, int gp, int g,
   }
   CObj& o = reinterpret_cast<NarrowScratch*>(&w.H[0][0])->o1;
   make_cobj(o, m, hull, w, g, 0.0f);
-  support_geom<NL>(o, nd, pt, lane);
+  const mreal ndd[3] = {nd[0], nd[1], nd[2]};
+  mreal ptd[3];
+  support_geom<NL>(o, ndd, ptd, lane);
+  for (int k = 0; k < 3; ++k) pt[k] = (real)ptd[k];
   sub3(rel, pt, gpos(m, w, gp));
   const real dist = dot3(rel, n);
   if (dist >= margin) return 0;

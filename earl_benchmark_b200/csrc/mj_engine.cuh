@@ -198,6 +198,16 @@ MJ_HD real wsum(real x) {
   return x;
 }
 template <int NL>
+MJ_HD double wmaxd(double x) {
+#if defined(__CUDA_ARCH__)
+  if (NL > 1) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x = fmax(x, __shfl_xor_sync(0xffffffffu, x, o));
+  }
+#endif
+  return x;
+}
+template <int NL>
 MJ_HD real wmax(real x) {
 #if defined(__CUDA_ARCH__)
   if (NL > 1) {
@@ -209,11 +219,17 @@ MJ_HD real wmax(real x) {
 }
 
 // ------------------------------------------------------------------------------------------------ small math
-MJ_HD void cross3(real* r, const real* a, const real* b) {
-  real x = a[1] * b[2] - a[2] * b[1], y = a[2] * b[0] - a[0] * b[2], z = a[0] * b[1] - a[1] * b[0];
+template <class T>
+MJ_HD void cross3(T* r, const T* a, const T* b) {
+  T x = a[1] * b[2] - a[2] * b[1], y = a[2] * b[0] - a[0] * b[2], z = a[0] * b[1] - a[1] * b[0];
   r[0] = x; r[1] = y; r[2] = z;
 }
-MJ_HD real dot3(const real* a, const real* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+template <class T>
+MJ_HD T dot3(const T* a, const T* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+MJ_HD float msqrt(float x) { return sqrtf(x); }
+MJ_HD double msqrt(double x) { return sqrt(x); }
+MJ_HD float mabs(float x) { return fabsf(x); }
+MJ_HD double mabs(double x) { return fabs(x); }
 MJ_HD void mulmatvec3(real* r, const real* m, const real* v) {
   real x = m[0] * v[0] + m[1] * v[1] + m[2] * v[2], y = m[3] * v[0] + m[4] * v[1] + m[5] * v[2],
        z = m[6] * v[0] + m[7] * v[1] + m[8] * v[2];

@@ -442,9 +442,19 @@ static double point_box_dist2(const double *c, const double *p, const double *R,
 }
 
 /* ------------------------------------------------------------------------------------------ driver */
+/* sensitivity probe (tests only): round the geom poses to fp32 before collision, i.e. give the fp64 narrow phase the
+ * inputs the fp32 engine has */
+static int g_round_poses = 0;
+void mje_debug_round_poses(int on) { g_round_poses = on; }
+
 void mje_collision(const mjModelF *m, mjDataF *d) {
   d->ncon = 0;
   g_flops = 0;
+  if (g_round_poses)
+    for (int g = 0; g < m->ngeom; ++g) {
+      for (int k = 0; k < 3; ++k) d->geom_xpos[g][k] = (double)(float)d->geom_xpos[g][k];
+      for (int k = 0; k < 9; ++k) d->geom_xmat[g][k] = (double)(float)d->geom_xmat[g][k];
+    }
   for (int g1 = 0; g1 < m->ngeom; ++g1)
     for (int g2 = g1 + 1; g2 < m->ngeom; ++g2) {
       if (!((m->geom_contype[g1] & m->geom_conaffinity[g2]) || (m->geom_contype[g2] & m->geom_conaffinity[g1]))) continue;

@@ -49,8 +49,8 @@ def test_one_step_parity_from_identical_states(oracle):
     obs = obs.cpu().numpy()
     e = oracle.e
     # "light": only the four door-on-table box-box contacts (always present); "convex": the gripper also touches the
-    # handle, i.e. contacts from portal refinement, whose result is not a continuous function of the state (fp32 and
-    # fp64 can follow different, equally valid, portals when a 6 mm thin pad is 4-7 mm deep in a cylinder)
+    # handle, i.e. contacts from portal refinement (run in fp64 inside the kernel: in fp32 its termination tests stop
+    # at other portals and these states used to differ by up to 3.6e-3 in qpos)
     worst = {k: dict(q=0.0, v=0.0, obs=0.0, n=0) for k in ("light", "convex")}
     for i, (q, v, w, mp) in enumerate(states):
         e.reset()
@@ -71,7 +71,7 @@ def test_one_step_parity_from_identical_states(oracle):
     print("one-step parity:", worst)
     assert worst["light"]["n"] >= 40 and worst["convex"]["n"] >= 10
     assert worst["light"]["q"] < TOL and worst["light"]["v"] < TOL and worst["light"]["obs"] < 1e-5, worst
-    assert worst["convex"]["q"] < 1e-2 and worst["convex"]["obs"] < 5e-3, worst
+    assert worst["convex"]["q"] < TOL and worst["convex"]["v"] < 1e-3 and worst["convex"]["obs"] < 1e-4, worst
     assert env.work_counters()["bad_states"] == 0
 
 
