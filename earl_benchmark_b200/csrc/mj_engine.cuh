@@ -563,6 +563,7 @@ __device__ __noinline__ int spd_solve_reg(real (*A)[LDM], int n, real* x, int la
   const int i = lane;
   const bool row = i < n;
   int ok = 1;
+  real invd = 1.0f;  // 1 / L[i][i] of this lane's row
   for (int j = 0; j < n; ++j) {
     real s = 0.0f;
     if (row && i >= j) {
@@ -572,17 +573,18 @@ __device__ __noinline__ int spd_solve_reg(real (*A)[LDM], int n, real* x, int la
     const real piv = __shfl_sync(FULL, s, j);
     if (!(piv > MINVAL)) ok = 0;
     const real inv = rsqrtf(fmaxf(piv, MINVAL));
+    if (i == j) invd = inv;
     if (row && i >= j) A[i][j] = (i == j) ? piv * inv : s * inv;
     __syncwarp();
   }
   real xi = row ? x[i] : 0.0f;
   for (int j = 0; j < n; ++j) {
-    if (i == j) xi = xi / A[j][j];
+    if (i == j) xi *= invd;
     const real xj = __shfl_sync(FULL, xi, j);
     if (row && i > j) xi -= A[i][j] * xj;
   }
   for (int j = n - 1; j >= 0; --j) {
-    if (i == j) xi = xi / A[j][j];
+    if (i == j) xi *= invd;
     const real xj = __shfl_sync(FULL, xi, j);
     if (i < j) xi -= A[j][i] * xj;
   }
