@@ -248,3 +248,29 @@ def test_dense_reward_matches_checker(oracle):
     assert np.abs(env.compute_reward(obs).cpu().numpy() - ref).max() < 2e-4
     assert np.abs(env.compute_reward(o) - ref).max() < 1e-9
     assert np.array_equal(info["success"].cpu().numpy(), np.linalg.norm(o[:, 4:7] - o[:, 11:14], axis=1) <= 0.02)
+
+
+def test_results_do_not_depend_on_batch_composition_or_scheduling():
+    """Environments are independent: the state of env i after 25 random-action steps must be BIT-identical whether it is
+    stepped inside a batch of 3,000 (many chunks, cost-sorted dynamic scheduling, reordered every step) or in a batch
+    of 37 that contains it, and identical between two runs of the same batch."""
+    n_big, pick = 3000, np.arange(0, 3000, 83)[:37]
+    rs = np.random.RandomState(8)
+    angles = -np.pi / 3 + rs.uniform(0, np.pi / 20, n_big)
+    actions = rs.uniform(-1, 1, (25, n_big, 4)).astype(np.float32)
+
+    def run(idx):
+        env = sawyer_door.SawyerDoorV2(num_envs=len(idx), device="cuda:0")
+        env.reset(door_angle=angles[idx])
+        for t in range(25):
+            obs, _, _, _ = env.step(torch.from_numpy(np.ascontiguousarray(actions[t, idx])).cuda())
+        st = env.get_state()
+        return st["qpos"], st["qvel"], obs.cpu().numpy(), env.work_counters()
+
+    all_idx = np.arange(n_big)
+    q1, v1, o1, w1 = run(all_idx)
+    q2, v2, o2, w2 = run(all_idx)
+    assert np.array_equal(q1, q2) and np.array_equal(v1, v2) and np.array_equal(o1, o2) and w1 == w2
+    qs, vs, os_, _ = run(pick)
+    assert np.array_equal(q1[pick], qs) and np.array_equal(v1[pick], vs) and np.array_equal(o1[pick], os_)
+    assert w1["contacts"] > 4 * 5 * 25 * n_big      # some grippers reached the handle: expensive envs were present
