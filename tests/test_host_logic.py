@@ -128,3 +128,30 @@ def test_demo_utilities():
     peg = demos.load("sawyer_peg", "forward")
     p = demos.peg_position_from_obs(peg["observations"][0])
     assert 0.0 <= p[0] <= 0.2 and 0.5 <= p[1] <= 0.7 and abs(p[2] - 0.02) < 1e-6                # obj_low / obj_high
+
+
+def test_sawyer_reset_draws_do_not_depend_on_the_number_of_shards():
+    """A job of 10 envs sharded over 1, 2 or 3 GPUs draws the same door angles / peg positions for the same global env
+    (every shard consumes the global np.random stream and keeps its slice)."""
+    from earl_benchmark_b200.envs import sawyer_door as sd, sawyer_peg as sp
+    total = 10
+    whole = sd.SawyerDoorV2(num_envs=total, seed=5)._draw_angles(None)
+    assert np.array_equal(whole, -np.pi / 3 + np.random.RandomState(5).uniform(0, np.pi / 20, total))
+    for world in (2, 3):
+        parts = []
+        for r in range(world):
+            lo, hi = shard_range(total, r, world)
+            parts.append(sd.SawyerDoorV2(num_envs=hi - lo, seed=5, env_offset=lo, total_envs=total)._draw_angles(None))
+        assert np.array_equal(np.concatenate(parts), whole)
+
+    def peg_draws(n, off):
+        env = sp.SawyerPegV2(reward_type="sparse", num_envs=n, seed=5, env_offset=off, total_envs=total)
+        out = []
+        for g in range(total):            # the loop of SawyerPegV2.reset(mask=None)
+            row, p = env._draw_one()
+            if off <= g < off + n:
+                out.append(p)
+        return np.array(out)
+    whole_p = peg_draws(total, 0)
+    lo, hi = shard_range(total, 1, 2)
+    assert np.array_equal(peg_draws(hi - lo, lo), whole_p[lo:hi])
