@@ -148,7 +148,7 @@ __global__ void __launch_bounds__(kWPB * 32, 1) mj_step_kernel(const StepArgs a)
   load_model(sm, a.model);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   Work& w = *reinterpret_cast<Work*>(smem + kModelBytes + warp * kWorkStride);
-  unsigned long long it = 0, rows = 0, cons = 0, bad = 0, over = 0, envs = 0;
+  unsigned long long it = 0, rows = 0, cons = 0, bad = 0, over = 0, envs = 0, ov_hit = 0, ov_con = 0, ov_row = 0;
   // Every warp of a block makes the same trips (the substep has block-wide phase barriers); a warp without an
   // environment in the last chunk re-runs another environment and discards the result.  Chunks of kWPB consecutive
   // entries of the cost-sorted order are handed out dynamically, so blocks that draw expensive chunks (gripper on
@@ -188,12 +188,13 @@ __global__ void __launch_bounds__(kWPB * 32, 1) mj_step_kernel(const StepArgs a)
       // PersistentStateWrapper.step: counters, horizon `done` (persistent_state_wrapper.py:22-31)
       const unsigned steps = w.steps == 0xffffffffu ? w.steps : w.steps + 1;
       w.steps = steps;
-      w.flags = (w.flags & ~2u) | (ok ? 3u : 0u) | ((w.bad & 1) ? 4u : 0u) | ((w.bad & 2) ? 8u : 0u);
+      w.flags = (w.flags & ~2u) | (ok ? 3u : 0u) | ((w.bad & 1) ? 4u : 0u) | ((w.bad & 14) ? 8u : 0u);
       a.reward[env] = r;
       a.done[env] = steps >= a.horizon ? 1 : 0;
       if (a.success) a.success[env] = ok ? 1 : 0;
       if (a.ep_return) a.ep_return[env] += (double)r;
-      it += w.acc_iter; rows += w.acc_rows; cons += w.acc_con; bad += (w.bad & 1) ? 1 : 0; over += (w.bad & 2) ? 1 : 0; envs += 1;
+      it += w.acc_iter; rows += w.acc_rows; cons += w.acc_con; bad += (w.bad & 1) ? 1 : 0; over += (w.bad & 14) ? 1 : 0; envs += 1;
+      ov_hit += (w.bad & 2) ? 1 : 0; ov_con += (w.bad & 4) ? 1 : 0; ov_row += (w.bad & 8) ? 1 : 0;
       // next step's visiting order: expensive environments first and together
       const bool heavy = w.acc_mpr > 0 || w.acc_iter > 2 * sm->frame_skip;
       const unsigned slot = heavy ? atomicAdd(&a.sched[1], 1u) : (unsigned)a.n - 1u - atomicAdd(&a.sched[2], 1u);
@@ -213,6 +214,9 @@ __global__ void __launch_bounds__(kWPB * 32, 1) mj_step_kernel(const StepArgs a)
     atomicAdd(&a.work[4], cons);
     atomicAdd(&a.work[5], bad);
     atomicAdd(&a.work[6], over);
+    atomicAdd(&a.work[7], ov_hit);
+    atomicAdd(&a.work[16], ov_con);
+    atomicAdd(&a.work[17], ov_row);
   }
 }
 
@@ -402,7 +406,7 @@ int earl_mj_create(const earl_mj_config* cfg, const void* model_blob, size_t mod
   if (!rc) rc = h->alloc(&a.interventions, n);
   if (!rc && (cfg->flags & EARL_FLAG_EVAL_STATS)) rc = h->alloc(&a.ep_return, n);
   if (!rc && (cfg->flags & EARL_FLAG_LIFELONG)) { rc = h->alloc(&a.ll_return, n); if (!rc) rc = h->alloc(&a.ll_steps, n); }
-  if (!rc) rc = h->alloc(&a.work, 16);
+  if (!rc) rc = h->alloc(&a.work, 20);
   if (!rc) rc = h->alloc(&h->d_tmpl, REC_FLOATS);
   if (!rc) rc = h->alloc(&h->d_order[0], n);
   if (!rc) rc = h->alloc(&h->d_order[1], n);
@@ -629,6 +633,12 @@ int earl_mj_work_counters(earl_mj_handle* h, uint64_t* out7_host) {
   if (!out7_host) return failf(EARL_ERR_INVALID, "null out");
   CU(cudaDeviceSynchronize());
   CU(cudaMemcpy(out7_host, h->a.work, 7 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+  if (getenv("EARL_MJ_OVERFLOW_DETAIL")) {
+    uint64_t d[20];
+    CU(cudaMemcpy(d, h->a.work, sizeof(d), cudaMemcpyDeviceToHost));
+    fprintf(stderr, "[mj overflow] env-steps with dropped candidate pairs %llu, dropped contacts %llu, dropped rows %llu\n",
+            (unsigned long long)d[7], (unsigned long long)d[16], (unsigned long long)d[17]);
+  }
 #ifdef MJ_PHASE_TIMING
   uint64_t ph[8];
   CU(cudaMemcpy(ph, h->a.work + 8, sizeof(ph), cudaMemcpyDeviceToHost));

@@ -639,7 +639,7 @@ MJ_FN void collide(const Model& m, const real* hull, Work& w, int lane) {
     int added = 0;
     for (int c = 0; c < n; ++c) {
       if (rc[c].dist >= margin) continue;
-      if (base + added >= MAXCON) { if (lane == 0) w.bad |= 2; continue; }
+      if (base + added >= MAXCON) { if (lane == 0) w.bad |= 4; continue; }
       const int k = base + added;
       ++added;
       if (lane == 0) {
@@ -666,7 +666,7 @@ MJ_FN void contact_rows(const Model& m, Work& w, int lane) {
   for (int c = 0; c < w.ncon; ++c) {
     const int g1 = w.con_g1[c], g2 = w.con_g2[c];
     const int dim = m.geom_condim[g1] > m.geom_condim[g2] ? m.geom_condim[g1] : m.geom_condim[g2];
-    if (row + dim > MAXEFC) { if (lane == 0) w.bad |= 2; break; }
+    if (row + dim > MAXEFC) { if (lane == 0) w.bad |= 8; break; }
     if (lane == 0) { w.con_row[c] = row; w.con_dim[c] = dim; }
     row += dim;
     ++used;

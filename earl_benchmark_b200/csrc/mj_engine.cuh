@@ -157,7 +157,7 @@ struct Work {
   unsigned steps, flags, goalrow;
   // diagnostics
   int solver_iter;
-  int bad;  // bit 0: numerical failure (non-positive pivot), bit 1: a fixed capacity (pairs / contacts / rows) overflowed
+  int bad;  // bit 0: numerical failure (non-positive pivot); capacity overflows: bit 1 candidate pairs, bit 2 contacts, bit 3 rows
   int acc_iter, acc_rows, acc_con, acc_mpr;  // summed over the substeps of one env step
 #ifdef MJ_PHASE_TIMING
   long long phase[8], phase_t0;     // SM cycles per engine phase (profiling builds only)
@@ -709,7 +709,7 @@ MJ_FN void make_constraints(const Model& m, Work& w, int lane) {
     const int qa = m.jnt_qposadr[j], da = m.jnt_dofadr[j];
     for (int side = 0; side < 2; ++side) {
       const real dist = side == 0 ? w.qpos[qa] - m.jnt_range[j][0] : m.jnt_range[j][1] - w.qpos[qa];
-      if (dist < m.jnt_margin[j] && r >= MAXEFC && lane == 0) w.bad |= 2;
+      if (dist < m.jnt_margin[j] && r >= MAXEFC && lane == 0) w.bad |= 8;
       if (dist < m.jnt_margin[j] && r < MAXEFC) {
         for (int c = lane; c < nv; c += NL) w.J[r][c] = (c == da) ? (side == 0 ? 1.0f : -1.0f) : 0.0f;
         if (lane == 0) { w.e_pos[r] = dist; w.e_type[r] = ROW_LIMIT; }
