@@ -42,6 +42,7 @@ using namespace earl::mj;
 
 constexpr int kWPB = 16;  // warps (= environments in flight) per block: 16 x 13.2 KB workspaces + the model fill one SM
 constexpr int kObs = 14, kAct = 4, kGoal = 7, kMaxGoals = 32;
+constexpr int kBuckets = 32;
 constexpr size_t kModelBytes = (sizeof(Model) + 15) & ~size_t(15);
 constexpr size_t kSmemBytes = kModelBytes + kWPB * ((sizeof(Work) + 15) & ~size_t(15));
 constexpr size_t kWorkStride = (sizeof(Work) + 15) & ~size_t(15);
@@ -58,10 +59,14 @@ struct StepArgs {
   unsigned goal_freq;
   unsigned long long* work;  // 6 counters
   // cost-sorted scheduling: environments are visited in the order of `order_cur` in chunks of kWPB grabbed from an
-  // atomic counter; every env appends itself to the front (expensive last step) or the back (cheap) of `order_next`
+  // atomic counter; every env files itself under one of kBuckets cost buckets (estimated from the work it just did)
+  // and a tiny second kernel turns (bucket, rank) into next step's order, most expensive first
   const int* order_cur;
   int* order_next;
-  unsigned* sched;           // {next chunk, #expensive, #cheap}
+  unsigned* sched;           // [0] next chunk, [1 .. kBuckets] bucket counters
+  unsigned char* env_bucket; // [N]
+  unsigned* env_rank;        // [N]
+  int bucket_width;          // estimated warp instructions per cost bucket
   int n;
   unsigned horizon;
   unsigned flags;
@@ -112,7 +117,7 @@ __device__ __forceinline__ float gather_rec(const Work& w, int idx) {
 __device__ __forceinline__ void load_env(Work& w, const float* rec, int lane) {
   scatter_rec(w, lane, rec[lane]);
   scatter_rec(w, lane + 32, rec[lane + 32]);
-  if (lane == 0) { w.bad = 0; w.acc_iter = w.acc_rows = w.acc_con = w.acc_mpr = 0; }
+  if (lane == 0) { w.bad = 0; w.acc_iter = w.acc_rows = w.acc_con = w.acc_mpr = w.acc_sup = 0; }
 #ifdef MJ_PHASE_TIMING
   if (lane < 8) w.phase[lane] = 0;
 #endif
@@ -195,10 +200,13 @@ __global__ void __launch_bounds__(kWPB * 32, 1) mj_step_kernel(const StepArgs a)
       if (a.ep_return) a.ep_return[env] += (double)r;
       it += w.acc_iter; rows += w.acc_rows; cons += w.acc_con; bad += (w.bad & 1) ? 1 : 0; over += (w.bad & 14) ? 1 : 0; envs += 1;
       ov_hit += (w.bad & 2) ? 1 : 0; ov_con += (w.bad & 4) ? 1 : 0; ov_row += (w.bad & 8) ? 1 : 0;
-      // next step's visiting order: expensive environments first and together
-      const bool heavy = w.acc_mpr > 0 || w.acc_iter > 2 * sm->frame_skip;
-      const unsigned slot = heavy ? atomicAdd(&a.sched[1], 1u) : (unsigned)a.n - 1u - atomicAdd(&a.sched[2], 1u);
-      a.order_next[slot] = env;
+      // next step's visiting order: estimated warp instructions of this env step above the contact-free baseline
+      // (one extra Newton iteration ~2.5k, a contact ~0.3k, a support-function call ~0.3k), in 32 buckets of 3k
+      const int est = 2500 * (w.acc_iter - sm->frame_skip) + 300 * (w.acc_con - 4 * sm->frame_skip) + 300 * w.acc_sup;
+      int b = est <= 0 ? 0 : 1 + est / a.bucket_width;
+      b = b > kBuckets - 1 ? kBuckets - 1 : b;
+      a.env_bucket[env] = (unsigned char)b;
+      a.env_rank[env] = atomicAdd(&a.sched[1 + b], 1u);
 #ifdef MJ_PHASE_TIMING
       for (int k = 0; k < 8; ++k) atomicAdd(&a.work[8 + k], (unsigned long long)w.phase[k]);
 #endif
@@ -276,6 +284,18 @@ __global__ void __launch_bounds__(32) mj_settle_kernel(const StepArgs a, float* 
   store_env(w, tmpl_out, lane);
 }
 
+// (bucket, rank within bucket) -> position in next step's visiting order, most expensive bucket first
+__global__ void mj_order_kernel(const StepArgs a) {
+  __shared__ unsigned base[kBuckets];
+  if (threadIdx.x == 0) {
+    unsigned acc = 0;
+    for (int b = kBuckets - 1; b >= 0; --b) { base[b] = acc; acc += a.sched[1 + b]; }
+  }
+  __syncthreads();
+  for (int env = blockIdx.x * blockDim.x + threadIdx.x; env < a.n; env += gridDim.x * blockDim.x)
+    a.order_next[base[a.env_bucket[env]] + a.env_rank[env]] = env;
+}
+
 __global__ void mj_eval_stats_kernel(const float* state, const double* ep_return, int n, double* out4) {
   double ret = 0, last = 0, any = 0;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -312,7 +332,10 @@ struct earl_mj_handle {
   float* d_goals = nullptr;
   int* d_order[2] = {nullptr, nullptr};
   unsigned* d_sched = nullptr;
+  unsigned char* d_env_bucket = nullptr;
+  unsigned* d_env_rank = nullptr;
   int order_sel = 0;
+  int bucket_width = 3000;
   // host-path staging
   float* d_act = nullptr;
   float* d_obs = nullptr;
@@ -410,7 +433,9 @@ int earl_mj_create(const earl_mj_config* cfg, const void* model_blob, size_t mod
   if (!rc) rc = h->alloc(&h->d_tmpl, REC_FLOATS);
   if (!rc) rc = h->alloc(&h->d_order[0], n);
   if (!rc) rc = h->alloc(&h->d_order[1], n);
-  if (!rc) rc = h->alloc(&h->d_sched, 4);
+  if (!rc) rc = h->alloc(&h->d_sched, 2 + kBuckets);
+  if (!rc) rc = h->alloc(&h->d_env_bucket, n);
+  if (!rc) rc = h->alloc(&h->d_env_rank, n);
   if (rc) { earl_mj_destroy(h); return rc; }
   {
     std::vector<int> ident(n);
@@ -430,6 +455,7 @@ int earl_mj_create(const earl_mj_config* cfg, const void* model_blob, size_t mod
   if (e != cudaSuccess) { earl_mj_destroy(h); return failf(EARL_ERR_CUDA, "engine setup: %s", cudaGetErrorString(e)); }
   if (per_sm < 1) { earl_mj_destroy(h); return failf(EARL_ERR_CUDA, "step kernel does not fit on an SM (%zu B shared memory)", kSmemBytes); }
   h->grid = h->sm_count * per_sm;
+  if (const char* v = getenv("EARL_MJ_BUCKET_WIDTH")) { const int bw = atoi(v); if (bw >= 100) h->bucket_width = bw; }
   a.model = d_model;
   a.hull = d_hull;
   a.goals = h->d_goals;
@@ -527,11 +553,18 @@ int earl_mj_step(earl_mj_handle* h, const float* actions_dev, float* obs_dev, fl
   a.order_cur = h->d_order[h->order_sel];
   a.order_next = h->d_order[h->order_sel ^ 1];
   a.sched = h->d_sched;
+  a.env_bucket = h->d_env_bucket;
+  a.env_rank = h->d_env_rank;
+  a.bucket_width = h->bucket_width;
   h->order_sel ^= 1;
-  CU(cudaMemsetAsync(h->d_sched, 0, 4 * sizeof(unsigned), static_cast<cudaStream_t>(stream)));
-  mj_step_kernel<<<grid_for(h, a.n), kWPB * 32, kSmemBytes, static_cast<cudaStream_t>(stream)>>>(a);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  CU(cudaMemsetAsync(h->d_sched, 0, (2 + kBuckets) * sizeof(unsigned), s));
+  mj_step_kernel<<<grid_for(h, a.n), kWPB * 32, kSmemBytes, s>>>(a);
   CU(cudaGetLastError());
-  h->launches += 1;
+  int og = (a.n + 255) / 256;
+  mj_order_kernel<<<og < 4 * h->sm_count ? og : 4 * h->sm_count, 256, 0, s>>>(a);
+  CU(cudaGetLastError());
+  h->launches += 2;
   h->total_steps += 1;
   return 0;
 }

@@ -45,6 +45,7 @@ struct CObj {
 };
 struct NarrowScratch {
   CObj o1, o2;
+  int nsup;  // support-function calls of the current portal refinement (scheduling cost estimate)
   RawCon rc[8];
   union {
     struct { real A[3][3], B[3][3], poly[16][3], tmp[16][3]; };  // box-box
@@ -355,6 +356,7 @@ template <int NL>
 MJ_FN int mpr_penetration(const CObj& o1, const CObj& o2, real* depth_out, real* dir_out, real* pos_out, NarrowScratch* S, int lane) {
   Supp* P = S->P;
   Supp& v4 = S->v4;
+  if (lane == 0) S->nsup = 0;
   const mreal origin[3] = {0, 0, 0};
   for (int k = 0; k < 3; ++k) { P[0].v1[k] = o1.pos[k]; P[0].v2[k] = o2.pos[k]; }
   sub3(P[0].v, P[0].v1, P[0].v2);
@@ -362,6 +364,7 @@ MJ_FN int mpr_penetration(const CObj& o1, const CObj& o2, real* depth_out, real*
   mreal d[3] = {-P[0].v[0], -P[0].v[1], -P[0].v[2]}, va[3], vb[3], dt, depth, dir[3], pos[3];
   normalize3(d);
   mpr_support<NL>(o1, o2, d, &P[1], lane);
+  if (lane == 0) S->nsup += 1;
   dt = dot3(P[1].v, d);
   if (is_zero(dt) || dt < 0) return 0;
   cross3(d, P[0].v, P[1].v);
@@ -376,6 +379,7 @@ MJ_FN int mpr_penetration(const CObj& o1, const CObj& o2, real* depth_out, real*
   }
   normalize3(d);
   mpr_support<NL>(o1, o2, d, &P[2], lane);
+  if (lane == 0) S->nsup += 1;
   dt = dot3(P[2].v, d);
   if (is_zero(dt) || dt < 0) return 0;
   sub3(va, P[1].v, P[0].v);
@@ -388,6 +392,7 @@ MJ_FN int mpr_penetration(const CObj& o1, const CObj& o2, real* depth_out, real*
   }
   for (int guard = 0; guard < 100; ++guard) {
     mpr_support<NL>(o1, o2, d, &P[3], lane);
+    if (lane == 0) S->nsup += 1;
     dt = dot3(P[3].v, d);
     if (is_zero(dt) || dt < 0) return 0;
     int cont = 0;
@@ -410,6 +415,7 @@ MJ_FN int mpr_penetration(const CObj& o1, const CObj& o2, real* depth_out, real*
     dt = dot3(d, P[1].v);
     if (is_zero(dt) || dt > 0) break;
     mpr_support<NL>(o1, o2, d, &v4, lane);
+    if (lane == 0) S->nsup += 1;
     dt = dot3(v4.v, d);
     if (!(is_zero(dt) || dt > 0) || reach_tolerance(P, &v4, d) || guard > 200) return 0;
     expand_portal(P, &v4);
@@ -417,6 +423,7 @@ MJ_FN int mpr_penetration(const CObj& o1, const CObj& o2, real* depth_out, real*
   for (int it = 0;; ++it) {  // findPenetr
     portal_dir(P, d);
     mpr_support<NL>(o1, o2, d, &v4, lane);
+    if (lane == 0) S->nsup += 1;
     if (reach_tolerance(P, &v4, d) || it > MPR_ITER) {
       mreal wit[3];
       depth = sqrt(tri_dist2(origin, P[1].v, P[2].v, P[3].v, wit));
@@ -625,6 +632,7 @@ MJ_FN void collide(const Model& m, const real* hull, Work& w, int lane) {
       const long before = g_support_calls;
 #endif
       const int pen = mpr_penetration<NL>(o1, o2, &depth, dir, pos, S, lane);
+      if (lane == 0) w.acc_sup += S->nsup;
 #if defined(MJ_DEBUG) && !defined(__CUDA_ARCH__)
       g_mpr_hits += pen;
       if (g_support_calls - before > 12) printf("  mpr pair (%d,%d) types %d %d: %ld supports, pen %d depth %g\n", ga, gb, t1, t2, g_support_calls - before, pen, pen ? (double)depth : 0.0);
