@@ -231,9 +231,9 @@ def run_door(dev, rank, world, sm_max_mhz, sm_count, with_cpu):
                         "contacts_per_substep": (w1["contacts"] - w0["contacts"]) / sub,
                         "bad_states": w1["bad_states"] - w0["bad_states"],
                         "overflow_states": w1["overflow_states"] - w0["overflow_states"]},
-               "kernel": "mj_step_kernel (one warp per env, 16 envs per SM in flight)",
+               "kernel": "mj_step_kernel (one warp per env, 16 envs per SM in flight) + mj_order_kernel (visiting order, <3 us)",
                "ncu": {"source": "profiles/r01/door/prof_door_step_16k_r01.details.csv (16,384 envs, not this run)",
-                       "executed_ipc": 2.11, "issue_slots_busy_pct": 52.7, "achieved_occupancy_pct": 25.0,
+                       "executed_ipc": 2.17, "issue_slots_busy_pct": 54.3, "achieved_occupancy_pct": 24.9,
                        "warp_instructions_per_env_step": 1.03e5, "dram_pct_of_peak": 0.03}}
         if with_cpu:
             procs = os.cpu_count() or 1
