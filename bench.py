@@ -19,6 +19,7 @@ One JSON line on stdout (rank 0):
   sawyer_door  second section (BASELINE.json configs[2]): batched Sawyer door step, 65,536 envs per GPU, random
                actions; env-steps/s, e2e with host buffers, FP32-issue roofline from the checker's flop count, CPU
                baseline (fp64 C restatement of the engine, one process per host core)
+  sawyer_peg   third section (BASELINE.json configs[3]): the same for the Sawyer peg task (free-joint peg, nv = 15)
 `--impl reference` times that CPU port alone on the same config (the reference itself is Python over
 mujoco-py and cannot run on the GPU box).
 """
@@ -141,15 +142,15 @@ DOOR_ENVS, DOOR_STEPS, DOOR_WARMUP, DOOR_RING = 1 << 16, 100, 100, 16
 DOOR_FRESH_STEPS, DOOR_FRESH_WARMUP = 30, 5
 
 
-def door_cpu_rate(procs, steps_per_proc=20000):
+def door_cpu_rate(procs, steps_per_proc=20000, task="sawyer_door"):
     """env-steps/s of the fp64 checker on `procs` host processes (oracle/door_cpu_bench.py, one checker instance each:
     oracle/mjengine.c keeps static scratch, so it is not thread-safe), and its flop count per env step -- the
     ALGORITHMIC flops of SURVEY.md 8d, counted inside the checker on the same random-action workload."""
     script = os.path.join(REPO, "oracle", "door_cpu_bench.py")
     env = dict(os.environ, OMP_NUM_THREADS="1")
-    subprocess.check_call([sys.executable, script, "0", "5"], stdout=subprocess.DEVNULL, env=env)  # builds the checker once
+    subprocess.check_call([sys.executable, script, "0", "5", task], stdout=subprocess.DEVNULL, env=env)  # builds the checker once
     t0 = time.perf_counter()
-    ps = [subprocess.Popen([sys.executable, script, str(100 + k), str(steps_per_proc)], stdout=subprocess.PIPE, text=True, env=env)
+    ps = [subprocess.Popen([sys.executable, script, str(100 + k), str(steps_per_proc), task], stdout=subprocess.PIPE, text=True, env=env)
           for k in range(procs)]
     res = [json.loads(p.communicate()[0].strip().splitlines()[-1]) for p in ps]
     wall = time.perf_counter() - t0
@@ -158,16 +159,18 @@ def door_cpu_rate(procs, steps_per_proc=20000):
     return procs * steps_per_proc / loop, flops, wall
 
 
-def run_door(dev, rank, world, sm_max_mhz, sm_count, with_cpu):
-    """Second bench section: batched sawyer_door step (BASELINE.json configs[2]), 65,536 envs per GPU, random actions."""
+def run_door(dev, rank, world, sm_max_mhz, sm_count, with_cpu, task="sawyer_door"):
+    """Second / third bench section: batched sawyer_door (BASELINE.json configs[2]) or sawyer_peg (configs[3]) step,
+    65,536 envs per GPU, random actions."""
     import torch
     import torch.distributed as dist
 
     from earl_benchmark_b200.distributed import max_over_ranks
-    from earl_benchmark_b200.envs import sawyer_door
+    from earl_benchmark_b200.envs import sawyer_door, sawyer_peg
 
     n = DOOR_ENVS
-    env = sawyer_door.SawyerDoorV2(num_envs=n, device=dev, seed=rank)
+    door = task == "sawyer_door"
+    env = (sawyer_door.SawyerDoorV2 if door else sawyer_peg.SawyerPegV2)(num_envs=n, device=dev, seed=rank)
     env.reset()
     gen = torch.Generator(device=dev)
     gen.manual_seed(4321 + rank)
@@ -217,13 +220,14 @@ def run_door(dev, rank, world, sm_max_mhz, sm_count, with_cpu):
     if rank == 0:
         sub = max(1, w1["substeps"] - w0["substeps"])
         value = n * world * DOOR_STEPS / (ms * 1e-3)
-        out = {"metric": "batched env-steps/sec (sawyer_door, sparse, 5 substeps per env step)", "value": value, "unit": UNIT,
+        out = {"metric": f"batched env-steps/sec ({task}, sparse, 5 substeps per env step)", "value": value, "unit": UNIT,
                "envs_per_gpu": n, "steps": DOOR_STEPS, "warmup": DOOR_WARMUP, "ms_per_step": ms / DOOR_STEPS,
                "dtype": "f32", "gpu_launches": launches,
                "window": f"steps {DOOR_WARMUP}..{DOOR_WARMUP + DOOR_STEPS} of a random-action rollout after reset",
                "first_steps_after_reset": {"value": n * world * DOOR_FRESH_STEPS / (ms_fresh * 1e-3), "unit": UNIT,
                                            "steps": DOOR_FRESH_STEPS, "warmup": DOOR_FRESH_WARMUP,
-                                           "note": "lighter workload: only the four door-on-table contacts per env"},
+                                           "note": "lighter workload: only the four door-on-table contacts per env" if door else
+                                                   "peg lying on the table, gripper above it"},
                "e2e": {"value": n * world * 5 / e2e_s, "unit": UNIT, "h2d_bytes_per_step": n * 16 * world,
                        "d2h_bytes_per_step": n * (14 * 4 + 4 + 1 + 1) * world, "steps": 5},
                "work": {"newton_iterations_per_substep": (w1["newton_iterations"] - w0["newton_iterations"]) / sub,
@@ -232,12 +236,12 @@ def run_door(dev, rank, world, sm_max_mhz, sm_count, with_cpu):
                         "bad_states": w1["bad_states"] - w0["bad_states"],
                         "overflow_states": w1["overflow_states"] - w0["overflow_states"]},
                "kernel": "mj_step_kernel (one warp per env, 16 envs per SM in flight) + mj_order_kernel (visiting order, <3 us)",
-               "ncu": {"source": "profiles/r01/door/prof_door_step_16k_r01.details.csv (16,384 envs, not this run)",
+               "ncu": {"source": "profiles/r01/door/prof_door_step_16k_r01.details.csv (sawyer_door, 16,384 envs, not this run)",
                        "executed_ipc": 2.17, "issue_slots_busy_pct": 54.3, "achieved_occupancy_pct": 24.9,
                        "warp_instructions_per_env_step": 1.03e5, "dram_pct_of_peak": 0.03}}
         if with_cpu:
             procs = os.cpu_count() or 1
-            rate, flops, wall = door_cpu_rate(procs)
+            rate, flops, wall = door_cpu_rate(procs, task=task)
             peak = sm_count * 128 * 2 * (sm_max_mhz or 1965.0) * 1e6 / 1e12
             ach = flops * (value / world) / 1e12
             out["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": procs, "kind": "port",
@@ -385,11 +389,13 @@ def run_ours(args):
                "kernel": "earl::tabletop_step_tma_kernel<3,256>  (cp.async.bulk pipeline)"}
         del a_b, o_b, r_b, d_b, tb, lb
 
-    door = None
+    door = peg = None
     if not args.profile and not args.no_door:
         props = torch.cuda.get_device_properties(dev)
         door = run_door(dev, rank, world, (clocks or {}).get("sm_max_mhz"), props.multi_processor_count,
                         with_cpu=(world == 1 and not args.no_cpu_baseline))
+        peg = run_door(dev, rank, world, (clocks or {}).get("sm_max_mhz"), props.multi_processor_count,
+                       with_cpu=(world == 1 and not args.no_cpu_baseline), task="sawyer_peg")
 
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
@@ -417,6 +423,8 @@ def run_ours(args):
             line["hbm_bound_check"] = big
         if door is not None:
             line["sawyer_door"] = door
+        if peg is not None:
+            line["sawyer_peg"] = peg
         if world == 1 and not args.no_cpu_baseline and not args.profile:
             threads = os.cpu_count() or 1
             rate, n_sample, el = cpu_port_rate(n, min(args.steps, 200), threads, budget_s=15.0)
@@ -440,7 +448,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-hbm-check", action="store_true", help="skip the 8M-env all-HBM operating point")
-    ap.add_argument("--no-door", action="store_true", help="skip the sawyer_door section")
+    ap.add_argument("--no-door", action="store_true", help="skip the sawyer_door / sawyer_peg sections")
     ap.add_argument("--profile", action="store_true", help="under ncu: no sustained warm-up, 1 e2e step, no CPU leg")
     ap.add_argument("--traffic-bytes", type=float, default=None,
                     help="dram bytes per launch from the committed ncu capture; default: profiles/r01 value for the "

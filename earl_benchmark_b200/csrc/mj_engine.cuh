@@ -625,10 +625,13 @@ MJ_HD real impedance(const real* solimp, real pos, real margin) {
 }
 
 // aref / R / D of row r from (solref, solimp, pos, margin, diagApprox); mj_makeImpedance + mj_referenceConstraint
-MJ_FN void finish_row(const Model& m, Work& w, int r, const real* solref, const real* solimp, real margin, real diag, real* R_out) {
+// `imp_pos` < 0: the impedance is evaluated at the row's own violation; >= 0: at this violation (vector residuals: the
+// six rows of a weld share the impedance of the residual's Euclidean norm, engine_core_constraint.c getposdim)
+MJ_FN void finish_row(const Model& m, Work& w, int r, const real* solref, const real* solimp, real margin, real diag, real* R_out,
+                      real imp_pos = -1.0f) {
   real vel = 0;
   for (int k = 0; k < m.nv; ++k) vel += w.J[r][k] * w.qvel[k];
-  const real imp = impedance(solimp, w.e_pos[r], margin);
+  const real imp = impedance(solimp, imp_pos >= 0 ? imp_pos : w.e_pos[r], margin);
   const real dmax = clampr(solimp[1], MINIMP, MAXIMP);
   real k, b;
   if (solref[0] > 0) {
@@ -699,8 +702,10 @@ MJ_FN void make_constraints(const Model& m, Work& w, int lane) {
     }
     for (int k = lane; k < 6; k += NL) { w.e_pos[r + k] = cpos[k]; w.e_type[r + k] = ROW_EQ; }
     wsync<NL>();
+    const real cnorm = msqrt(cpos[0] * cpos[0] + cpos[1] * cpos[1] + cpos[2] * cpos[2] + cpos[3] * cpos[3] + cpos[4] * cpos[4] +
+                             cpos[5] * cpos[5]);
     for (int k = lane; k < 6; k += NL)
-      finish_row(m, w, r + k, m.weld_solref[wi], m.weld_solimp[wi], 0.0f, m.weld_invweight[wi][k >= 3], nullptr);
+      finish_row(m, w, r + k, m.weld_solref[wi], m.weld_solimp[wi], 0.0f, m.weld_invweight[wi][k >= 3], nullptr, cnorm);
     r += 6;
   }
   // --- joint limits (hinge / slide); row allocation is uniform across lanes

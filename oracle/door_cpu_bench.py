@@ -1,4 +1,4 @@
-"""CPU baseline worker for bench.py: one process = one fp64 checker instance stepping the Sawyer door env with random
+"""CPU baseline worker for bench.py: one process = one fp64 checker instance stepping the Sawyer door (or peg) env with random
 actions.  TEST / BENCH INFRASTRUCTURE ONLY (bench.py's cpu_baseline leg).  Prints one JSON line:
 {"seconds": wall time of the stepping loop, "steps": n, "flops_per_env_step": checker flop counter / n}."""
 import json
@@ -12,12 +12,17 @@ REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, REPO)
 
 
-def main(seed, steps):
+def main(seed, steps, task="sawyer_door"):
     from earl_benchmark_b200.mjcf.compile import Model
-    from oracle.engine import SawyerDoorOracle
-    o = SawyerDoorOracle(Model.load(os.path.join(REPO, "earl_benchmark_b200", "models", "sawyer_door.npz")))
+    from oracle.engine import SawyerDoorOracle, SawyerPegOracle
+    model = Model.load(os.path.join(REPO, "earl_benchmark_b200", "models", task + ".npz"))
     rs = np.random.RandomState(seed)
-    o.reset(door_angle=-np.pi / 3 + rs.uniform(0, np.pi / 20))
+    if task == "sawyer_door":
+        o = SawyerDoorOracle(model)
+        o.reset(door_angle=-np.pi / 3 + rs.uniform(0, np.pi / 20))
+    else:
+        o = SawyerPegOracle(model)
+        o.reset()
     acts = rs.uniform(-1, 1, (steps, 4))
     for a in acts[:10]:
         o.step(a)
@@ -29,4 +34,4 @@ def main(seed, steps):
 
 
 if __name__ == "__main__":
-    main(int(sys.argv[1]), int(sys.argv[2]))
+    main(int(sys.argv[1]), int(sys.argv[2]), sys.argv[3] if len(sys.argv) > 3 else "sawyer_door")

@@ -391,11 +391,12 @@ static double impedance(const double *solimp, double pos, double margin) {
   return dmin + y * (dmax - dmin);
 }
 
+static double mje_imp_pos = -1; /* >= 0: violation used for the impedance instead of the row's own (vector residuals) */
 /* fill aref / R / D of row i from (solref, solimp, pos, margin, vel, diagApprox); mj_makeImpedance */
 void mje_finish_row(const mjModelF *m, mjDataF *d, int i, const double *solref, const double *solimp, double margin, double diag) {
   double vel = 0;
   for (int k = 0; k < m->nv; ++k) vel += d->efc_J[i][k] * d->qvel[k];
-  double imp = impedance(solimp, d->efc_pos[i], margin);
+  double imp = mje_imp_pos >= 0 ? impedance(solimp, mje_imp_pos, margin) : impedance(solimp, d->efc_pos[i], margin);
   double dmax = solimp[1] < MJMINIMP ? MJMINIMP : (solimp[1] > MJMAXIMP ? MJMAXIMP : solimp[1]);
   double k, b;
   if (solref[0] > 0) {
@@ -449,11 +450,14 @@ void mje_make_constraints(const mjModelF *m, mjDataF *d) {
       for (int k = 0; k < 3; ++k) d->efc_J[r + 3 + k][c] = 0.5 * q3[1 + k];
     }
     d->flops += (long long)nv * 60 + 120;
+    /* vector residual: all six rows share the impedance of its Euclidean norm (getposdim) */
+    mje_imp_pos = sqrt(cpos[0]*cpos[0]+cpos[1]*cpos[1]+cpos[2]*cpos[2]+cpos[3]*cpos[3]+cpos[4]*cpos[4]+cpos[5]*cpos[5]);
     for (int k = 0; k < 6; ++k) {
       d->efc_pos[r + k] = cpos[k];
       d->efc_type[r + k] = 0;
       mje_finish_row(m, d, r + k, m->weld_solref + 2 * w, m->weld_solimp + 5 * w, 0.0, m->weld_invweight[2 * w + (k >= 3)]);
     }
+    mje_imp_pos = -1;
     r += 6;
   }
   /* --- joint limits (hinge / slide), mj_instantiateLimit */
