@@ -23,6 +23,11 @@ constexpr int GEOM_PLANE = 0, GEOM_CYLINDER = 5, GEOM_BOX = 6, GEOM_MESH = 7;
 // cannot be resolved in fp32, where the refinement stops at a different portal and contact normals of thin-box-vs-
 // cylinder pairs came out up to 30 degrees away from the fp64 result; rounding the INPUTS to fp32 changes nothing
 // measurable.  B200 issues fp64 at half the fp32 rate and MPR is a minor share of the step.
+// Its branches are also DISCONTINUOUS in the inputs: at a near-degenerate portal (thin pad edge on a cylinder) a 1e-7
+// change of a pose decides which portal the refinement continues with, and the two contact normals can be degrees
+// apart (measured: 3 degrees, 1 of 96 probe states; the fp64 checker perturbed by 1e-7 flips the same way).  That is a
+// property of the reference's algorithm, not of the precision: forcing the device to round like the host build (no
+// FMA contraction) did not change a single result.
 typedef double mreal;
 constexpr mreal MPR_TOL = 1e-6;
 constexpr int MPR_ITER = 50;
@@ -47,9 +52,11 @@ struct NarrowScratch {
   CObj o1, o2;
   int nsup;  // support-function calls of the current portal refinement (scheduling cost estimate)
   RawCon rc[8];
+  struct BoxScratch { real A[3][3], B[3][3], poly[16][3], tmp[16][3]; };
+  struct PortalScratch { Supp P[4], v4; };
   union {
-    struct { real A[3][3], B[3][3], poly[16][3], tmp[16][3]; };  // box-box
-    struct { Supp P[4], v4; };                                   // portal refinement
+    BoxScratch bb;     // box-box
+    PortalScratch pr;  // portal refinement
   };
 };
 static_assert(sizeof(NarrowScratch) <= sizeof(real) * MAXV * LDM, "narrow-phase scratch must fit in Work::H");
@@ -117,10 +124,10 @@ MJ_FN int clip_poly(real (*poly)[3], int n, const real* pn, real pd, real (*out)
 
 MJ_FN int box_box(const real* p1, const real* R1, const real* s1, const real* p2, const real* R2, const real* s2, real margin,
                   RawCon* out, NarrowScratch* S) {
-  real (*A)[3] = S->A;
-  real (*B)[3] = S->B;
-  real (*poly)[3] = S->poly;
-  real (*tmp)[3] = S->tmp;
+  real (*A)[3] = S->bb.A;
+  real (*B)[3] = S->bb.B;
+  real (*poly)[3] = S->bb.poly;
+  real (*tmp)[3] = S->bb.tmp;
   real pp[3], pA[3], pB[3], Q[3][3];
   for (int k = 0; k < 3; ++k) { col3(A[k], R1, k); col3(B[k], R2, k); }
   sub3(pp, p2, p1);
@@ -354,8 +361,8 @@ MJ_FN mreal tri_dist2(const mreal* Pt, const mreal* x0, const mreal* B, const mr
 // returns 1 with (depth, dir, pos) when the (inflated) geoms penetrate; all lanes take the same path
 template <int NL>
 MJ_FN int mpr_penetration(const CObj& o1, const CObj& o2, real* depth_out, real* dir_out, real* pos_out, NarrowScratch* S, int lane) {
-  Supp* P = S->P;
-  Supp& v4 = S->v4;
+  Supp* P = S->pr.P;
+  Supp& v4 = S->pr.v4;
   if (lane == 0) S->nsup = 0;
   const mreal origin[3] = {0, 0, 0};
   for (int k = 0; k < 3; ++k) { P[0].v1[k] = o1.pos[k]; P[0].v2[k] = o2.pos[k]; }

@@ -20,6 +20,13 @@ MJ_FN void substep(const Model& m, const real* hull, Work& w, int lane) {
   MJ_PHASE_END(w, 1);
   collide<NL>(m, hull, w, lane);
   bsync<NL>();
+#if defined(MJ_TRACE_DEVICE) && defined(__CUDA_ARCH__)
+  if (threadIdx.x == 0)
+    for (int c = 0; c < w.ncon; ++c)
+      printf("  [dev] con %d g %d %d dist %.9g pos %.9g %.9g %.9g n %.9g %.9g %.9g\n", c, w.con_g1[c], w.con_g2[c], (double)w.con_dist[c],
+             (double)w.con_pos[c][0], (double)w.con_pos[c][1], (double)w.con_pos[c][2], (double)w.con_frame[c][0],
+             (double)w.con_frame[c][1], (double)w.con_frame[c][2]);
+#endif
   MJ_PHASE_END(w, 2);
   make_constraints<NL>(m, w, lane);
   contact_rows<NL>(m, w, lane);
