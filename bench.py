@@ -170,7 +170,7 @@ def run_door(dev, rank, world, sm_max_mhz, sm_count, with_cpu, task="sawyer_door
 
     n = DOOR_ENVS
     door = task == "sawyer_door"
-    env = (sawyer_door.SawyerDoorV2 if door else sawyer_peg.SawyerPegV2)(num_envs=n, device=dev, seed=rank)
+    env = (sawyer_door.SawyerDoorV2 if door else sawyer_peg.SawyerPegV2)(reward_type="sparse", num_envs=n, device=dev, seed=rank)
     env.reset()
     gen = torch.Generator(device=dev)
     gen.manual_seed(4321 + rank)

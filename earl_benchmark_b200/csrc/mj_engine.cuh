@@ -46,7 +46,7 @@ constexpr int MAXS = 8;     // sites kept on the device
 constexpr int MAXU = 2;     // actuators
 constexpr int MAXW = 1;     // welds
 constexpr int MAXEFC = 64;  // constraint rows
-constexpr int MAXCON = 12;  // contacts
+constexpr int MAXCON = 16;  // contacts
 constexpr int MAXPAIR = 192; // candidate geom pairs
 constexpr int MAXMG = 16;    // geoms on moving bodies (their world poses are recomputed every substep)
 constexpr int MAXHIT = 24;   // candidate pairs that survive the broad phase in one substep
@@ -145,13 +145,17 @@ struct Work {
   real e_pos[MAXEFC], e_aref[MAXEFC], e_D[MAXEFC], e_R[MAXEFC], e_jar[MAXEFC], e_jv[MAXEFC], e_force[MAXEFC];
   int e_type[MAXEFC], e_state[MAXEFC];
   // collision
-  real mg_xpos[MAXMG][3], mg_xmat[MAXMG][9];
+  // world poses of the geoms on moving bodies: written and read by the collision phase only, so the same storage
+  // holds the cone Hessian blocks (dim x dim, dim <= 4; middle zone) that only the solve phase touches
+  union {
+    struct { real mg_xpos[MAXMG][3], mg_xmat[MAXMG][9]; };
+    real con_H[MAXCON][16];
+  };
   int nhit;
   unsigned char hit_list[MAXHIT];
   // contacts
   real con_pos[MAXCON][3], con_frame[MAXCON][9], con_dist[MAXCON], con_fri[MAXCON][5], con_mu[MAXCON];
   int con_g1[MAXCON], con_g2[MAXCON], con_dim[MAXCON], con_row[MAXCON];
-  real con_H[MAXCON][16];  // cone Hessian block (dim x dim, dim <= 4) in the middle zone
   // task layer
   real action[4], obs7[8];
   unsigned steps, flags, goalrow;
