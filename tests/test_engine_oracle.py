@@ -143,3 +143,35 @@ def test_gripper_opening_trajectory_known_answer(oracle):
     ref = d["next_observations"][:40, 3]
     oracle.goal = oracle.GOAL.copy()
     assert ref.min() < 0.28 and np.abs(sim - ref).max() < 4e-4, np.abs(sim - ref).max()
+
+
+def test_recorded_weld_lag_vs_documented_and_calibrated_weld():
+    """KNOWN GAP, kept measurable.  The mocap position follows from the recorded actions, so hand - mocap is observable
+    in the demonstrations.  While the mocap descends at ~0.93 cm per env step the RECORDED hand settles 32-34 mm behind
+    it.  With MuJoCo's documented weld regulariser the checker settles at the critically damped value
+    2 * timeconst * v (minus one substep of observation staleness) = 28-29 mm; with the calibrated translational
+    regulariser (`WELD_TRAN_SCALE` = 3.35) it follows the recording within 2 mm."""
+    from earl_benchmark_b200.mjcf.compile import WELD_TRAN_SCALE
+    d = demos.load("sawyer_door", "forward")
+    obs, nobs, act = d["observations"], d["next_observations"], d["actions"]
+    assert np.all(act[:9, 2] < -0.85)                      # steady descent
+    lags = {}
+    for name, scale in (("calibrated", 1.0), ("documented", 1.0 / WELD_TRAN_SCALE)):
+        m = Model.load(sawyer_door.MODEL_PATH)
+        m.weld_invweight[:, 0] *= scale
+        o = SawyerDoorOracle(m)
+        o.goal = obs[0][7:14].astype(np.float64)
+        o.reset(door_angle=door_angle(obs[0][4:6]))
+        mocap = o.HAND_INIT.copy()
+        lag_demo, lag_sim = [], []
+        for t in range(9):
+            a = np.clip(act[t].astype(np.float64), -1, 1)
+            mocap = np.clip(mocap + a[:3] * o.ACTION_SCALE, o.MOCAP_LOW, o.MOCAP_HIGH)
+            ob, _ = o.step(act[t])
+            lag_demo.append(nobs[t][2] - mocap[2])
+            lag_sim.append(ob[2] - mocap[2])
+        lags[name] = np.array(lag_sim)
+    lag_demo = np.array(lag_demo)
+    assert 0.0315 < lag_demo[6:].max() < 0.0355, lag_demo               # recorded: 32-34 mm
+    assert 0.0275 < lags["documented"][6:].max() < 0.0300, lags         # 2 * 0.02 s * 0.74 m/s - staleness
+    assert np.abs(lags["calibrated"][3:] - lag_demo[3:]).max() < 2e-3, (lags, lag_demo)
