@@ -2,8 +2,9 @@
 
     python -m earl_benchmark_b200.build [--force] [--verbose]
 
-Two translation units: the tabletop step (bit-exact fp64 arithmetic, so no FMA contraction) and the
-articulated-body engine of the Sawyer tasks (fp32, FMA on).  The .so is git-ignored but travels to the GPU box with
+Translation units: the tabletop step (bit-exact fp64 arithmetic, so no FMA contraction), the articulated-body engine
+of the Sawyer tasks (fp32, FMA on) once per compile-time capacity set (earl_mj_small.cu, earl_mj_large.cu), and the
+dispatcher that exports the earl_mj_* entry points (earl_mj.cu).  The .so is git-ignored but travels to the GPU box with
 the repo snapshot.
 """
 import os
@@ -16,7 +17,8 @@ INCLUDE = os.path.join(os.path.dirname(PKG), "include")
 LIB = os.path.join(PKG, "libearl_b200.so")
 OBJDIR = os.path.join(PKG, "build")
 # (source, extra flags)
-UNITS = [("earl_b200.cu", ["--fmad=false"]), ("earl_mj.cu", [])]
+MJ_EXTRA = os.environ.get("EARL_MJ_EXTRA_FLAGS", "").split()  # profiling / trace builds (-DMJ_PHASE_TIMING, -DMJ_TRACE_DEVICE)
+UNITS = [("earl_b200.cu", ["--fmad=false"]), ("earl_mj.cu", []), ("earl_mj_small.cu", MJ_EXTRA), ("earl_mj_large.cu", MJ_EXTRA)]
 SOURCES = [os.path.join(CSRC, u[0]) for u in UNITS]
 DEPS = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(INCLUDE, f) for f in os.listdir(INCLUDE)]
 

@@ -45,11 +45,19 @@ constexpr int MAXG = 32;    // geoms kept on the device
 constexpr int MAXS = 8;     // sites kept on the device
 constexpr int MAXU = 2;     // actuators
 constexpr int MAXW = 1;     // welds
-constexpr int MAXEFC = 64;  // constraint rows
-constexpr int MAXCON = 16;  // contacts
+// Two capacity sets are compiled from these sources (earl_mj_small.cu / earl_mj_large.cu): the workspace of one
+// environment lives in shared memory, so rows x dofs and contacts decide how many environments one SM keeps in flight.
+#if defined(MJ_CAPSET_LARGE)
+constexpr int MAXEFC = 96;  // constraint rows
+constexpr int MAXCON = 24;  // contacts
+constexpr int MAXHIT = 32;  // candidate pairs that survive the broad phase in one substep
+#else
+constexpr int MAXEFC = 64;
+constexpr int MAXCON = 16;
+constexpr int MAXHIT = 24;
+#endif
 constexpr int MAXPAIR = 192; // candidate geom pairs
 constexpr int MAXMG = 16;    // geoms on moving bodies (their world poses are recomputed every substep)
-constexpr int MAXHIT = 24;   // candidate pairs that survive the broad phase in one substep
 constexpr int LDM = MAXV + 1;  // padded leading dimension of the dense nv x nv matrices
 
 constexpr real MINVAL = 1e-15f;

@@ -103,7 +103,8 @@ EARL_API int earl_mj_counters(earl_mj_handle* h, int64_t* total_steps_host, int6
 EARL_API int earl_mj_eval_stats(earl_mj_handle* h, double* out4_dev, void* stream);
 /* Work counters accumulated by the step kernel since creation (host): { env_steps, substeps, newton_iterations,
  * constraint_rows, contacts, bad_states (env steps with a non-positive Cholesky pivot), overflow_states (env steps in
- * which a fixed capacity -- 24 candidate pairs, 16 contacts, 64 rows -- dropped work) }. */
+ * which a fixed capacity -- 24 / 32 candidate pairs, 16 / 24 contacts, 64 / 96 rows for the door / peg capacity set
+ * -- dropped work) }. */
 EARL_API int earl_mj_work_counters(earl_mj_handle* h, uint64_t* out7_host);
 EARL_API int64_t earl_mj_launch_count(const earl_mj_handle* h);
 
