@@ -235,9 +235,9 @@ def run_door(dev, rank, world, sm_max_mhz, sm_count, with_cpu, task="sawyer_door
                         "contacts_per_substep": (w1["contacts"] - w0["contacts"]) / sub,
                         "bad_states": w1["bad_states"] - w0["bad_states"],
                         "overflow_states": w1["overflow_states"] - w0["overflow_states"]},
-               "kernel": "mj_step_kernel (one warp per env, 16 envs per SM in flight) + mj_order_kernel (visiting order, <3 us)",
+               "kernel": ("mj_step_kernel (one warp per env, %d envs per SM in flight) + mj_order_kernel (visiting order, <3 us)" % (16 if door else 12)),
                "ncu": {"source": "profiles/r01/door/prof_door_step_16k_r01.details.csv (sawyer_door, 16,384 envs, not this run)",
-                       "executed_ipc": 2.17, "issue_slots_busy_pct": 54.3, "achieved_occupancy_pct": 24.9,
+                       "executed_ipc": 2.15, "issue_slots_busy_pct": 53.9, "achieved_occupancy_pct": 25.0,
                        "warp_instructions_per_env_step": 1.03e5, "dram_pct_of_peak": 0.03}}
         if with_cpu:
             procs = os.cpu_count() or 1
