@@ -319,12 +319,31 @@ class Model:
         ("weld_solimp", "f8"), ("weld_invweight", "f8"),
         ("mocap_pos0", "f8"), ("mocap_quat0", "f8"),
     )
+    # blob version 2 (written only when a model has joint equalities; the kitchen): appended after FIELDS
+    EXT_FIELDS = (
+        ("neq", "i4"),
+        ("eq_qposadr", "i4"), ("eq_dofadr", "i4"),   # [neq,2]: joint1, joint2 (hinge / slide)
+        ("eq_polycoef", "f8"),                       # [neq,5]: q1 - q1_0 = poly(q2 - q2_0)
+        ("eq_solref", "f8"), ("eq_solimp", "f8"), ("eq_invweight", "f8"),
+        ("dof_solref_friction", "f8"), ("dof_solimp_friction", "f8"),   # [nv,2], [nv,5]: friction-loss rows
+    )
 
     def __init__(self):
         self.names = {"body": [], "joint": [], "geom": [], "site": []}
 
+    def _ext_defaults(self):
+        nv = int(self.nv)
+        d = dict(neq=np.int32(0), eq_qposadr=np.zeros((0, 2), np.int32), eq_dofadr=np.zeros((0, 2), np.int32),
+                 eq_polycoef=np.zeros((0, 5)), eq_solref=np.zeros((0, 2)), eq_solimp=np.zeros((0, 5)), eq_invweight=np.zeros(0),
+                 dof_solref_friction=np.tile(np.array([0.02, 1.0]), (nv, 1)),
+                 dof_solimp_friction=np.tile(np.array([0.9, 0.95, 0.001, 0.5, 2.0]), (nv, 1)))
+        for k, v in d.items():
+            if not hasattr(self, k):
+                setattr(self, k, v)
+
     def save(self, path):
-        np.savez_compressed(path, **{k: getattr(self, k) for k, _ in self.FIELDS},
+        self._ext_defaults()
+        np.savez_compressed(path, **{k: getattr(self, k) for k, _ in self.FIELDS + self.EXT_FIELDS},
                             **{f"name_{k}": np.array(v) for k, v in self.names.items()})
 
     @classmethod
@@ -333,14 +352,20 @@ class Model:
         with np.load(path, allow_pickle=False) as z:
             for k, _ in cls.FIELDS:
                 setattr(m, k, z[k])
+            for k, _ in cls.EXT_FIELDS:
+                if k in z.files:
+                    setattr(m, k, z[k])
             for k in m.names:
                 m.names[k] = [str(x) for x in z[f"name_{k}"]]
         return m
 
     def to_blob(self):
-        """Flat binary: magic 'EMDL', version, then for each field: i4 ndim, i4 dims..., data (i4 or f8), 8-byte aligned."""
-        out = [np.array([0x4C444D45, 1], dtype="<i4").tobytes()]
-        for k, dt in self.FIELDS:
+        """Flat binary: magic 'EMDL', version, then for each field: i4 ndim, i4 dims..., data (i4 or f8), 8-byte aligned.
+        Version 1 = FIELDS (door, peg); version 2 = FIELDS + EXT_FIELDS (models with joint equalities or friction loss)."""
+        self._ext_defaults()
+        version = 2 if int(self.neq) > 0 or np.any(np.asarray(self.dof_frictionloss) > 0) else 1
+        out = [np.array([0x4C444D45, version], dtype="<i4").tobytes()]
+        for k, dt in self.FIELDS + (self.EXT_FIELDS if version == 2 else ()):
             a = np.ascontiguousarray(np.asarray(getattr(self, k)), dtype="<" + dt)
             hdr = np.array([a.ndim] + list(a.shape), dtype="<i4").tobytes()
             if len(hdr) % 8:
@@ -366,12 +391,15 @@ class Model:
 WELD_TRAN_SCALE = 3.35
 
 
-def compile_model(spec, body_pos_overrides=None, keep_geoms=(), keep_sites=None, frame_sites=(), weld_tran_scale=WELD_TRAN_SCALE):
+def compile_model(spec, body_pos_overrides=None, keep_geoms=(), keep_sites=None, frame_sites=(), weld_tran_scale=WELD_TRAN_SCALE,
+                  weld_relpose="identity"):
     """Spec -> fused Model.
 
     keep_geoms: names of non-colliding geoms to keep (their frames are observed, e.g. 'handle').
     frame_sites: names of ORIGINAL bodies whose frames are needed (observations, welds): each becomes a site
                  named 'body:<name>' on the fused body.
+    weld_relpose: "identity" = metaworld's reset_mocap_welds() (eq_data <- [0 0 0 1 0 0 0]); "qpos0" = MuJoCo's compiler
+                 default when the MJCF gives no relpose: pose of body2 in the frame of body1 at qpos0 (kitchen).
     """
     raw = RawModel(spec, body_pos_overrides)
     biw, diw = raw.invweight0()
@@ -540,8 +568,16 @@ def compile_model(spec, body_pos_overrides=None, keep_geoms=(), keep_sites=None,
         t2 = T[b2] if anchor[b2] != b2 else Transform()
         wp.append(t2.pos)
         wq.append(t2.quat)
-        # metaworld's reset_mocap_welds() overwrites eq_data with the identity relative pose
-        wr.append(_floats(e.get("relpose", "0 0 0 1 0 0 0"), 7))
+        if "relpose" in e and np.any(_floats(e["relpose"], 7)[3:] != 0):
+            wr.append(_floats(e["relpose"], 7))
+        elif weld_relpose == "identity":
+            # metaworld's reset_mocap_welds() overwrites eq_data with the identity relative pose
+            wr.append(_floats("0 0 0 1 0 0 0", 7))
+        else:
+            xpos0, xmat0 = raw.fk(raw.qpos0)[:2]
+            R1 = xmat0[b1]
+            rq = mat2quat(R1.T @ xmat0[b2])
+            wr.append(np.concatenate([R1.T @ (xpos0[b2] - xpos0[b1]), rq]))
         wsr.append(_floats(e["solref"], 2))
         wsi.append(_solimp(e["solimp"]))
         wiw.append((biw[b1] + biw[b2]) * np.array([weld_tran_scale, 1.0]))
@@ -551,6 +587,26 @@ def compile_model(spec, body_pos_overrides=None, keep_geoms=(), keep_sites=None,
     m.weld_relpose = np.array(wr).reshape(nw, 7)
     m.weld_solref, m.weld_solimp = np.array(wsr).reshape(nw, 2), np.array(wsi).reshape(nw, 5)
     m.weld_invweight = np.array(wiw).reshape(nw, 2)
+    # joint equalities (mjEQ_JOINT): q1 - q1_0 = poly(q2 - q2_0), hinge / slide joints
+    eqs = [e for e in spec.equalities if e["tag"] == "joint" and _bool(e.get("active", "true"))]
+    m.neq = np.int32(len(eqs))
+    eq_q, eq_d, eq_c, eq_sr, eq_si, eq_iw = [], [], [], [], [], []
+    for e in eqs:
+        j1, j2 = raw.joints[jn.index(e["joint1"])], raw.joints[jn.index(e["joint2"])]
+        if j1["jtype"] < 2 or j2["jtype"] < 2:
+            raise NotImplementedError("joint equality on a free / ball joint")
+        eq_q.append((j1["qposadr"], j2["qposadr"]))
+        eq_d.append((j1["dofadr"], j2["dofadr"]))
+        eq_c.append(_floats(e.get("polycoef", "0 1 0 0 0"), 5))
+        eq_sr.append(_floats(e["solref"], 2))
+        eq_si.append(_solimp(e["solimp"]))
+        eq_iw.append(diw[j1["dofadr"]] + diw[j2["dofadr"]])     # mj_diagApprox, mjEQ_JOINT
+    ne = len(eqs)
+    m.eq_qposadr, m.eq_dofadr = np.array(eq_q, np.int32).reshape(ne, 2), np.array(eq_d, np.int32).reshape(ne, 2)
+    m.eq_polycoef, m.eq_solref, m.eq_solimp = np.array(eq_c).reshape(ne, 5), np.array(eq_sr).reshape(ne, 2), np.array(eq_si).reshape(ne, 5)
+    m.eq_invweight = np.array(eq_iw).reshape(ne)
+    m.dof_solref_friction = np.array([_floats(raw.joints[k]["solreffriction"], 2) for k in range(len(raw.joints)) for _ in range({0: 6, 1: 3, 2: 1, 3: 1}[raw.joints[k]["jtype"]])]).reshape(raw.nv, 2)
+    m.dof_solimp_friction = np.array([_solimp(raw.joints[k]["solimpfriction"]) for k in range(len(raw.joints)) for _ in range({0: 6, 1: 3, 2: 1, 3: 1}[raw.joints[k]["jtype"]])]).reshape(raw.nv, 5)
     mc = [b for b in range(nb) if raw.mocap[b]]
     m.mocap_pos0 = raw.pos[mc[0]].copy() if mc else np.zeros(3)
     m.mocap_quat0 = raw.quat[mc[0]].copy() if mc else np.array([1.0, 0, 0, 0])

@@ -216,3 +216,53 @@ class SawyerPegOracle:
         self.e.step(self.FRAME_SKIP)
         o = self.obs()  # stale by one substep, as in the reference (see SawyerDoorOracle.step)
         return o, float(np.linalg.norm(o[4:7] - o[11:14]) <= self.TARGET_RADIUS)
+
+
+class KitchenOracle:
+    """Reference kitchen task on the fp64 checker engine: ENV/kitchen.py::Kitchen over adept_envs KitchenV0 / Robot_VelAct
+    (SURVEY.md 3.4, rows a12-a14).  The logic around the physics is oracle/kitchen_logic.py (pinned bit for bit against
+    the reference's own code); the physics is this file's Engine on the compiled franka_kitchen_jntpos_act_ab.xml model
+    (friction-loss rows, joint equalities, pyramidal cones, capsule collisions) -- PARITY UNPINNED: the reference ships no
+    kitchen trajectory, MuJoCo is not in this image."""
+
+    def __init__(self, model):
+        from . import kitchen_logic as KL
+        self.KL = KL
+        self.e = Engine(model)
+        self.logic = KL.KitchenLogic()
+        self.site_names = KL.SITES
+
+    def seed(self, seed):
+        self.logic.seed(seed)
+
+    def _simulate(self, ctrl):
+        self.e.ctrl[:] = ctrl                       # do_simulation writes ctrl[0:nu]; the engine clamps to ctrlrange
+        self.e.step(self.KL.FRAME_SKIP)
+
+    def sites(self):
+        return np.stack([self.e.site_xpos(s) for s in self.site_names])
+
+    def reset(self):
+        """Kitchen.reset_model (ENV/kitchen.py:118-139): drawn object configuration, robot.reset (sim.reset + qpos write +
+        forward + 5 cached observations at noise ratio 1), mocap <- midpoint, 10 x robot.step(0), observation."""
+        KL = self.KL
+        q0, self.config_index = self.logic.reset_state()
+        self.e.reset()
+        self.e.qpos[:] = q0
+        self.e.qvel[:] = 0
+        self.e.forward()
+        for _ in range(5):
+            self.logic.observe(self.e.qpos, noise_ratio=1)
+        self.e.mocap_pos[:] = KL.MIDPOINT
+        for _ in range(10):
+            _, ctrl = self.logic.control(np.zeros(9), KL.MIDPOINT)
+            self._simulate(ctrl)
+        return self.logic.observe(self.e.qpos)
+
+    def step(self, action):
+        """KitchenV0.step (ADEPT/franka/kitchen_multitask_v0.py:91-125) -> (obs, reward, success)."""
+        mocap, ctrl = self.logic.control(np.asarray(action, np.float64), self.e.mocap_pos.copy())
+        self.e.mocap_pos[:] = mocap
+        self._simulate(ctrl)
+        obs = self.logic.observe(self.e.qpos)
+        return obs, self.logic.reward(obs, self.e.mocap_pos.copy(), self.sites()), self.logic.success(obs)

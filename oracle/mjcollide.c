@@ -22,6 +22,7 @@
 #include <string.h>
 
 #define GEOM_PLANE 0
+#define GEOM_CAPSULE 3
 #define GEOM_CYLINDER 5
 #define GEOM_BOX 6
 #define GEOM_MESH 7
@@ -204,6 +205,12 @@ static void support_geom(const CObj *o, const double *dir, double *res) {
       double t = sqrt(dl[0] * dl[0] + dl[1] * dl[1]);
       if (t > MINVAL) { loc[0] = dl[0] / t * sz[0]; loc[1] = dl[1] / t * sz[0]; } else { loc[0] = loc[1] = 0; }
       loc[2] = dl[2] >= 0 ? sz[1] : -sz[1];
+      break;
+    }
+    case GEOM_CAPSULE: { /* segment along local z (half length size[1]) inflated by the radius size[0] */
+      double t = sqrt(dl[0] * dl[0] + dl[1] * dl[1] + dl[2] * dl[2]);
+      for (int k = 0; k < 3; ++k) loc[k] = t > MINVAL ? dl[k] / t * sz[0] : 0;
+      loc[2] += dl[2] >= 0 ? sz[1] : -sz[1];
       break;
     }
     case GEOM_MESH: {
@@ -444,6 +451,74 @@ static double point_box_dist2(const double *c, const double *p, const double *R,
 /* ------------------------------------------------------------------------------------------ driver */
 /* sensitivity probe (tests only): round the geom poses to fp32 before collision, i.e. give the fp64 narrow phase the
  * inputs the fp32 engine has */
+/* mjc_PlaneCapsule: one contact per end sphere */
+static int plane_capsule(const mjModelF *m, const mjDataF *d, int gp, int g, double margin, RawCon *out) {
+  const double *Rp = d->geom_xmat[gp], *R = d->geom_xmat[g], *sz = m->geom_size + 3 * g;
+  double n[3] = {Rp[2], Rp[5], Rp[8]}, ax[3] = {R[2], R[5], R[8]};
+  int nc = 0;
+  for (int e = -1; e <= 1; e += 2) {
+    double c[3], rel[3];
+    for (int k = 0; k < 3; ++k) c[k] = d->geom_xpos[g][k] + e * sz[1] * ax[k];
+    sub3(rel, c, d->geom_xpos[gp]);
+    double dist = dot3(rel, n) - sz[0];
+    if (dist >= margin) continue;
+    for (int k = 0; k < 3; ++k) { out[nc].pos[k] = c[k] - n[k] * (sz[0] + 0.5 * dist); out[nc].normal[k] = n[k]; }
+    out[nc].dist = dist;
+    ++nc;
+  }
+  return nc;
+}
+
+/* sphere-sphere kernel shared by the capsule routines (mjraw_SphereSphere) */
+static int sphere_sphere(const double *c1, double r1, const double *c2, double r2, double margin, RawCon *out) {
+  double n[3];
+  sub3(n, c2, c1);
+  double len = sqrt(dot3(n, n));
+  double dist = len - r1 - r2;
+  if (dist >= margin) return 0;
+  if (len < MINVAL) { n[0] = 1; n[1] = n[2] = 0; } else { for (int k = 0; k < 3; ++k) n[k] /= len; }
+  for (int k = 0; k < 3; ++k) { out->pos[k] = c1[k] + n[k] * (r1 + 0.5 * dist); out->normal[k] = n[k]; }
+  out->dist = dist;
+  return 1;
+}
+
+/* mjc_CapsuleCapsule: closest points of the two axis segments; parallel axes give two contacts (the ends of the overlap) */
+static int capsule_capsule(const mjModelF *m, const mjDataF *d, int g1, int g2, double margin, RawCon *out) {
+  const double *R1 = d->geom_xmat[g1], *R2 = d->geom_xmat[g2], *s1 = m->geom_size + 3 * g1, *s2 = m->geom_size + 3 * g2;
+  const double *p1 = d->geom_xpos[g1], *p2 = d->geom_xpos[g2];
+  double a1[3] = {R1[2] * s1[1], R1[5] * s1[1], R1[8] * s1[1]}, a2[3] = {R2[2] * s2[1], R2[5] * s2[1], R2[8] * s2[1]}, dif[3];
+  sub3(dif, p1, p2);
+  double ma = dot3(a1, a1), mb = -dot3(a1, a2), mc = dot3(a2, a2), u = -dot3(a1, dif), v = dot3(a2, dif);
+  double det = ma * mc - mb * mb;
+  if (fabs(det) >= MINVAL) { /* general configuration */
+    double x1 = (mc * u - mb * v) / det, x2 = (ma * v - mb * u) / det;
+    if (x1 > 1) { x1 = 1; x2 = (v - mb) / mc; } else if (x1 < -1) { x1 = -1; x2 = (v + mb) / mc; }
+    if (x2 > 1) { x2 = 1; x1 = (u - mb) / ma; if (x1 > 1) x1 = 1; else if (x1 < -1) x1 = -1; }
+    else if (x2 < -1) { x2 = -1; x1 = (u + mb) / ma; if (x1 > 1) x1 = 1; else if (x1 < -1) x1 = -1; }
+    double c1[3], c2[3];
+    for (int k = 0; k < 3; ++k) { c1[k] = p1[k] + a1[k] * x1; c2[k] = p2[k] + a2[k] * x2; }
+    return sphere_sphere(c1, s1[0], c2, s2[0], margin, out);
+  }
+  /* parallel axes: contacts at both ends of the projected overlap */
+  int nc = 0;
+  double x1, x2, c1[3], c2[3];
+  for (int e = -1; e <= 1; e += 2) {
+    x1 = e;                               /* end of capsule 1 projected on capsule 2 */
+    x2 = (v - mb * x1) / mc;
+    if (x2 > 1) x2 = 1; else if (x2 < -1) x2 = -1;
+    x1 = (u - mb * x2) / ma;
+    if (x1 > 1) x1 = 1; else if (x1 < -1) x1 = -1;
+    for (int k = 0; k < 3; ++k) { c1[k] = p1[k] + a1[k] * x1; c2[k] = p2[k] + a2[k] * x2; }
+    nc += sphere_sphere(c1, s1[0], c2, s2[0], margin, out + nc);
+  }
+  if (nc == 2) { /* identical points: keep one */
+    double dd[3];
+    sub3(dd, out[0].pos, out[1].pos);
+    if (dot3(dd, dd) < 1e-20) nc = 1;
+  }
+  return nc;
+}
+
 static int g_round_poses = 0;
 void mje_debug_round_poses(int on) { g_round_poses = on; }
 
@@ -493,7 +568,9 @@ void mje_collision(const mjModelF *m, mjDataF *d) {
       if (t1 == GEOM_BOX && t2 == GEOM_BOX) g_flops += 700;
       if (t1 == GEOM_PLANE) {
         if (t2 == GEOM_PLANE) continue;
-        n = plane_convex(m, d, ga, gb, margin, rc);
+        n = t2 == GEOM_CAPSULE ? plane_capsule(m, d, ga, gb, margin, rc) : plane_convex(m, d, ga, gb, margin, rc);
+      } else if (t1 == GEOM_CAPSULE && t2 == GEOM_CAPSULE) {
+        n = capsule_capsule(m, d, ga, gb, margin, rc);
       } else if (t1 == GEOM_BOX && t2 == GEOM_BOX) {
         n = box_box(d->geom_xpos[ga], d->geom_xmat[ga], m->geom_size + 3 * ga, d->geom_xpos[gb], d->geom_xmat[gb],
                     m->geom_size + 3 * gb, margin, rc);
@@ -542,6 +619,48 @@ int mje_contact_rows(const mjModelF *m, mjDataF *d, int row) {
   int nv = m->nv;
   for (int c = 0; c < d->ncon; ++c) {
     int dim = d->con_dim[c], g1 = d->con_geom1[c], g2 = d->con_geom2[c];
+    if (!m->cone_elliptic) {
+      /* pyramidal cone (mj_instantiateContact): 2 (dim - 1) rows J_n +- mu_k J_k, every one a unilateral row with the
+       * contact distance as residual; frictionless contacts keep the single normal row.
+       * R (mj_makeImpedance, pyramidal): R_py = 2 mu_1^2 R_n / impratio with R_n from the translational weights. */
+      int nrow = dim > 1 ? 2 * (dim - 1) : 1;
+      if (row + nrow > MJ_MAXEFC) break;
+      d->flops += (long long)nv * (30 + 6 * nrow);
+      mje_body_jac(m, d, m->geom_body[g1], d->con_pos[c], jp1, jr1);
+      mje_body_jac(m, d, m->geom_body[g2], d->con_pos[c], jp2, jr2);
+      const double *fr = d->con_frame[c], *f = d->con_friction[c];
+      double jn[MJ_MAXV], jk[MJ_MAXV];
+      for (int q = 0; q < nv; ++q) {
+        double sn = 0;
+        for (int a = 0; a < 3; ++a) sn += fr[a] * (jp2[a][q] - jp1[a][q]);
+        jn[q] = sn;
+      }
+      double tran = m->geom_invweight0[2 * g1] + m->geom_invweight0[2 * g2];
+      for (int e = 0; e < nrow; ++e) {
+        int k = 1 + e / 2;                /* friction dimension of this edge */
+        double sgn = (e & 1) ? -1.0 : 1.0, mu = dim > 1 ? f[k - 1] : 0.0;
+        if (dim > 1) {
+          const double *ax = k < 3 ? fr + 3 * k : fr + 3 * (k - 3);
+          for (int q = 0; q < nv; ++q) {
+            double sk = 0;
+            if (k < 3) for (int a = 0; a < 3; ++a) sk += ax[a] * (jp2[a][q] - jp1[a][q]);
+            else for (int a = 0; a < 3; ++a) sk += ax[a] * (jr2[a][q] - jr1[a][q]);
+            jk[q] = sk;
+          }
+        }
+        for (int q = 0; q < nv; ++q) d->efc_J[row + e][q] = jn[q] + (dim > 1 ? sgn * mu * jk[q] : 0.0);
+        d->efc_pos[row + e] = d->con_dist[c];
+        d->efc_type[row + e] = 1;
+        d->efc_dim[row + e] = 1;
+        mje_finish_row(m, d, row + e, d->con_solref[c], d->con_solimp[c], d->con_margin[c], tran);
+        if (dim > 1) {
+          d->efc_R[row + e] = fmax(MINVAL, 2 * f[0] * f[0] * d->efc_R[row + e] / fmax(MINVAL, m->impratio));
+          d->efc_D[row + e] = 1 / d->efc_R[row + e];
+        }
+      }
+      row += nrow;
+      continue;
+    }
     if (row + dim > MJ_MAXEFC) break;
     d->flops += (long long)nv * (30 + 6 * dim);
     mje_body_jac(m, d, m->geom_body[g1], d->con_pos[c], jp1, jr1);

@@ -87,7 +87,8 @@ mjModelF *mje_load(const void *blob, long long nbytes) {
   m->blob = malloc((size_t)nbytes);
   memcpy(m->blob, blob, (size_t)nbytes);
   Rd r = {(const unsigned char *)m->blob, (const unsigned char *)m->blob + nbytes};
-  if (((const int *)r.p)[0] != 0x4C444D45 || ((const int *)r.p)[1] != 1) { free(m->blob); free(m); return 0; }
+  m->version = ((const int *)r.p)[1];
+  if (((const int *)r.p)[0] != 0x4C444D45 || (m->version != 1 && m->version != 2)) { free(m->blob); free(m); return 0; }
   r.p += 8;
   RI(nbody); RI(nq); RI(nv); RI(ngeom); RI(nsite); RI(nu); RI(nweld); RI(nhullvert); RI(iterations); RI(cone_elliptic);
   RD(timestep); RD(tolerance); RD(impratio); PD(gravity);
@@ -103,6 +104,10 @@ mjModelF *mje_load(const void *blob, long long nbytes) {
   PI(act_dof); PI(act_qposadr); PD(act_kp); PD(act_ctrlrange); PI(act_ctrllimited); PD(act_forcerange); PI(act_forcelimited);
   PI(weld_body); PD(weld_pos); PD(weld_quat); PD(weld_relpose); PD(weld_solref); PD(weld_solimp); PD(weld_invweight);
   PD(mocap_pos0); PD(mocap_quat0);
+  if (m->version == 2) {
+    RI(neq); PI(eq_qposadr); PI(eq_dofadr); PD(eq_polycoef); PD(eq_solref); PD(eq_solimp); PD(eq_invweight);
+    PD(dof_solref_friction); PD(dof_solimp_friction);
+  }
   if (r.p != r.end || m->nbody > MJ_MAXB || m->nv > MJ_MAXV || m->nq > MJ_MAXQ || m->ngeom > MJ_MAXG || m->nsite > MJ_MAXS) {
     free(m->blob); free(m); return 0;
   }
@@ -460,6 +465,36 @@ void mje_make_constraints(const mjModelF *m, mjDataF *d) {
     mje_imp_pos = -1;
     r += 6;
   }
+  /* --- equality: joint1 - ref1 = poly(joint2 - ref2), mj_instantiateEquality, mjEQ_JOINT */
+  for (int e = 0; e < m->neq; ++e) {
+    int q1 = m->eq_qposadr[2 * e], q2 = m->eq_qposadr[2 * e + 1], d1 = m->eq_dofadr[2 * e], d2 = m->eq_dofadr[2 * e + 1];
+    const double *c = m->eq_polycoef + 5 * e;
+    double dif = d->qpos[q2] - m->qpos0[q2], pw = 1, cpos = d->qpos[q1] - m->qpos0[q1], deriv = 0;
+    for (int k = 0; k < 5; ++k) {
+      cpos -= c[k] * pw;
+      if (k < 4) deriv += (k + 1) * c[k + 1] * pw;
+      pw *= dif;
+    }
+    memset(d->efc_J[r], 0, sizeof(double) * nv);
+    d->efc_J[r][d1] = 1;
+    d->efc_J[r][d2] = -deriv;
+    d->efc_pos[r] = cpos;
+    d->efc_type[r] = 0;
+    mje_finish_row(m, d, r, m->eq_solref + 2 * e, m->eq_solimp + 5 * e, 0.0, m->eq_invweight[e]);
+    ++r;
+  }
+  /* --- dof friction loss, mj_instantiateFriction: one row per dof with frictionloss > 0, residual 0 */
+  if (m->version == 2)
+    for (int i = 0; i < nv; ++i) {
+      if (!(m->dof_frictionloss[i] > 0)) continue;
+      memset(d->efc_J[r], 0, sizeof(double) * nv);
+      d->efc_J[r][i] = 1;
+      d->efc_pos[r] = 0;
+      d->efc_type[r] = 4;
+      d->efc_floss[r] = m->dof_frictionloss[i];
+      mje_finish_row(m, d, r, m->dof_solref_friction + 2 * i, m->dof_solimp_friction + 5 * i, 0.0, m->dof_invweight0[i]);
+      ++r;
+    }
   /* --- joint limits (hinge / slide), mj_instantiateLimit */
   for (int b = 1; b < m->nbody; ++b) {
     int j = m->body_jnt[b];
@@ -632,6 +667,12 @@ static double row_cost_update(const mjModelF *m, mjDataF *d, const double *jar, 
     } else if (d->efc_type[r] == 1) {
       if (jar[r] < 0) { force[r] = -d->efc_D[r] * jar[r]; active[r] = 1; cost += 0.5 * d->efc_D[r] * jar[r] * jar[r]; }
       else { force[r] = 0; active[r] = 0; }
+    } else if (d->efc_type[r] == 4) {
+      /* friction loss (PrimalUpdateConstraint, mjCNSTR_FRICTION_*): quadratic inside |jar| < R f, linear outside */
+      double f = d->efc_floss[r], rf = d->efc_R[r] * f;
+      if (jar[r] <= -rf) { force[r] = f; active[r] = 0; cost += -0.5 * rf * f - f * jar[r]; }
+      else if (jar[r] >= rf) { force[r] = -f; active[r] = 0; cost += -0.5 * rf * f + f * jar[r]; }
+      else { force[r] = -d->efc_D[r] * jar[r]; active[r] = 1; cost += 0.5 * d->efc_D[r] * jar[r] * jar[r]; }
     } else {
       /* elliptic cone (MuJoCo engine_solver.c: PrimalUpdateConstraint / HessianCone).  Scaled variables:
        * U0 = jar0 * mu, Uj = jar_j * fri_j;  N = U0, T = |U_1..| */

@@ -45,6 +45,10 @@ typedef struct {
   const int *weld_body;
   const double *weld_pos, *weld_quat, *weld_relpose, *weld_solref, *weld_solimp, *weld_invweight;
   const double *mocap_pos0, *mocap_quat0;
+  /* blob version 2 (models with joint equalities / friction loss: the kitchen); neq = 0 and defaults otherwise */
+  int version, neq;
+  const int *eq_qposadr, *eq_dofadr;
+  const double *eq_polycoef, *eq_solref, *eq_solimp, *eq_invweight, *dof_solref_friction, *dof_solimp_friction;
   void *blob; /* owned copy of the serialized model */
 } mjModelF;
 
@@ -66,7 +70,9 @@ typedef struct {
   int nefc, ncon;
   double efc_J[MJ_MAXEFC][MJ_MAXV], efc_pos[MJ_MAXEFC], efc_aref[MJ_MAXEFC], efc_R[MJ_MAXEFC], efc_D[MJ_MAXEFC],
       efc_force[MJ_MAXEFC];
-  int efc_type[MJ_MAXEFC];   /* 0 equality, 1 limit/frictionless, 2 elliptic normal row (followed by dim-1 friction rows) */
+  int efc_type[MJ_MAXEFC];   /* 0 equality, 1 limit / frictionless / pyramid edge (force >= 0), 2 elliptic normal row (followed by
+                                dim-1 friction rows of type 3), 4 dof friction loss (|force| <= efc_floss) */
+  double efc_floss[MJ_MAXEFC];
   int efc_dim[MJ_MAXEFC];    /* for type 2: contact dimension */
   double efc_mu[MJ_MAXEFC];  /* for type 2: regularised friction coefficient */
   double efc_fri[MJ_MAXEFC][5];

@@ -34,9 +34,20 @@ def sawyer_peg():
                            keep_sites=("rightEndEffector", "leftEndEffector", "pegHead", "pegGrasp"))
 
 
+def kitchen():
+    """Franka kitchen (ENV/kitchen.py -> adept_envs KitchenV0.MODEl).  The weld keeps MuJoCo's documented regulariser
+    (the 3.35 calibration of the Sawyer welds comes from metaworld demonstrations and does not transfer) and the
+    compiler's default relative pose (kitchen never calls reset_mocap_welds)."""
+    spec = parser.load(os.path.join(REF, "earl_benchmark/envs/kitchen_assets/adept_envs/adept_envs/franka/assets",
+                                    "franka_kitchen_jntpos_act_ab.xml"))
+    return C.compile_model(spec, weld_tran_scale=1.0, weld_relpose="qpos0",
+                           keep_sites=("microhandle_site", "hinge_site2", "slide_site", "knob1_site", "knob2_site", "knob3_site",
+                                       "knob4_site", "light_site", "end_effector"))
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    for name, fn in (("sawyer_door", sawyer_door), ("sawyer_peg", sawyer_peg)):
+    for name, fn in (("sawyer_door", sawyer_door), ("sawyer_peg", sawyer_peg), ("kitchen", kitchen)):
         m = fn()
         m.save(os.path.join(OUT, name + ".npz"))
         print(name, ": bodies", int(m.nbody), "nq", int(m.nq), "nv", int(m.nv), "geoms", int(m.ngeom), "sites", int(m.nsite),
