@@ -18,7 +18,7 @@
 namespace earl {
 namespace mj {
 
-constexpr int GEOM_PLANE = 0, GEOM_CYLINDER = 5, GEOM_BOX = 6, GEOM_MESH = 7;
+constexpr int GEOM_PLANE = 0, GEOM_CAPSULE = 3, GEOM_CYLINDER = 5, GEOM_BOX = 6, GEOM_MESH = 7;
 // Portal refinement runs in fp64 (`mreal`) on fp32 poses: its termination tests (libccd: |x| < eps, portal tolerance 1e-6)
 // cannot be resolved in fp32, where the refinement stops at a different portal and contact normals of thin-box-vs-
 // cylinder pairs came out up to 30 degrees away from the fp64 result; rounding the INPUTS to fp32 changes nothing
@@ -263,6 +263,10 @@ MJ_HD void support_geom(const CObj& o, const mreal* dir, mreal* res, int lane) {
     const mreal t = sqrt(dl[0] * dl[0] + dl[1] * dl[1]);
     if (t > 1e-15) { loc[0] = dl[0] / t * sz[0]; loc[1] = dl[1] / t * sz[0]; }
     loc[2] = dl[2] >= 0 ? (mreal)sz[1] : -(mreal)sz[1];
+  } else if (o.type == GEOM_CAPSULE) {  // segment along local z (half length size[1]) inflated by the radius size[0]
+    const mreal t = sqrt(dl[0] * dl[0] + dl[1] * dl[1] + dl[2] * dl[2]);
+    if (t > 1e-15) for (int k = 0; k < 3; ++k) loc[k] = dl[k] / t * sz[0];
+    loc[2] += dl[2] >= 0 ? (mreal)sz[1] : -(mreal)sz[1];
   } else if (o.type == GEOM_MESH) {
     // lane-parallel argmax over the hull vertices; the first vertex reaching the maximum wins
     const real* hv = o.hv;
@@ -502,6 +506,64 @@ MJ_FN int plane_convex(const Model& m, const real* hull, Work& w, int gp, int g,
 }
 
 // squared distance from point c to the box (centre p, axes R columns, half sizes s)
+// mjc_PlaneCapsule: one contact per end sphere
+MJ_FN int plane_capsule(const real* pp, const real* Rp, const real* pc, const real* Rc, const real* sz, real margin, RawCon* out) {
+  const real n[3] = {Rp[2], Rp[5], Rp[8]}, ax[3] = {Rc[2], Rc[5], Rc[8]};
+  int nc = 0;
+  for (int e = -1; e <= 1; e += 2) {
+    real c[3], rel[3];
+    for (int k = 0; k < 3; ++k) c[k] = pc[k] + e * sz[1] * ax[k];
+    sub3(rel, c, pp);
+    const real dist = dot3(rel, n) - sz[0];
+    if (dist >= margin) continue;
+    for (int k = 0; k < 3; ++k) { out[nc].pos[k] = c[k] - n[k] * (sz[0] + 0.5f * dist); out[nc].normal[k] = n[k]; }
+    out[nc].dist = dist;
+    ++nc;
+  }
+  return nc;
+}
+MJ_HD int sphere_sphere(const real* c1, real r1, const real* c2, real r2, real margin, RawCon* out) {
+  real n[3];
+  sub3(n, c2, c1);
+  const real len = msqrt(dot3(n, n)), dist = len - r1 - r2;
+  if (dist >= margin) return 0;
+  if (len < MINVAL) { n[0] = 1; n[1] = n[2] = 0; } else { for (int k = 0; k < 3; ++k) n[k] /= len; }
+  for (int k = 0; k < 3; ++k) { out->pos[k] = c1[k] + n[k] * (r1 + 0.5f * dist); out->normal[k] = n[k]; }
+  out->dist = dist;
+  return 1;
+}
+// mjc_CapsuleCapsule: closest points of the two axis segments; parallel axes give the two ends of the overlap
+MJ_FN int capsule_capsule(const real* p1, const real* R1, const real* s1, const real* p2, const real* R2, const real* s2, real margin,
+                          RawCon* out) {
+  const real a1[3] = {R1[2] * s1[1], R1[5] * s1[1], R1[8] * s1[1]}, a2[3] = {R2[2] * s2[1], R2[5] * s2[1], R2[8] * s2[1]};
+  real dif[3], c1[3], c2[3];
+  sub3(dif, p1, p2);
+  const real ma = dot3(a1, a1), mb = -dot3(a1, a2), mc = dot3(a2, a2), u = -dot3(a1, dif), v = dot3(a2, dif);
+  const real det = ma * mc - mb * mb;
+  if (mabs(det) >= 1e-9f * ma * mc) {  // general configuration (fp32: relative test for parallelism)
+    real x1 = (mc * u - mb * v) / det, x2 = (ma * v - mb * u) / det;
+    if (x1 > 1) { x1 = 1; x2 = (v - mb) / mc; } else if (x1 < -1) { x1 = -1; x2 = (v + mb) / mc; }
+    if (x2 > 1) { x2 = 1; x1 = clampr((u - mb) / ma, -1.0f, 1.0f); }
+    else if (x2 < -1) { x2 = -1; x1 = clampr((u + mb) / ma, -1.0f, 1.0f); }
+    for (int k = 0; k < 3; ++k) { c1[k] = p1[k] + a1[k] * x1; c2[k] = p2[k] + a2[k] * x2; }
+    return sphere_sphere(c1, s1[0], c2, s2[0], margin, out);
+  }
+  int nc = 0;
+  for (int e = -1; e <= 1; e += 2) {
+    real x1 = (real)e;
+    const real x2 = clampr((v - mb * x1) / mc, -1.0f, 1.0f);
+    x1 = clampr((u - mb * x2) / ma, -1.0f, 1.0f);
+    for (int k = 0; k < 3; ++k) { c1[k] = p1[k] + a1[k] * x1; c2[k] = p2[k] + a2[k] * x2; }
+    nc += sphere_sphere(c1, s1[0], c2, s2[0], margin, out + nc);
+  }
+  if (nc == 2) {
+    real dd[3];
+    sub3(dd, out[0].pos, out[1].pos);
+    if (dot3(dd, dd) < 1e-12f) nc = 1;
+  }
+  return nc;
+}
+
 MJ_HD real point_box_dist2(const real* c, const real* p, const real* R, const real* s) {
   real rel[3], d2 = 0;
   sub3(rel, c, p);
@@ -553,7 +615,7 @@ MJ_FN void compact_append(Work& w, int item, int flag, int lane) {
     const unsigned mask = __ballot_sync(0xffffffffu, flag);
     const int base = w.nhit;
     const int pos = base + __popc(mask & ((1u << lane) - 1u));
-    if (flag && pos < MAXHIT) w.hit_list[pos] = (unsigned char)item;
+    if (flag && pos < MAXHIT) w.hit_list[pos] = (unsigned short)item;
     __syncwarp();
     if (lane == 0) { const int n = base + __popc(mask); w.nhit = n < MAXHIT ? n : MAXHIT; if (n > MAXHIT) w.bad |= 2; }
     __syncwarp();
@@ -561,7 +623,7 @@ MJ_FN void compact_append(Work& w, int item, int flag, int lane) {
   }
 #endif
   if (flag) {
-    if (w.nhit < MAXHIT) w.hit_list[w.nhit++] = (unsigned char)item;
+    if (w.nhit < MAXHIT) w.hit_list[w.nhit++] = (unsigned short)item;
     else w.bad |= 2;  // capacity overflow: a candidate pair was dropped
   }
 }
@@ -624,7 +686,10 @@ MJ_FN void collide(const Model& m, const real* hull, Work& w, int lane) {
     RawCon* rc = S->rc;
     int n = 0;
     if (t1 == GEOM_PLANE) {
-      n = plane_convex<NL>(m, hull, w, ga, gb, margin, rc, lane);
+      n = t2 == GEOM_CAPSULE ? plane_capsule(gpos(m, w, ga), gmat(m, w, ga), gpos(m, w, gb), gmat(m, w, gb), m.geom_size[gb], margin, rc)
+                             : plane_convex<NL>(m, hull, w, ga, gb, margin, rc, lane);
+    } else if (t1 == GEOM_CAPSULE && t2 == GEOM_CAPSULE) {
+      n = capsule_capsule(gpos(m, w, ga), gmat(m, w, ga), m.geom_size[ga], gpos(m, w, gb), gmat(m, w, gb), m.geom_size[gb], margin, rc);
     } else if (t1 == GEOM_BOX && t2 == GEOM_BOX) {
       n = box_box(gpos(m, w, ga), gmat(m, w, ga), m.geom_size[ga], gpos(m, w, gb), gmat(m, w, gb), m.geom_size[gb], margin, rc, S);
     } else {
@@ -681,12 +746,62 @@ MJ_FN void contact_rows(const Model& m, Work& w, int lane) {
   for (int c = 0; c < w.ncon; ++c) {
     const int g1 = w.con_g1[c], g2 = w.con_g2[c];
     const int dim = m.geom_condim[g1] > m.geom_condim[g2] ? m.geom_condim[g1] : m.geom_condim[g2];
-    if (row + dim > MAXEFC) { if (lane == 0) w.bad |= 8; break; }
-    if (lane == 0) { w.con_row[c] = row; w.con_dim[c] = dim; }
-    row += dim;
+    // elliptic: dim rows (con_dim = dim); pyramidal: 2 (dim - 1) unilateral rows, or 1 when frictionless (con_dim = -rows)
+    const int nrow = m.cone_elliptic ? dim : (dim > 1 ? 2 * (dim - 1) : 1);
+    if (row + nrow > MAXEFC) { if (lane == 0) w.bad |= 8; break; }
+    if (lane == 0) { w.con_row[c] = row; w.con_dim[c] = m.cone_elliptic ? dim : -nrow; }
+    row += nrow;
     ++used;
   }
   wsync<NL>();
+  if (!m.cone_elliptic) {
+    // pyramidal cone (mj_instantiateContact): edge e of friction dimension k = 1 + e / 2 has the row J_n +- mu_k J_k, the
+    // contact distance as residual and R_py = 2 mu_1^2 R_n / impratio (mj_makeImpedance, pyramidal)
+    for (int idx = lane; idx < used * nv; idx += NL) {
+      const int c = idx / nv, q = idx - c * nv;
+      const int g1 = w.con_g1[c], g2 = w.con_g2[c], r = w.con_row[c], nrow = -w.con_dim[c];
+      const int dim = nrow > 1 ? nrow / 2 + 1 : 1;
+      const real* fr = w.con_frame[c];
+      real jp1[3], jr1[3], jp2[3], jr2[3];
+      jac_col(m, w, m.geom_body[g1], w.con_pos[c], q, jp1, jr1);
+      jac_col(m, w, m.geom_body[g2], w.con_pos[c], q, jp2, jr2);
+      const real dp[3] = {jp2[0] - jp1[0], jp2[1] - jp1[1], jp2[2] - jp1[2]}, dr[3] = {jr2[0] - jr1[0], jr2[1] - jr1[1], jr2[2] - jr1[2]};
+      const real jn = dot3(fr, dp);
+      if (dim == 1) { w.J[r][q] = jn; continue; }
+      real f[3];
+      for (int a = 0; a < 3; ++a) f[a] = fmaxf(m.geom_friction[g1][a], m.geom_friction[g2][a]);
+      const real fri[5] = {f[0], f[0], f[1], f[2], f[2]};
+      for (int k = 1; k < dim; ++k) {
+        const real jk = k < 3 ? dot3(fr + 3 * k, dp) : dot3(fr + 3 * (k - 3), dr);
+        w.J[r + 2 * (k - 1)][q] = jn + fri[k - 1] * jk;
+        w.J[r + 2 * (k - 1) + 1][q] = jn - fri[k - 1] * jk;
+      }
+    }
+    wsync<NL>();
+    for (int c = lane; c < used; c += NL) {
+      const int g1 = w.con_g1[c], g2 = w.con_g2[c], r = w.con_row[c], nrow = -w.con_dim[c];
+      const real margin = fmaxf(m.geom_margin[g1], m.geom_margin[g2]), gap = fmaxf(m.geom_gap[g1], m.geom_gap[g2]);
+      const real mix = m.geom_solmix[g1] / (m.geom_solmix[g1] + m.geom_solmix[g2]);
+      real solref[2], solimp[5];
+      for (int q = 0; q < 2; ++q) solref[q] = mix * m.geom_solref[g1][q] + (1 - mix) * m.geom_solref[g2][q];
+      for (int q = 0; q < 5; ++q) solimp[q] = mix * m.geom_solimp[g1][q] + (1 - mix) * m.geom_solimp[g2][q];
+      const real mu1 = fmaxf(m.geom_friction[g1][0], m.geom_friction[g2][0]);
+      const real tran = m.geom_invweight0[g1][0] + m.geom_invweight0[g2][0];
+      for (int e = 0; e < nrow; ++e) {
+        w.e_pos[r + e] = w.con_dist[c];
+        w.e_type[r + e] = ROW_LIMIT;
+        finish_row(m, w, r + e, solref, solimp, margin - gap, tran, nullptr);
+        if (nrow > 1) {
+          w.e_R[r + e] = fmaxf(MINVAL, 2 * mu1 * mu1 * w.e_R[r + e] / fmaxf(MINVAL, m.impratio));
+          w.e_D[r + e] = 1.0f / w.e_R[r + e];
+        }
+      }
+    }
+    wsync<NL>();
+    if (lane == 0) { w.nefc = row; w.ncon = used; }
+    wsync<NL>();
+    return;
+  }
   // Jacobian entries: one (contact, dof) pair per lane
   for (int idx = lane; idx < used * nv; idx += NL) {
     const int c = idx / nv, q = idx - c * nv;

@@ -37,16 +37,36 @@ namespace mj {
 
 typedef float real;
 
+#if defined(MJ_CAPSET_KITCHEN)
+// Third capacity set: the Franka kitchen (23 dofs, 118 colliding geoms, friction loss on every dof, pyramidal cones).
+// So far instantiated by the host build of this source only (tests/host_emulation); the device instantiation is the
+// next step.
+constexpr int MAXB = 24;    // fused bodies incl. world
+constexpr int MAXV = 24;    // dofs
+constexpr int MAXQ = 24;    // generalized coordinates
+constexpr int MAXJ = 24;    // joints
+constexpr int MAXG = 128;   // geoms kept on the device
+constexpr int MAXS = 12;    // sites kept on the device
+#else
 constexpr int MAXB = 12;    // fused bodies incl. world
 constexpr int MAXV = 16;    // dofs
 constexpr int MAXQ = 20;    // generalized coordinates
 constexpr int MAXJ = 12;    // joints
 constexpr int MAXG = 32;    // geoms kept on the device
 constexpr int MAXS = 8;     // sites kept on the device
+#endif
 constexpr int MAXU = 2;     // actuators
 constexpr int MAXW = 1;     // welds
+constexpr int MAXEQ = 8;    // joint equalities
 // Two capacity sets are compiled from these sources (earl_mj_small.cu / earl_mj_large.cu): the workspace of one
 // environment lives in shared memory, so rows x dofs and contacts decide how many environments one SM keeps in flight.
+#if defined(MJ_CAPSET_KITCHEN)
+constexpr int MAXEFC = 320; // constraint rows (6 weld + 5 equality + 23 friction loss + limits + 4 / 10 per pyramidal contact)
+constexpr int MAXCON = 24;  // contacts
+constexpr int MAXHIT = 64;  // candidate pairs that survive the broad phase in one substep
+constexpr int MAXPAIR = 4096; // candidate geom pairs
+constexpr int MAXMG = 96;    // geoms on moving bodies (their world poses are recomputed every substep)
+#else
 #if defined(MJ_CAPSET_LARGE)
 constexpr int MAXEFC = 96;  // constraint rows
 constexpr int MAXCON = 24;  // contacts
@@ -58,6 +78,7 @@ constexpr int MAXHIT = 24;
 #endif
 constexpr int MAXPAIR = 192; // candidate geom pairs
 constexpr int MAXMG = 16;    // geoms on moving bodies (their world poses are recomputed every substep)
+#endif
 constexpr int LDM = MAXV + 1;  // padded leading dimension of the dense nv x nv matrices
 
 constexpr real MINVAL = 1e-15f;
@@ -65,7 +86,9 @@ constexpr real MINIMP = 0.0001f;
 constexpr real MAXIMP = 0.9999f;
 
 // constraint row types
-enum { ROW_EQ = 0, ROW_LIMIT = 1, ROW_CONE = 2, ROW_CONE_FRIC = 3 };
+// ROW_FRICTION: dof friction loss, |force| <= e_pos[r] (the row's residual is 0, so e_pos carries the bound after finish_row)
+enum { ROW_EQ = 0, ROW_LIMIT = 1, ROW_CONE = 2, ROW_CONE_FRIC = 3, ROW_FRICTION = 4 };
+MJ_HD bool is_cone_row(int tp) { return tp == ROW_CONE || tp == ROW_CONE_FRIC; }
 
 // ------------------------------------------------------------------------------------------------ device model
 // Built on the host from the serialized structure-of-arrays model (mjcf/compile.py: Model.FIELDS); plain floats.
@@ -85,7 +108,12 @@ struct Model {
   // dofs
   int dof_body[MAXV], dof_rot[MAXV], dof_parent[MAXV];
   real dof_damping[MAXV], dof_armature[MAXV], dof_invweight0[MAXV];
+  real dof_frictionloss[MAXV], dof_solref_friction[MAXV][2], dof_solimp_friction[MAXV][5];
   real qpos0[MAXQ];
+  // joint equalities q1 - q1_0 = poly(q2 - q2_0) and the friction-cone type (blob version 2: kitchen)
+  int neq, cone_elliptic;
+  int eq_qposadr[MAXEQ][2], eq_dofadr[MAXEQ][2];
+  real eq_polycoef[MAXEQ][5], eq_solref[MAXEQ][2], eq_solimp[MAXEQ][5], eq_invweight[MAXEQ];
   // sites (observation frames)
   int site_body[MAXS];
   real site_pos[MAXS][3];
@@ -160,7 +188,7 @@ struct Work {
     real con_H[MAXCON][16];
   };
   int nhit;
-  unsigned char hit_list[MAXHIT];
+  unsigned short hit_list[MAXHIT];
   // contacts
   real con_pos[MAXCON][3], con_frame[MAXCON][9], con_dist[MAXCON], con_fri[MAXCON][5], con_mu[MAXCON];
   int con_g1[MAXCON], con_g2[MAXCON], con_dim[MAXCON], con_row[MAXCON];
@@ -720,6 +748,36 @@ MJ_FN void make_constraints(const Model& m, Work& w, int lane) {
       finish_row(m, w, r + k, m.weld_solref[wi], m.weld_solimp[wi], 0.0f, m.weld_invweight[wi][k >= 3], nullptr, cnorm);
     r += 6;
   }
+  // --- joint equalities q1 - q1_0 = poly(q2 - q2_0) (mj_instantiateEquality, mjEQ_JOINT)
+  for (int e = 0; e < m.neq; ++e) {
+    if (r >= MAXEFC) { if (lane == 0) w.bad |= 8; break; }
+    const int q1 = m.eq_qposadr[e][0], q2 = m.eq_qposadr[e][1], d1 = m.eq_dofadr[e][0], d2 = m.eq_dofadr[e][1];
+    const real dif = w.qpos[q2] - m.qpos0[q2];
+    real pw = 1, cpos = w.qpos[q1] - m.qpos0[q1], deriv = 0;
+    for (int k = 0; k < 5; ++k) {
+      cpos -= m.eq_polycoef[e][k] * pw;
+      if (k < 4) deriv += (k + 1) * m.eq_polycoef[e][k + 1] * pw;
+      pw *= dif;
+    }
+    for (int c = lane; c < nv; c += NL) w.J[r][c] = c == d1 ? 1.0f : (c == d2 ? -deriv : 0.0f);
+    if (lane == 0) { w.e_pos[r] = cpos; w.e_type[r] = ROW_EQ; }
+    wsync<NL>();
+    if (lane == 0) finish_row(m, w, r, m.eq_solref[e], m.eq_solimp[e], 0.0f, m.eq_invweight[e], nullptr);
+    ++r;
+  }
+  // --- dof friction loss (mj_instantiateFriction): one row per dof with frictionloss > 0, residual 0
+  for (int i = 0; i < nv; ++i) {
+    if (!(m.dof_frictionloss[i] > 0)) continue;
+    if (r >= MAXEFC) { if (lane == 0) w.bad |= 8; break; }
+    for (int c = lane; c < nv; c += NL) w.J[r][c] = c == i ? 1.0f : 0.0f;
+    if (lane == 0) { w.e_pos[r] = 0; w.e_type[r] = ROW_FRICTION; }
+    wsync<NL>();
+    if (lane == 0) {
+      finish_row(m, w, r, m.dof_solref_friction[i], m.dof_solimp_friction[i], 0.0f, m.dof_invweight0[i], nullptr);
+      w.e_pos[r] = m.dof_frictionloss[i];  // from here on e_pos of a friction row is its force bound
+    }
+    ++r;
+  }
   // --- joint limits (hinge / slide); row allocation is uniform across lanes
   for (int j = 0; j < m.njnt; ++j) {
     if (!m.jnt_limited[j] || m.jnt_type[j] < 2) continue;
@@ -750,6 +808,11 @@ MJ_HD void row_update(Work& w, int r) {
   else if (tp == ROW_LIMIT) {
     if (jar < 0) { w.e_force[r] = -D * jar; w.e_state[r] = 1; }
     else { w.e_force[r] = 0; w.e_state[r] = 0; }
+  } else if (tp == ROW_FRICTION) {  // quadratic inside |jar| < R f, linear (saturated force) outside; states 3 / 4 = saturated
+    const real f = w.e_pos[r], rf = w.e_R[r] * f;
+    if (jar <= -rf) { w.e_force[r] = f; w.e_state[r] = 3; }
+    else if (jar >= rf) { w.e_force[r] = -f; w.e_state[r] = 4; }
+    else { w.e_force[r] = -D * jar; w.e_state[r] = 1; }
   }
 }
 
@@ -831,12 +894,13 @@ MJ_FN int solver_update(const Model& m, Work& w, int lane) {
   }
   wsync<NL>();
   for (int r = lane; r < ne; r += NL)
-    if (w.e_type[r] < ROW_CONE) {
+    if (!is_cone_row(w.e_type[r])) {
       const int old = w.e_state[r];
       row_update(w, r);
       changed += (old != w.e_state[r]) ? 1.0f : 0.0f;
     }
   for (int c = lane; c < w.ncon; c += NL) {
+    if (w.con_dim[c] <= 0) continue;  // pyramidal contact: its rows are plain unilateral rows
     const int old = w.e_state[w.con_row[c]];
     cone_eval(w, c, 0, false, true, nullptr, nullptr, nullptr);
     changed += (old != w.e_state[w.con_row[c]] || old == 2) ? 1.0f : 0.0f;  // the cone zone is not quadratic
@@ -858,11 +922,17 @@ MJ_FN void line_eval(Work& w, real alpha, int lane, real* d1, real* d2) {
   real g = 0, h = 0;
   for (int r = lane; r < w.nefc; r += NL) {
     const int tp = w.e_type[r];
-    if (tp >= ROW_CONE) continue;
+    if (is_cone_row(tp)) continue;
     const real x = w.e_jar[r] + alpha * w.e_jv[r], D = w.e_D[r], jv = w.e_jv[r];
-    if (tp == ROW_EQ || x < 0) { g += D * x * jv; h += D * jv * jv; }
+    if (tp == ROW_FRICTION) {
+      const real f = w.e_pos[r], rf = w.e_R[r] * f;
+      if (x <= -rf) g -= f * jv;
+      else if (x >= rf) g += f * jv;
+      else { g += D * x * jv; h += D * jv * jv; }
+    } else if (tp == ROW_EQ || x < 0) { g += D * x * jv; h += D * jv * jv; }
   }
   for (int c = lane; c < w.ncon; c += NL) {
+    if (w.con_dim[c] <= 0) continue;
     real cg, ch;
     cone_eval(w, c, alpha, true, false, nullptr, &cg, &ch);
     g += cg; h += ch;
@@ -905,7 +975,7 @@ MJ_FN void solve(const Model& m, Work& w, int lane) {
         if (w.e_state[r] == 1) s += w.e_D[r] * w.J[r][i] * w.J[r][j];
       for (int c = 0; c < w.ncon; ++c) {
         const int r0 = w.con_row[c];
-        if (w.e_state[r0] != 2) continue;
+        if (w.con_dim[c] <= 0 || w.e_state[r0] != 2) continue;
         const int dim = w.con_dim[c];
         for (int a = 0; a < dim; ++a)
           for (int b = 0; b < dim; ++b) s += w.con_H[c][4 * a + b] * w.J[r0 + a][i] * w.J[r0 + b][j];
@@ -972,7 +1042,7 @@ MJ_FN void solve(const Model& m, Work& w, int lane) {
     // ~1 can still be 1e-3 of a large step away from the minimiser); otherwise stop once the step is at the fp32
     // noise floor of the largest acceleration
     int nmid = 0;
-    for (int c = 0; c < w.ncon; ++c) nmid += w.e_state[w.con_row[c]] == 2;
+    for (int c = 0; c < w.ncon; ++c) nmid += w.con_dim[c] > 0 && w.e_state[w.con_row[c]] == 2;
     const real floor_ = 1e-4f + 1e-5f * an;
     bool exact = nchg == 0 && nmid == 0 && fabsf(alpha - 1.0f) < 1e-3f;
     if (exact) {

@@ -43,8 +43,10 @@ class BlobReader {
     int32_t h[2];
     memcpy(h, p_, 8);
     p_ += 8;
-    return h[0] == 0x4C444D45 && h[1] == 1;
+    version = h[1];
+    return h[0] == 0x4C444D45 && (h[1] == 1 || h[1] == 2);
   }
+  int version = 0;  // 1: door / peg; 2: + joint equalities and friction-loss parameters (kitchen)
   // next field as doubles / ints; returns element count or -1
   template <typename T>
   long field(std::vector<T>* out, int elem) {
@@ -175,7 +177,10 @@ inline bool build_model(const void* blob, size_t nbytes, const TaskSpec& task, H
   RD(m.timestep);
   if (rd.field(&D, 8) != 1) return bad("tolerance");  // <option tolerance>: the fp32 solver uses its own termination rule
   RD(m.impratio);
-  if (!cone_elliptic) return bad("model blob: only elliptic friction cones are built");
+  m.cone_elliptic = cone_elliptic;
+#if !defined(MJ_CAPSET_KITCHEN)
+  if (!cone_elliptic) return bad("model blob: only elliptic friction cones are built in this capacity set");
+#endif
   if (m.nbody > MAXB || m.nv > MAXV || m.nq > MAXQ || m.ngeom > MAXG || m.nsite > MAXS || m.nu > MAXU || m.nweld > MAXW)
     return bad("model blob: model exceeds the engine's fixed sizes");
   const int nb = m.nbody, nv = m.nv, ng = m.ngeom, ns = m.nsite, nu = m.nu, nw = m.nweld;
@@ -209,8 +214,15 @@ inline bool build_model(const void* blob, size_t nbytes, const TaskSpec& task, H
   VI(nv, m.dof_body[k] = I[k]);
   VD(nv, m.dof_damping[k] = (real)D[k]);
   VD(nv, m.dof_armature[k] = (real)D[k]);
-  VD(nv, (void)D[k]);  // dof_frictionloss (zero in the Sawyer scenes; kitchen needs it)
-  for (int k = 0; k < nv; ++k) if (D[k] != 0.0) return bad("model blob: frictionloss is not built");
+  VD(nv, m.dof_frictionloss[k] = (real)D[k]);
+#if !defined(MJ_CAPSET_KITCHEN)
+  for (int k = 0; k < nv; ++k) if (D[k] != 0.0) return bad("model blob: frictionloss is not built in this capacity set");
+#endif
+  for (int k = 0; k < nv; ++k) {  // defaults (blob version 1 carries none)
+    m.dof_solref_friction[k][0] = 0.02f; m.dof_solref_friction[k][1] = 1.0f;
+    const real si[5] = {0.9f, 0.95f, 0.001f, 0.5f, 2.0f};
+    for (int q = 0; q < 5; ++q) m.dof_solimp_friction[k][q] = si[q];
+  }
   VD(nv, m.dof_invweight0[k] = (real)D[k]);
   VD(m.nq, m.qpos0[k] = (real)D[k]);
   VI(ng, m.geom_body[k] = I[k]);
@@ -264,6 +276,20 @@ inline bool build_model(const void* blob, size_t nbytes, const TaskSpec& task, H
   VD(nw * 2, m.weld_invweight[k / 2][k % 2] = (real)D[k]);
   VD(3, (void)D[k]);  // mocap_pos0
   VD(4, (void)D[k]);  // mocap_quat0
+  m.neq = 0;
+  if (rd.version == 2) {
+    RI(m.neq);
+    if (m.neq < 0 || m.neq > MAXEQ) return bad("model blob: too many joint equalities");
+    const int ne = m.neq;
+    VI(ne * 2, m.eq_qposadr[k / 2][k % 2] = I[k]);
+    VI(ne * 2, m.eq_dofadr[k / 2][k % 2] = I[k]);
+    VD(ne * 5, m.eq_polycoef[k / 5][k % 5] = (real)D[k]);
+    VD(ne * 2, m.eq_solref[k / 2][k % 2] = (real)D[k]);
+    VD(ne * 5, m.eq_solimp[k / 5][k % 5] = (real)D[k]);
+    VD(ne, m.eq_invweight[k] = (real)D[k]);
+    VD(nv * 2, m.dof_solref_friction[k / 2][k % 2] = (real)D[k]);
+    VD(nv * 5, m.dof_solimp_friction[k / 5][k % 5] = (real)D[k]);
+  }
 #undef RI
 #undef RD
 #undef VI
@@ -306,6 +332,7 @@ inline bool build_model(const void* blob, size_t nbytes, const TaskSpec& task, H
     off[0] = off[1] = off[2] = 0;
     if (m.geom_type[g] == GEOM_BOX) { for (int k = 0; k < 3; ++k) sz[k] = m.geom_size[g][k]; }
     else if (m.geom_type[g] == GEOM_CYLINDER) { sz[0] = sz[1] = m.geom_size[g][0]; sz[2] = m.geom_size[g][1]; }
+    else if (m.geom_type[g] == GEOM_CAPSULE) { sz[0] = sz[1] = m.geom_size[g][0]; sz[2] = m.geom_size[g][0] + m.geom_size[g][1]; }
     else if (m.geom_type[g] == GEOM_MESH && m.geom_hullnum[g] > 0) {
       real lo[3] = {1e30f, 1e30f, 1e30f}, hi[3] = {-1e30f, -1e30f, -1e30f};
       for (int v = 0; v < m.geom_hullnum[g]; ++v)
@@ -338,7 +365,8 @@ inline bool build_model(const void* blob, size_t nbytes, const TaskSpec& task, H
       if (b1 != 0 && b2 != 0 && (m.body_parent[b1] == b2 || m.body_parent[b2] == b1)) continue;
       if (np >= MAXPAIR) return bad("too many candidate collision pairs");
       const int cd = m.geom_condim[g1] > m.geom_condim[g2] ? m.geom_condim[g1] : m.geom_condim[g2];
-      if (cd != 3 && cd != 4) return bad("only contact dimensions 3 and 4 are built");
+      if (cone_elliptic ? (cd != 3 && cd != 4) : (cd != 1 && cd != 3 && cd != 4 && cd != 6))
+        return bad("contact dimension not built (elliptic: 3, 4; pyramidal: 1, 3, 4, 6)");
       if (never_touch(m, g1, g2) || never_touch(m, g2, g1)) continue;
       const bool swap = m.geom_type[g1] > m.geom_type[g2];  // MuJoCo orders a pair by geom type
       m.pair_g1[np] = swap ? g2 : g1;
