@@ -263,7 +263,7 @@ MJ_HD void support_geom(const CObj& o, const mreal* dir, mreal* res, int lane) {
     const mreal t = sqrt(dl[0] * dl[0] + dl[1] * dl[1]);
     if (t > 1e-15) { loc[0] = dl[0] / t * sz[0]; loc[1] = dl[1] / t * sz[0]; }
     loc[2] = dl[2] >= 0 ? (mreal)sz[1] : -(mreal)sz[1];
-  } else if (o.type == GEOM_CAPSULE) {  // segment along local z (half length size[1]) inflated by the radius size[0]
+  } else if (KITCHEN_ROWS && o.type == GEOM_CAPSULE) {  // segment along local z (half length size[1]) inflated by the radius size[0]
     const mreal t = sqrt(dl[0] * dl[0] + dl[1] * dl[1] + dl[2] * dl[2]);
     if (t > 1e-15) for (int k = 0; k < 3; ++k) loc[k] = dl[k] / t * sz[0];
     loc[2] += dl[2] >= 0 ? (mreal)sz[1] : -(mreal)sz[1];
@@ -686,9 +686,9 @@ MJ_FN void collide(const Model& m, const real* hull, Work& w, int lane) {
     RawCon* rc = S->rc;
     int n = 0;
     if (t1 == GEOM_PLANE) {
-      n = t2 == GEOM_CAPSULE ? plane_capsule(gpos(m, w, ga), gmat(m, w, ga), gpos(m, w, gb), gmat(m, w, gb), m.geom_size[gb], margin, rc)
+      n = KITCHEN_ROWS && t2 == GEOM_CAPSULE ? plane_capsule(gpos(m, w, ga), gmat(m, w, ga), gpos(m, w, gb), gmat(m, w, gb), m.geom_size[gb], margin, rc)
                              : plane_convex<NL>(m, hull, w, ga, gb, margin, rc, lane);
-    } else if (t1 == GEOM_CAPSULE && t2 == GEOM_CAPSULE) {
+    } else if (KITCHEN_ROWS && t1 == GEOM_CAPSULE && t2 == GEOM_CAPSULE) {
       n = capsule_capsule(gpos(m, w, ga), gmat(m, w, ga), m.geom_size[ga], gpos(m, w, gb), gmat(m, w, gb), m.geom_size[gb], margin, rc);
     } else if (t1 == GEOM_BOX && t2 == GEOM_BOX) {
       n = box_box(gpos(m, w, ga), gmat(m, w, ga), m.geom_size[ga], gpos(m, w, gb), gmat(m, w, gb), m.geom_size[gb], margin, rc, S);
@@ -747,14 +747,15 @@ MJ_FN void contact_rows(const Model& m, Work& w, int lane) {
     const int g1 = w.con_g1[c], g2 = w.con_g2[c];
     const int dim = m.geom_condim[g1] > m.geom_condim[g2] ? m.geom_condim[g1] : m.geom_condim[g2];
     // elliptic: dim rows (con_dim = dim); pyramidal: 2 (dim - 1) unilateral rows, or 1 when frictionless (con_dim = -rows)
-    const int nrow = m.cone_elliptic ? dim : (dim > 1 ? 2 * (dim - 1) : 1);
+    const bool elliptic = !KITCHEN_ROWS || m.cone_elliptic;
+    const int nrow = elliptic ? dim : (dim > 1 ? 2 * (dim - 1) : 1);
     if (row + nrow > MAXEFC) { if (lane == 0) w.bad |= 8; break; }
-    if (lane == 0) { w.con_row[c] = row; w.con_dim[c] = m.cone_elliptic ? dim : -nrow; }
+    if (lane == 0) { w.con_row[c] = row; w.con_dim[c] = elliptic ? dim : -nrow; }
     row += nrow;
     ++used;
   }
   wsync<NL>();
-  if (!m.cone_elliptic) {
+  if (KITCHEN_ROWS && !m.cone_elliptic) {
     // pyramidal cone (mj_instantiateContact): edge e of friction dimension k = 1 + e / 2 has the row J_n +- mu_k J_k, the
     // contact distance as residual and R_py = 2 mu_1^2 R_n / impratio (mj_makeImpedance, pyramidal)
     for (int idx = lane; idx < used * nv; idx += NL) {

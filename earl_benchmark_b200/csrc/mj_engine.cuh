@@ -58,6 +58,13 @@ constexpr int MAXS = 8;     // sites kept on the device
 constexpr int MAXU = 2;     // actuators
 constexpr int MAXW = 1;     // welds
 constexpr int MAXEQ = 8;    // joint equalities
+// joint-equality / friction-loss / pyramidal rows and capsule geoms only exist in the kitchen: the door / peg builds drop
+// those branches at compile time (they cost 3.5 % of the step when left in)
+#if defined(MJ_CAPSET_KITCHEN)
+constexpr bool KITCHEN_ROWS = true;
+#else
+constexpr bool KITCHEN_ROWS = false;
+#endif
 // Two capacity sets are compiled from these sources (earl_mj_small.cu / earl_mj_large.cu): the workspace of one
 // environment lives in shared memory, so rows x dofs and contacts decide how many environments one SM keeps in flight.
 #if defined(MJ_CAPSET_KITCHEN)
@@ -749,7 +756,7 @@ MJ_FN void make_constraints(const Model& m, Work& w, int lane) {
     r += 6;
   }
   // --- joint equalities q1 - q1_0 = poly(q2 - q2_0) (mj_instantiateEquality, mjEQ_JOINT)
-  for (int e = 0; e < m.neq; ++e) {
+  for (int e = 0; KITCHEN_ROWS && e < m.neq; ++e) {
     if (r >= MAXEFC) { if (lane == 0) w.bad |= 8; break; }
     const int q1 = m.eq_qposadr[e][0], q2 = m.eq_qposadr[e][1], d1 = m.eq_dofadr[e][0], d2 = m.eq_dofadr[e][1];
     const real dif = w.qpos[q2] - m.qpos0[q2];
@@ -766,7 +773,7 @@ MJ_FN void make_constraints(const Model& m, Work& w, int lane) {
     ++r;
   }
   // --- dof friction loss (mj_instantiateFriction): one row per dof with frictionloss > 0, residual 0
-  for (int i = 0; i < nv; ++i) {
+  for (int i = 0; KITCHEN_ROWS && i < nv; ++i) {
     if (!(m.dof_frictionloss[i] > 0)) continue;
     if (r >= MAXEFC) { if (lane == 0) w.bad |= 8; break; }
     for (int c = lane; c < nv; c += NL) w.J[r][c] = c == i ? 1.0f : 0.0f;
@@ -808,7 +815,7 @@ MJ_HD void row_update(Work& w, int r) {
   else if (tp == ROW_LIMIT) {
     if (jar < 0) { w.e_force[r] = -D * jar; w.e_state[r] = 1; }
     else { w.e_force[r] = 0; w.e_state[r] = 0; }
-  } else if (tp == ROW_FRICTION) {  // quadratic inside |jar| < R f, linear (saturated force) outside; states 3 / 4 = saturated
+  } else if (KITCHEN_ROWS && tp == ROW_FRICTION) {  // quadratic inside |jar| < R f, linear (saturated force) outside; states 3 / 4 = saturated
     const real f = w.e_pos[r], rf = w.e_R[r] * f;
     if (jar <= -rf) { w.e_force[r] = f; w.e_state[r] = 3; }
     else if (jar >= rf) { w.e_force[r] = -f; w.e_state[r] = 4; }
@@ -900,7 +907,7 @@ MJ_FN int solver_update(const Model& m, Work& w, int lane) {
       changed += (old != w.e_state[r]) ? 1.0f : 0.0f;
     }
   for (int c = lane; c < w.ncon; c += NL) {
-    if (w.con_dim[c] <= 0) continue;  // pyramidal contact: its rows are plain unilateral rows
+    if (KITCHEN_ROWS && w.con_dim[c] <= 0) continue;  // pyramidal contact: its rows are plain unilateral rows
     const int old = w.e_state[w.con_row[c]];
     cone_eval(w, c, 0, false, true, nullptr, nullptr, nullptr);
     changed += (old != w.e_state[w.con_row[c]] || old == 2) ? 1.0f : 0.0f;  // the cone zone is not quadratic
@@ -924,7 +931,7 @@ MJ_FN void line_eval(Work& w, real alpha, int lane, real* d1, real* d2) {
     const int tp = w.e_type[r];
     if (is_cone_row(tp)) continue;
     const real x = w.e_jar[r] + alpha * w.e_jv[r], D = w.e_D[r], jv = w.e_jv[r];
-    if (tp == ROW_FRICTION) {
+    if (KITCHEN_ROWS && tp == ROW_FRICTION) {
       const real f = w.e_pos[r], rf = w.e_R[r] * f;
       if (x <= -rf) g -= f * jv;
       else if (x >= rf) g += f * jv;
@@ -932,7 +939,7 @@ MJ_FN void line_eval(Work& w, real alpha, int lane, real* d1, real* d2) {
     } else if (tp == ROW_EQ || x < 0) { g += D * x * jv; h += D * jv * jv; }
   }
   for (int c = lane; c < w.ncon; c += NL) {
-    if (w.con_dim[c] <= 0) continue;
+    if (KITCHEN_ROWS && w.con_dim[c] <= 0) continue;
     real cg, ch;
     cone_eval(w, c, alpha, true, false, nullptr, &cg, &ch);
     g += cg; h += ch;
@@ -975,7 +982,7 @@ MJ_FN void solve(const Model& m, Work& w, int lane) {
         if (w.e_state[r] == 1) s += w.e_D[r] * w.J[r][i] * w.J[r][j];
       for (int c = 0; c < w.ncon; ++c) {
         const int r0 = w.con_row[c];
-        if (w.con_dim[c] <= 0 || w.e_state[r0] != 2) continue;
+        if ((KITCHEN_ROWS && w.con_dim[c] <= 0) || w.e_state[r0] != 2) continue;
         const int dim = w.con_dim[c];
         for (int a = 0; a < dim; ++a)
           for (int b = 0; b < dim; ++b) s += w.con_H[c][4 * a + b] * w.J[r0 + a][i] * w.J[r0 + b][j];
@@ -1042,7 +1049,7 @@ MJ_FN void solve(const Model& m, Work& w, int lane) {
     // ~1 can still be 1e-3 of a large step away from the minimiser); otherwise stop once the step is at the fp32
     // noise floor of the largest acceleration
     int nmid = 0;
-    for (int c = 0; c < w.ncon; ++c) nmid += w.con_dim[c] > 0 && w.e_state[w.con_row[c]] == 2;
+    for (int c = 0; c < w.ncon; ++c) nmid += (!KITCHEN_ROWS || w.con_dim[c] > 0) && w.e_state[w.con_row[c]] == 2;
     const real floor_ = 1e-4f + 1e-5f * an;
     bool exact = nchg == 0 && nmid == 0 && fabsf(alpha - 1.0f) < 1e-3f;
     if (exact) {
