@@ -68,7 +68,7 @@ constexpr bool KITCHEN_ROWS = false;
 // Two capacity sets are compiled from these sources (earl_mj_small.cu / earl_mj_large.cu): the workspace of one
 // environment lives in shared memory, so rows x dofs and contacts decide how many environments one SM keeps in flight.
 #if defined(MJ_CAPSET_KITCHEN)
-constexpr int MAXEFC = 320; // constraint rows (6 weld + 5 equality + 23 friction loss + limits + 4 / 10 per pyramidal contact)
+constexpr int MAXEFC = 192; // constraint rows (6 weld + 5 equality + 23 friction loss + limits + 4 / 10 per pyramidal contact)
 constexpr int MAXCON = 24;  // contacts
 constexpr int MAXHIT = 64;  // candidate pairs that survive the broad phase in one substep
 constexpr int MAXPAIR = 4096; // candidate geom pairs

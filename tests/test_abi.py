@@ -9,7 +9,7 @@ import pytest
 from conftest import REPO
 from earl_benchmark_b200 import _lib, build
 
-HEADERS = [os.path.join(REPO, "include", f) for f in ("earl_b200.h", "earl_mj_b200.h")]
+HEADERS = [os.path.join(REPO, "include", f) for f in ("earl_b200.h", "earl_mj_b200.h", "earl_mj_kitchen_b200.h")]
 
 
 def header_symbols():
