@@ -27,7 +27,7 @@ continuing_eval_config = {
     'minitaur': {'num_initial_state_samples': 1, 'num_goals': 4, 'train_horizon': int(1e5), 'goal_change_frequency': 2000},
 }
 
-_BUILT = ("tabletop_manipulation", "sawyer_door", "sawyer_peg")
+_BUILT = ("tabletop_manipulation", "sawyer_door", "sawyer_peg", "kitchen")
 
 
 def shard_range(num_envs, rank, world_size):
@@ -105,6 +105,10 @@ class EARLEnvs(object):
             train_env = sawyer_peg.SawyerPegV2(reward_type=self._reward_type,
                                                reset_at_goal=self._reset_train_env_at_goal,
                                                eval_stats=False, **self._shard_kwargs(0))
+        elif self._env_name == 'kitchen':
+            from .envs import kitchen
+            kitchen_task = self._kwargs.get('kitchen_task', deployment_eval_config[self._env_name]['task'])
+            train_env = kitchen.Kitchen(task=kitchen_task, reward_type=self._reward_type, **self._shard_kwargs(0))
         else:
             deployment_eval_config[self._env_name]  # KeyError for unknown names
             self._not_built()
@@ -131,6 +135,10 @@ class EARLEnvs(object):
             from .envs import sawyer_peg
             eval_env = sawyer_peg.SawyerPegV2(reward_type=self._reward_type,
                                               eval_stats=self._kwargs.get('eval_stats', True), **self._shard_kwargs(1))
+        elif self._env_name == 'kitchen':
+            from .envs import kitchen
+            kitchen_task = self._kwargs.get('kitchen_task', deployment_eval_config[self._env_name]['task'])
+            eval_env = kitchen.Kitchen(task=kitchen_task, reward_type=self._reward_type, **self._shard_kwargs(1))
         else:
             self._not_built()
         return persistent_state_wrapper.PersistentStateWrapper(eval_env, episode_horizon=self._eval_horizon)
@@ -154,6 +162,9 @@ class EARLEnvs(object):
         if self._env_name == 'sawyer_peg':
             from .envs import sawyer_peg
             return sawyer_peg.initial_states
+        if self._env_name == 'kitchen':
+            from .envs import kitchen
+            return kitchen.initial_states['all_pairs']      # reference :212-217 (get_init_states of a throw-away Kitchen)
         self._not_built()
 
     def get_goal_states(self):
@@ -166,6 +177,9 @@ class EARLEnvs(object):
         if self._env_name == 'sawyer_peg':
             from .envs import sawyer_peg
             return sawyer_peg.goal_states
+        if self._env_name == 'kitchen':
+            from .envs import kitchen
+            return kitchen.goal_states
         self._not_built()
 
     def get_demonstrations(self, device=None):

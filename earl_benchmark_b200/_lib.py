@@ -106,6 +106,15 @@ SIGNATURES = [
     ("earl_mjk_engine_destroy", C.c_int, [_VP]),
     ("earl_mjk_engine_nv", C.c_int, [_VP]),
     ("earl_mjk_engine_substeps", C.c_int, [_VP, C.c_int32, C.c_int32, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
+    ("earl_mjk_create", C.c_int, [_VP, _VP, _SZ, C.POINTER(_VP)]),
+    ("earl_mjk_destroy", C.c_int, [_VP]),
+    ("earl_mjk_seed", C.c_int, [_VP, _VP]),
+    ("earl_mjk_reset", C.c_int, [_VP, _VP, C.c_int32, _VP, _VP, _VP]),
+    ("earl_mjk_step", C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP, _VP]),
+    ("earl_mjk_get_state", C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP, _VP]),
+    ("earl_mjk_set_state", C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP]),
+    ("earl_mjk_counters", C.c_int, [_VP, C.POINTER(_I64), _VP, _VP, _VP, _VP]),
+    ("earl_mjk_work_counters", C.c_int, [_VP, _VP]),
 ]
 
 _lib = None

@@ -12,6 +12,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <vector>
 
 #include <cuda_runtime.h>
 
@@ -81,11 +82,214 @@ mjk_substeps_kernel(const Model* __restrict__ gm, const real* __restrict__ hull,
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------ task layer
+constexpr int kNQ = 23, kRobot = 9, kObj = 14, kObs = 46, kAct = 9, kSites = 8;
+
+struct TaskArgs {
+  int n, frame_skip;
+  unsigned flags;
+  long long horizon;
+  double goal[kNQ], init_qpos[kNQ], pos_noise_amp[kNQ], pos_bound[kRobot][2], vel_bound[kRobot][2];
+  double midpoint[3], mocap_low[3], mocap_high[3], noise_ratio;
+  int site[kSites];
+  // per-env state (device)
+  float *qpos, *qvel, *warm;        // [N,23]
+  double* mocap;                    // [N,3]
+  double* last_qp;                  // [N,9]   Robot_VelAct observation cache (last NOISY robot qpos)
+  double* sites;                    // [N,8,3] site positions of the last forward pass
+  unsigned long long* rng;          // [N,4]   PCG64 state hi, lo, inc hi, lo
+  unsigned* steps_since_reset;
+  long long* num_interventions;
+  double* lifelong_return;
+  unsigned long long* work;         // 7 counters
+  float4 mocap_quat;
+};
+
+// numpy's PCG64 (pcg64.h: pcg_setseq_128_step_r + pcg_output_xsl_rr_128_64) and Generator.uniform(-1, 1)
+struct Pcg { unsigned __int128 state, inc; };
+__device__ __forceinline__ double pcg_uniform_pm1(Pcg& g) {
+  const unsigned __int128 mult = ((unsigned __int128)0x2360ED051FC65DA4ULL << 64) | 0x4385DF649FCCF645ULL;
+  g.state = g.state * mult + g.inc;
+  const unsigned long long hi = (unsigned long long)(g.state >> 64), lo = (unsigned long long)g.state;
+  const unsigned long long x = hi ^ lo;
+  const unsigned rot = (unsigned)(hi >> 58);
+  const unsigned long long out = (x >> rot) | (x << ((64 - rot) & 63));
+  const double r = (double)(out >> 11) * (1.0 / 9007199254740992.0);
+  return -1.0 + 2.0 * r;  // random_uniform(low, high - low): low + range * next_double
+}
+
+// Robot.get_obs (franka_robot.py:137-168): four draws per observation -- robot qpos (9), robot qvel (9, discarded), object
+// qpos (14), object qvel (14, discarded); obs46 = [noisy robot qpos, noisy object qpos, goal] when non-null
+__device__ void kitchen_observe(const TaskArgs& a, const Work& w, Pcg& g, double ratio, double* last_qp, double* obs46) {
+  double qp[kRobot];
+  // __dmul_rn / __dadd_rn: never contracted into a fused multiply-add, so the sums round exactly like numpy's
+  for (int i = 0; i < kRobot; ++i) qp[i] = __dadd_rn((double)w.qpos[i], __dmul_rn(__dmul_rn(ratio, a.pos_noise_amp[i]), pcg_uniform_pm1(g)));
+  for (int i = 0; i < kRobot; ++i) pcg_uniform_pm1(g);
+  for (int i = 0; i < kRobot; ++i) { last_qp[i] = qp[i]; if (obs46) obs46[i] = qp[i]; }
+  for (int i = 0; i < kObj; ++i) {
+    const double o = __dadd_rn((double)w.qpos[kRobot + i], __dmul_rn(__dmul_rn(ratio, a.pos_noise_amp[kRobot + i]), pcg_uniform_pm1(g)));
+    if (obs46) obs46[kRobot + i] = o;
+  }
+  for (int i = 0; i < kObj; ++i) pcg_uniform_pm1(g);
+  if (obs46) for (int i = 0; i < kNQ; ++i) obs46[kNQ + i] = a.goal[i];
+}
+
+// KitchenV0.step :91-105 + Robot_VelAct.ctrl_velocity_limits / ctrl_position_limits (franka_robot.py:172-174,255-264):
+// mocap update and the nu = 2 controls do_simulation writes (mujoco_env.py:148-153)
+__device__ void kitchen_control(const TaskArgs& a, const float* act9, const double* last_qp, double* mocap, real* ctrl2) {
+  double sc[kRobot];
+  for (int i = 0; i < kRobot; ++i) {
+    double x = act9 ? (double)act9[i] : 0.0;
+    x = x < -1.0 ? -1.0 : (x > 1.0 ? 1.0 : x);
+    sc[i] = 0.0 + x * 2.0;  // act_mid + a * act_amp
+  }
+  if (act9)
+    for (int k = 0; k < 3; ++k) {
+      const double p = __dadd_rn(mocap[k], __dmul_rn(sc[k], 0.01));
+      mocap[k] = p < a.mocap_low[k] ? a.mocap_low[k] : (p > a.mocap_high[k] ? a.mocap_high[k] : p);
+    }
+  const double dur = (double)a.frame_skip * 0.002;  // skip * model.opt.timestep
+  for (int i = 0; i < 2; ++i) {
+    double v = sc[i] < a.vel_bound[i][0] ? a.vel_bound[i][0] : (sc[i] > a.vel_bound[i][1] ? a.vel_bound[i][1] : sc[i]);
+    double p = __dadd_rn(last_qp[i], __dmul_rn(v, dur));
+    p = p < a.pos_bound[i][0] ? a.pos_bound[i][0] : (p > a.pos_bound[i][1] ? a.pos_bound[i][1] : p);
+    ctrl2[i] = (real)p;
+  }
+}
+
+// Kitchen._get_reward_n_score / is_successful (ENV/kitchen.py:141-183) on the noisy observation
+__device__ double kitchen_reward(const double* obs, const double* mocap, const double* sites, bool* success) {
+  double s = 0;
+  for (int i = 9; i < 23; ++i) { const double d = obs[i] - obs[i + 23]; s += d * d; }
+  const double dist = sqrt(s);
+  double r = -10 * dist;
+  *success = dist <= 0.3;
+  // component_to_state_idx (:15-25) in dict order: burner0..3, light_switch, slide_cabinet, hinge_cabinet, microwave
+  const int first[8] = {9, 11, 13, 15, 17, 19, 20, 22}, count[8] = {2, 2, 2, 2, 2, 1, 2, 1};
+  bool reaching = false;
+  for (int c = 0; c < 8; ++c) {
+    double q = 0;
+    for (int k = 0; k < count[c]; ++k) { const double d = obs[first[c] + k] - obs[first[c] + k + 23]; q += d * d; }
+    if (sqrt(q) < count[c] * 0.01) r += 1;
+    else if (!reaching) {
+      reaching = true;
+      double t = 0;
+      for (int k = 0; k < 3; ++k) { const double d = mocap[k] - sites[3 * c + k]; t += d * d; }
+      r += -0.5 * sqrt(t);
+    }
+  }
+  return r;
+}
+
+__device__ __forceinline__ void task_load(const TaskArgs& a, Work& w, int env, int lane) {
+  for (int k = lane; k < kNQ; k += 32) { w.qpos[k] = a.qpos[(size_t)env * kNQ + k]; w.qvel[k] = a.qvel[(size_t)env * kNQ + k]; w.warm[k] = a.warm[(size_t)env * kNQ + k]; }
+  if (lane == 0) {
+    for (int k = 0; k < 3; ++k) w.mocap_pos[k] = a.mocap[(size_t)env * 3 + k];
+    w.mocap_quat[0] = a.mocap_quat.x; w.mocap_quat[1] = a.mocap_quat.y; w.mocap_quat[2] = a.mocap_quat.z; w.mocap_quat[3] = a.mocap_quat.w;
+    w.bad = 0; w.acc_iter = w.acc_rows = w.acc_con = w.acc_mpr = w.acc_sup = 0;
+  }
+  __syncwarp();
+}
+__device__ __forceinline__ void task_store(const TaskArgs& a, const Model& m, const Work& w, int env, int lane) {
+  for (int k = lane; k < kNQ; k += 32) { a.qpos[(size_t)env * kNQ + k] = w.qpos[k]; a.qvel[(size_t)env * kNQ + k] = w.qvel[k]; a.warm[(size_t)env * kNQ + k] = w.warm[k]; }
+  if (lane < kSites) {  // site positions of the LAST forward pass (one substep stale, as sim.data.site_xpos after sim.step())
+    real p[3];
+    site_xpos(m, w, a.site[lane], p);
+    for (int k = 0; k < 3; ++k) a.sites[((size_t)env * kSites + lane) * 3 + k] = (double)p[k];
+  }
+  if (lane == 0) for (int k = 0; k < 3; ++k) a.mocap[(size_t)env * 3 + k] = w.mocap_pos[k];
+  __syncwarp();
+}
+
+// mode 0: one env step of every environment.  mode 1: reset of the environments in env_ids.
+__global__ void __launch_bounds__(kWPB * 32, 1)
+mjk_task_kernel(const Model* __restrict__ gm, const real* __restrict__ hull, const TaskArgs a, int mode, const int* env_ids, int count,
+                const float* actions, const double* object_qpos, double* obs_out, double* reward_out, unsigned char* done_out,
+                unsigned char* success_out) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  Work& w = *reinterpret_cast<Work*>(smem + warp * kWorkStride);
+  const Model& m = *gm;
+  unsigned long long c_it = 0, c_rows = 0, c_con = 0, c_bad = 0, c_over = 0, c_env = 0;
+  for (int base = blockIdx.x * kWPB; base < count; base += gridDim.x * kWPB) {
+    const bool own = base + warp < count;
+    const int slot = own ? base + warp : count - 1;
+    const int env = env_ids ? env_ids[slot] : slot;
+    Pcg g;
+    double last_qp[kRobot];
+    if (mode == 1) {  // Kitchen.reset_model: robot.reset (sim.reset, qpos write, forward, 5 cached observations at ratio 1)
+      for (int k = lane; k < kNQ; k += 32) {
+        const double q = k < kRobot ? a.init_qpos[k] : object_qpos[(size_t)slot * kObj + (k - kRobot)];
+        w.qpos[k] = (real)q; w.qvel[k] = 0; w.warm[k] = 0;
+      }
+      if (lane == 0) {
+        for (int k = 0; k < 3; ++k) w.mocap_pos[k] = a.midpoint[k];
+        w.mocap_quat[0] = a.mocap_quat.x; w.mocap_quat[1] = a.mocap_quat.y; w.mocap_quat[2] = a.mocap_quat.z; w.mocap_quat[3] = a.mocap_quat.w;
+        w.bad = 0; w.acc_iter = w.acc_rows = w.acc_con = w.acc_mpr = w.acc_sup = 0;
+      }
+      __syncwarp();
+    } else {
+      task_load(a, w, env, lane);
+    }
+    if (lane == 0) {
+      const unsigned long long* r = a.rng + (size_t)env * 4;
+      g.state = ((unsigned __int128)r[0] << 64) | r[1];
+      g.inc = ((unsigned __int128)r[2] << 64) | r[3];
+      if (mode == 1) {
+        for (int k = 0; k < 5; ++k) kitchen_observe(a, w, g, 1.0, last_qp, nullptr);  // _observation_cache_refresh: default ratio 1
+        kitchen_control(a, nullptr, last_qp, w.mocap_pos, w.ctrl);
+      } else {
+        for (int k = 0; k < kRobot; ++k) last_qp[k] = a.last_qp[(size_t)env * kRobot + k];
+        kitchen_control(a, actions + (size_t)env * kAct, last_qp, w.mocap_pos, w.ctrl);
+      }
+    }
+    __syncwarp();
+    const int nsub = mode == 1 ? 10 * a.frame_skip : a.frame_skip;
+    for (int s = 0; s < nsub; ++s) substep<32>(m, hull, w, lane);
+    __syncwarp();
+    if (own) {
+      task_store(a, m, w, env, lane);
+      if (lane == 0) {
+        double obs[kObs];
+        kitchen_observe(a, w, g, a.noise_ratio, last_qp, obs);
+        for (int k = 0; k < kRobot; ++k) a.last_qp[(size_t)env * kRobot + k] = last_qp[k];
+        unsigned long long* r = a.rng + (size_t)env * 4;
+        r[0] = (unsigned long long)(g.state >> 64); r[1] = (unsigned long long)g.state;
+        double* orow = obs_out ? obs_out + (size_t)slot * kObs : nullptr;
+        if (orow) for (int k = 0; k < kObs; ++k) orow[k] = obs[k];
+        if (mode == 0) {
+          bool ok;
+          const double rew = kitchen_reward(obs, w.mocap_pos, a.sites + (size_t)env * kSites * 3, &ok);
+          reward_out[env] = rew;
+          if (success_out) success_out[env] = ok;
+          const unsigned st = a.steps_since_reset[env] + 1;  // PersistentStateWrapper.step (persistent_state_wrapper.py:22-31)
+          a.steps_since_reset[env] = st;
+          done_out[env] = (long long)st >= a.horizon;
+          if (a.flags & EARL_FLAG_LIFELONG) a.lifelong_return[env] += rew;   // LifelongWrapper.step (lifelong_wrapper.py:30-44)
+        } else {
+          a.steps_since_reset[env] = 0;                     // PersistentStateWrapper.reset (:17-20)
+          a.num_interventions[env] += 1;
+        }
+        c_it += w.acc_iter; c_rows += w.acc_rows; c_con += w.acc_con; c_bad += (w.bad & 1) ? 1 : 0; c_over += (w.bad & 14) ? 1 : 0; c_env += 1;
+      }
+    }
+    __syncthreads();
+  }
+  if (lane == 0 && c_env) {
+    atomicAdd(&a.work[0], mode == 0 ? c_env : 0ULL);
+    atomicAdd(&a.work[1], c_env * (unsigned long long)(mode == 1 ? 10 * a.frame_skip : a.frame_skip));
+    atomicAdd(&a.work[2], c_it); atomicAdd(&a.work[3], c_rows); atomicAdd(&a.work[4], c_con);
+    atomicAdd(&a.work[5], c_bad); atomicAdd(&a.work[6], c_over);
+  }
+}
+
 }  // namespace
 
 struct earl_mjk_engine {
   HostModel hm;
   int device = 0, sm_count = 0;
+  float mocap_quat[4] = {1, 0, 0, 0};  // the model's mocap orientation (the task never moves it)
   Model* d_model = nullptr;
   real* d_hull = nullptr;
 };
@@ -110,6 +314,7 @@ int earl_mjk_engine_create(const void* model_blob, size_t model_nbytes, int32_t 
     return failf(EARL_ERR_INVALID, "%s", msg.c_str());
   }
   e->device = device;
+  for (int k = 0; k < 4; ++k) e->mocap_quat[k] = (float)e->hm.mocap_quat0[k];
   CU(cudaSetDevice(device));
   cudaDeviceProp prop;
   CU(cudaGetDeviceProperties(&prop, device));
@@ -148,6 +353,176 @@ int earl_mjk_engine_substeps(earl_mjk_engine* e, int32_t num_envs, int32_t nsub,
   mjk_substeps_kernel<<<grid, kWPB * 32, kSmemBytes, static_cast<cudaStream_t>(stream)>>>(
       e->d_model, e->d_hull, num_envs, nsub, qpos_dev, qvel_dev, warm_dev, mocap_pos_dev, mq, ctrl_dev, info_dev);
   CU(cudaGetLastError());
+  return 0;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------ task-level ABI
+static_assert(sizeof(earl_mjk_config) == 976, "earl_mjk_config layout (mirrored by envs/kitchen.py::MjkConfig)");
+struct earl_mjk_handle {
+  earl_mjk_engine* eng = nullptr;
+  TaskArgs a{};
+  int64_t total_steps = 0;
+  bool seeded = false;
+  std::vector<void*> owned;
+  template <typename T>
+  int alloc(T** ptr, size_t count) {
+    void* q = nullptr;
+    cudaError_t e = cudaMalloc(&q, count * sizeof(T) + 16);
+    if (e != cudaSuccess) return failf(EARL_ERR_NOMEM, "cudaMalloc(%zu B) failed: %s", count * sizeof(T), cudaGetErrorString(e));
+    e = cudaMemset(q, 0, count * sizeof(T));
+    if (e != cudaSuccess) return failf(EARL_ERR_CUDA, "cudaMemset failed: %s", cudaGetErrorString(e));
+    owned.push_back(q);
+    *ptr = static_cast<T*>(q);
+    return 0;
+  }
+};
+
+namespace {
+int launch_task(earl_mjk_handle* h, int mode, const int* env_ids, int count, const float* actions, const double* object_qpos,
+                double* obs, double* reward, unsigned char* done, unsigned char* success, void* stream) {
+  const int blocks = (count + kWPB - 1) / kWPB;
+  const int grid = blocks < h->eng->sm_count ? blocks : h->eng->sm_count;
+  mjk_task_kernel<<<grid, kWPB * 32, kSmemBytes, static_cast<cudaStream_t>(stream)>>>(h->eng->d_model, h->eng->d_hull, h->a, mode, env_ids,
+                                                                                   count, actions, object_qpos, obs, reward, done, success);
+  CU(cudaGetLastError());
+  return 0;
+}
+}  // namespace
+
+extern "C" {
+
+int earl_mjk_create(const earl_mjk_config* cfg, const void* model_blob, size_t model_nbytes, earl_mjk_handle** out) {
+  if (!cfg || !model_blob || !out) return failf(EARL_ERR_INVALID, "null argument");
+  *out = nullptr;
+  if (cfg->num_envs <= 0 || cfg->frame_skip <= 0 || cfg->episode_horizon <= 0) return failf(EARL_ERR_INVALID, "bad kitchen config");
+  earl_mjk_engine* eng = nullptr;
+  if (int rc = earl_mjk_engine_create(model_blob, model_nbytes, cfg->device, &eng)) return rc;
+  earl_mjk_handle* h = new (std::nothrow) earl_mjk_handle();
+  if (!h) { earl_mjk_engine_destroy(eng); return failf(EARL_ERR_NOMEM, "out of host memory"); }
+  h->eng = eng;
+  const Model& m = eng->hm.m;
+  if (m.nq != kNQ || m.nv != kNQ || m.nu != 2) { earl_mjk_destroy(h); return failf(EARL_ERR_INVALID, "not the kitchen model (nq %d nv %d nu %d)", m.nq, m.nv, m.nu); }
+  for (int k = 0; k < kSites; ++k)
+    if (cfg->site[k] < 0 || cfg->site[k] >= m.nsite) { earl_mjk_destroy(h); return failf(EARL_ERR_INVALID, "site index out of range"); }
+  TaskArgs& a = h->a;
+  a.n = cfg->num_envs; a.frame_skip = cfg->frame_skip; a.flags = cfg->flags; a.horizon = cfg->episode_horizon;
+  memcpy(a.goal, cfg->goal, sizeof a.goal); memcpy(a.init_qpos, cfg->init_qpos, sizeof a.init_qpos);
+  memcpy(a.pos_noise_amp, cfg->pos_noise_amp, sizeof a.pos_noise_amp);
+  memcpy(a.pos_bound, cfg->pos_bound, sizeof a.pos_bound); memcpy(a.vel_bound, cfg->vel_bound, sizeof a.vel_bound);
+  memcpy(a.midpoint, cfg->midpoint, sizeof a.midpoint); memcpy(a.mocap_low, cfg->mocap_low, sizeof a.mocap_low);
+  memcpy(a.mocap_high, cfg->mocap_high, sizeof a.mocap_high);
+  a.noise_ratio = cfg->noise_ratio;
+  memcpy(a.site, cfg->site, sizeof a.site);
+  const size_t n = (size_t)cfg->num_envs;
+  int rc = 0;
+  if ((rc = h->alloc(&a.qpos, n * kNQ)) || (rc = h->alloc(&a.qvel, n * kNQ)) || (rc = h->alloc(&a.warm, n * kNQ)) ||
+      (rc = h->alloc(&a.mocap, n * 3)) || (rc = h->alloc(&a.last_qp, n * kRobot)) || (rc = h->alloc(&a.sites, n * kSites * 3)) ||
+      (rc = h->alloc(&a.rng, n * 4)) || (rc = h->alloc(&a.steps_since_reset, n)) || (rc = h->alloc(&a.num_interventions, n)) ||
+      (rc = h->alloc(&a.lifelong_return, n)) || (rc = h->alloc(&a.work, 8))) {
+    earl_mjk_destroy(h);
+    return rc;
+  }
+  CU(cudaFuncSetAttribute(mjk_task_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+  *out = h;
+  return 0;
+}
+
+int earl_mjk_destroy(earl_mjk_handle* h) {
+  if (!h) return 0;
+  if (h->eng) cudaSetDevice(h->eng->device);
+  for (void* p : h->owned) cudaFree(p);
+  earl_mjk_engine_destroy(h->eng);
+  delete h;
+  return 0;
+}
+
+int earl_mjk_seed(earl_mjk_handle* h, const uint64_t* pcg_state_host) {
+  if (!h || !pcg_state_host) return failf(EARL_ERR_INVALID, "null argument");
+  CU(cudaSetDevice(h->eng->device));
+  CU(cudaMemcpy(h->a.rng, pcg_state_host, (size_t)h->a.n * 4 * sizeof(uint64_t), cudaMemcpyHostToDevice));
+  h->seeded = true;
+  return 0;
+}
+
+int earl_mjk_reset(earl_mjk_handle* h, const int32_t* env_ids_dev, int32_t count, const double* object_qpos_dev, double* obs_out_dev,
+                   void* stream) {
+  if (!h || !object_qpos_dev) return failf(EARL_ERR_INVALID, "null argument");
+  if (!h->seeded) return failf(EARL_ERR_INVALID, "earl_mjk_seed must be called before the first reset (the observation noise stream)");
+  if (!env_ids_dev) count = h->a.n;
+  if (count <= 0 || count > h->a.n) return failf(EARL_ERR_INVALID, "bad env count %d", count);
+  CU(cudaSetDevice(h->eng->device));
+  h->a.mocap_quat = make_float4(h->eng->mocap_quat[0], h->eng->mocap_quat[1], h->eng->mocap_quat[2], h->eng->mocap_quat[3]);
+  return launch_task(h, 1, env_ids_dev, count, nullptr, object_qpos_dev, obs_out_dev, nullptr, nullptr, nullptr, stream);
+}
+
+int earl_mjk_step(earl_mjk_handle* h, const float* actions_dev, double* obs_dev, double* reward_dev, uint8_t* done_dev, uint8_t* success_dev,
+                  void* stream) {
+  if (!h || !actions_dev || !obs_dev || !reward_dev || !done_dev) return failf(EARL_ERR_INVALID, "null argument");
+  CU(cudaSetDevice(h->eng->device));
+  h->a.mocap_quat = make_float4(h->eng->mocap_quat[0], h->eng->mocap_quat[1], h->eng->mocap_quat[2], h->eng->mocap_quat[3]);
+  h->total_steps += 1;
+  return launch_task(h, 0, nullptr, h->a.n, actions_dev, nullptr, obs_dev, reward_dev, done_dev, success_dev, stream);
+}
+
+int earl_mjk_get_state(earl_mjk_handle* h, double* qpos_host, double* qvel_host, double* warm_host, double* mocap_host, double* last_qp_host,
+                       double* sites_host) {
+  if (!h) return failf(EARL_ERR_INVALID, "null handle");
+  CU(cudaSetDevice(h->eng->device));
+  CU(cudaDeviceSynchronize());
+  const size_t n = (size_t)h->a.n;
+  std::vector<float> tmp(n * kNQ);
+  const float* src[3] = {h->a.qpos, h->a.qvel, h->a.warm};
+  double* dst[3] = {qpos_host, qvel_host, warm_host};
+  for (int k = 0; k < 3; ++k) {
+    if (!dst[k]) continue;
+    CU(cudaMemcpy(tmp.data(), src[k], n * kNQ * sizeof(float), cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < n * kNQ; ++i) dst[k][i] = tmp[i];
+  }
+  if (mocap_host) CU(cudaMemcpy(mocap_host, h->a.mocap, n * 3 * sizeof(double), cudaMemcpyDeviceToHost));
+  if (last_qp_host) CU(cudaMemcpy(last_qp_host, h->a.last_qp, n * kRobot * sizeof(double), cudaMemcpyDeviceToHost));
+  if (sites_host) CU(cudaMemcpy(sites_host, h->a.sites, n * kSites * 3 * sizeof(double), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int earl_mjk_set_state(earl_mjk_handle* h, const double* qpos_host, const double* qvel_host, const double* warm_host,
+                       const double* mocap_host, const double* last_qp_host) {
+  if (!h) return failf(EARL_ERR_INVALID, "null handle");
+  CU(cudaSetDevice(h->eng->device));
+  CU(cudaDeviceSynchronize());
+  const size_t n = (size_t)h->a.n;
+  std::vector<float> tmp(n * kNQ);
+  float* dst[3] = {h->a.qpos, h->a.qvel, h->a.warm};
+  const double* src[3] = {qpos_host, qvel_host, warm_host};
+  for (int k = 0; k < 3; ++k) {
+    if (!src[k]) continue;
+    for (size_t i = 0; i < n * kNQ; ++i) tmp[i] = (float)src[k][i];
+    CU(cudaMemcpy(dst[k], tmp.data(), n * kNQ * sizeof(float), cudaMemcpyHostToDevice));
+  }
+  if (mocap_host) CU(cudaMemcpy(h->a.mocap, mocap_host, n * 3 * sizeof(double), cudaMemcpyHostToDevice));
+  if (last_qp_host) CU(cudaMemcpy(h->a.last_qp, last_qp_host, n * kRobot * sizeof(double), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+int earl_mjk_counters(earl_mjk_handle* h, int64_t* total_steps_host, int64_t* num_interventions_dev, uint32_t* steps_since_reset_dev,
+                      double* lifelong_return_dev, void* stream) {
+  if (!h) return failf(EARL_ERR_INVALID, "null handle");
+  CU(cudaSetDevice(h->eng->device));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const size_t n = (size_t)h->a.n;
+  if (total_steps_host) *total_steps_host = h->total_steps;
+  if (num_interventions_dev) CU(cudaMemcpyAsync(num_interventions_dev, h->a.num_interventions, n * sizeof(int64_t), cudaMemcpyDeviceToDevice, s));
+  if (steps_since_reset_dev) CU(cudaMemcpyAsync(steps_since_reset_dev, h->a.steps_since_reset, n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
+  if (lifelong_return_dev) CU(cudaMemcpyAsync(lifelong_return_dev, h->a.lifelong_return, n * sizeof(double), cudaMemcpyDeviceToDevice, s));
+  return 0;
+}
+
+int earl_mjk_work_counters(earl_mjk_handle* h, uint64_t* out7_host) {
+  if (!h || !out7_host) return failf(EARL_ERR_INVALID, "null argument");
+  CU(cudaSetDevice(h->eng->device));
+  CU(cudaDeviceSynchronize());
+  CU(cudaMemcpy(out7_host, h->a.work, 7 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
   return 0;
 }
 

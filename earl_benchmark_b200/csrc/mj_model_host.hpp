@@ -82,6 +82,7 @@ class BlobReader {
 struct HostModel {
   Model m;
   std::vector<float> hull_vert;  // [nhull][3]
+  double mocap_pos0[3] = {0, 0, 0}, mocap_quat0[4] = {1, 0, 0, 0};  // mocap pose after sim.reset()
 };
 
 // Compile-time pruning of candidate pairs (static geom gs, geom gm on a body whose only ancestor is the world and whose
@@ -274,8 +275,8 @@ inline bool build_model(const void* blob, size_t nbytes, const TaskSpec& task, H
   VD(nw * 2, m.weld_solref[k / 2][k % 2] = (real)D[k]);
   VD(nw * 5, m.weld_solimp[k / 5][k % 5] = (real)D[k]);
   VD(nw * 2, m.weld_invweight[k / 2][k % 2] = (real)D[k]);
-  VD(3, (void)D[k]);  // mocap_pos0
-  VD(4, (void)D[k]);  // mocap_quat0
+  VD(3, out->mocap_pos0[k] = D[k]);
+  VD(4, out->mocap_quat0[k] = D[k]);
   m.neq = 0;
   if (rd.version == 2) {
     RI(m.neq);

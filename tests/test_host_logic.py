@@ -31,9 +31,28 @@ def test_unknown_env_is_keyerror_like_reference():
 
 
 def test_unbuilt_envs_fail_loudly():
-    for name in ("sawyer_peg", "kitchen"):
-        with pytest.raises(NotImplementedError):
-            eb.EARLEnvs(name, reward_type="dense")
+    with pytest.raises(NotImplementedError):
+        eb.EARLEnvs("sawyer_peg", reward_type="dense")
+
+
+def test_kitchen_loader_surface():
+    """Reference: Kitchen(reward_type='sparse') raises ValueError (envs/kitchen.py:91-92) and EARLEnvs passes its default
+    'sparse' through (__init__.py:135-138), so the dense reward has to be asked for; initial / goal states :205-236."""
+    with pytest.raises(ValueError):
+        eb.EARLEnvs("kitchen")
+    e = eb.EARLEnvs("kitchen", reward_type="dense", num_envs=3)
+    assert e.get_initial_states().shape == (6, 23) and e.get_goal_states().shape == (1, 23)
+    tr, ev = e.get_envs()
+    assert tr.get_task() == "all_pairs" and tr.get_init_states().shape == (6, 23)
+    assert np.array_equal(tr.get_next_goal(), e.get_goal_states()[0])
+    assert not e.has_demos()
+    from earl_benchmark_b200.envs import kitchen
+    st = kitchen.pcg64_states([5, 6])
+    g = np.random.Generator(np.random.PCG64(np.random.SeedSequence(5)))
+    s = g.bit_generator.state["state"]
+    assert int(st[0, 0]) == s["state"] >> 64 and int(st[0, 1]) == s["state"] & ((1 << 64) - 1) and int(st[0, 3]) == s["inc"] & ((1 << 64) - 1)
+    import ctypes
+    assert ctypes.sizeof(kitchen.MjkConfig) == 976
 
 
 def test_states_and_demos(golden_dir):

@@ -1,0 +1,151 @@
+"""Kitchen task on the device (envs/kitchen.py -> include/earl_mj_kitchen_b200.h) against the checker
+(oracle/engine.py::KitchenOracle = pinned task logic + fp64 engine).  Tolerances: the observation NOISE and all integer
+bookkeeping are exact; states go through 40 fp32 substeps per env step (north-star bar 1e-4 per one-step qpos)."""
+import numpy as np
+import pytest
+import torch
+
+import earl_benchmark_b200 as eb
+from earl_benchmark_b200.envs import kitchen
+from earl_benchmark_b200.mjcf.compile import Model
+from oracle import kitchen_logic as KL
+from oracle.engine import KitchenOracle
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle(seed):
+    k = KitchenOracle(Model.load(kitchen.MODEL_PATH))
+    k.seed(seed)
+    return k
+
+
+def test_reset_and_open_loop_rollout_against_checker():
+    n, seed = 6, 11
+    env = kitchen.Kitchen(num_envs=n, device="cuda:0", seed=seed)
+    env.seed(seed)
+    ob = env.reset(config_index=np.arange(n) % 6).cpu().numpy()
+    oracles = []
+    for i in range(n):
+        k = _oracle(seed + i)
+        q0 = KL.INIT_QPOS.copy()
+        q0[9:] = KL.ALL_PAIRS[i % 6, 9:]
+        # KitchenOracle.reset with a given configuration
+        k.e.reset()
+        k.e.qpos[:], k.e.qvel[:] = q0, 0
+        k.e.forward()
+        for _ in range(5):
+            k.logic.observe(k.e.qpos, noise_ratio=1)
+        k.e.mocap_pos[:] = KL.MIDPOINT
+        for _ in range(10):
+            _, ctrl = k.logic.control(np.zeros(9), KL.MIDPOINT)
+            k._simulate(ctrl)
+        ob_ref = k.logic.observe(k.e.qpos)
+        oracles.append(k)
+        assert np.abs(ob[i] - ob_ref).max() < 2e-5, (i, np.abs(ob[i] - ob_ref).max())
+        assert np.array_equal(ob[i, 23:], KL.GOAL)
+    st = env.get_state()
+    for i, k in enumerate(oracles):
+        assert np.array_equal(st["mocap_pos"][i], KL.MIDPOINT)
+        assert np.abs(st["last_noisy_qp"][i] - k.logic.last_qp).max() < 2e-5
+        # the noise itself is exact: obs - state on both sides is the same PCG64 draw times the same amplitude
+        assert np.abs((ob[i, :9] - st["qpos"][i, :9]) - (k.logic.last_qp - k.e.qpos[:9])).max() < 2e-7
+    rs = np.random.RandomState(3)
+    worst_q = worst_ob = worst_r = 0.0
+    for t in range(12):
+        a = rs.uniform(-1.2, 1.2, (n, 9)).astype(np.float32)
+        obs, rew, done, info = env.step(torch.from_numpy(a).cuda())
+        obs, rew = obs.cpu().numpy(), rew.cpu().numpy()
+        st = env.get_state()
+        for i, k in enumerate(oracles):
+            ob_ref, r_ref, s_ref = k.step(a[i])
+            assert np.abs(st["mocap_pos"][i] - k.e.mocap_pos).max() == 0          # fp64 mocap arithmetic: exact
+            worst_q = max(worst_q, np.abs(st["qpos"][i] - k.e.qpos).max())
+            worst_ob = max(worst_ob, np.abs(obs[i] - ob_ref).max())
+            worst_r = max(worst_r, abs(rew[i] - r_ref))
+            assert bool(info["success"][i]) == s_ref and not bool(done[i])
+    print("kitchen open loop, 12 env steps: |dqpos| %.2e |dobs| %.2e |dreward| %.2e" % (worst_q, worst_ob, worst_r))
+    assert worst_q < 2e-3 and worst_ob < 2e-3 and worst_r < 2e-2
+    assert env.work_counters()["bad_states"] == 0
+
+
+def test_one_env_step_from_identical_states():
+    """set_state on both sides (states along a scripted checker rollout into the cabinets), one env step = 40 substeps."""
+    import test_kitchen_engine_gpu as T
+    kref, states = T._states(24)
+    n = len(states)
+    env = kitchen.Kitchen(num_envs=n, device="cuda:0", seed=5)
+    env.seed(5)
+    env.reset(config_index=np.zeros(n, int))
+    last = np.stack([s[0][:9] for s in states])
+    env.set_state(qpos=np.stack([s[0] for s in states]), qvel=np.stack([s[1] for s in states]),
+                  qacc_warmstart=np.stack([s[2] for s in states]), mocap_pos=np.stack([s[3] for s in states]), last_noisy_qp=last)
+    rs = np.random.RandomState(9)
+    a = rs.uniform(-1, 1, (n, 9)).astype(np.float32)
+    obs, rew, done, info = env.step(torch.from_numpy(a).cuda())
+    st = env.get_state()
+    e = kref.e
+    dq, dv = [], []
+    for i, (q, v, w, mp, c) in enumerate(states):
+        e.reset()
+        e.qpos[:], e.qvel[:], e.mocap_pos[:] = q.astype(np.float32), v.astype(np.float32), mp
+        e.arr("qacc_warmstart", (32,))[:23] = w.astype(np.float32)
+        kref.logic.last_qp = last[i].copy()
+        mocap, ctrl = kref.logic.control(a[i], e.mocap_pos.copy())
+        e.mocap_pos[:] = mocap
+        kref._simulate(ctrl)
+        dq.append(np.abs(st["qpos"][i] - e.qpos).max())
+        dv.append(np.abs(st["qvel"][i] - e.qvel).max())
+        ref_sites = np.stack([e.site_xpos(nm) for nm in kitchen.REWARD_SITES])      # device order: component_to_state_idx
+        assert np.abs(st["site_xpos"][i] - ref_sites).max() < 1e-4
+    dq, dv = np.array(dq), np.array(dv)
+    print("kitchen one env step (40 substeps): dq median %.2e max %.2e, dv median %.2e max %.2e" % (np.median(dq), dq.max(), np.median(dv), dv.max()))
+    assert np.median(dq) < 1e-5 and np.percentile(dq, 90) < 1e-4 and dq.max() < 5e-3
+    assert np.median(dv) < 1e-4 and dv.max() < 0.5
+
+
+def test_loader_wrappers_counters_and_reset_draws():
+    envs = eb.EARLEnvs("kitchen", reward_type="dense", num_envs=4, seed=21, train_horizon=3, eval_horizon=2)
+    tr, ev = envs.get_envs()
+    ob = tr.reset()
+    assert tuple(ob.shape) == (4, 46) and ob.dtype == torch.float64
+    # reset_model's np.random.randint(6), one legacy numpy stream in environment order
+    np.random.seed(21)
+    assert tr.last_config_index.tolist() == [np.random.randint(6) for _ in range(4)]
+    assert tr.num_interventions.tolist() == [1] * 4 and tr.total_steps == 0
+    a = torch.zeros((4, 9), device="cuda")
+    for t in range(3):
+        ob, r, done, info = tr.step(a)
+        assert done.tolist() == [t == 2] * 4 and tr.steps_since_reset.tolist() == [t + 1] * 4
+    assert tr.total_steps == 3
+    tr.reset(mask=[True, False, True, False])
+    assert tr.num_interventions.tolist() == [2, 1, 2, 1] and tr.steps_since_reset.tolist() == [0, 3, 0, 3]
+    assert bool(torch.all(tr.is_successful(ob) == info["success"]))
+    ll = eb.EARLEnvs("kitchen", reward_type="dense", setup_as_lifelong_learning=True, num_envs=2, seed=2).get_envs()
+    ll.reset()
+    tot = torch.zeros(2, dtype=torch.float64, device="cuda")
+    for t in range(3):
+        ob, r, done, info = ll.step(torch.zeros((2, 9), device="cuda"))
+        tot += r
+    assert torch.equal(ll.lifelong_return, tot)
+
+
+def test_same_results_for_any_batch_composition():
+    a = np.random.RandomState(1).uniform(-1, 1, (5, 9)).astype(np.float32)
+
+    def run(idx):
+        env = kitchen.Kitchen(num_envs=len(idx), device="cuda:0", seed=0)
+        env.seed(0)
+        # give every environment the stream of its GLOBAL index
+        st = np.ascontiguousarray(kitchen.pcg64_states([int(i) for i in idx]))
+        from earl_benchmark_b200 import _lib
+        _lib.check(_lib.lib().earl_mjk_seed(env._handle, st.ctypes.data))
+        env.reset(config_index=np.asarray(idx) % 6)
+        out = []
+        for t in range(3):
+            ob, r, d, info = env.step(torch.from_numpy(np.repeat(a[t:t + 1], len(idx), 0)).cuda())
+            out.append((ob.clone(), r.clone()))
+        return out
+    full, part = run([0, 1, 2, 3, 4, 5, 6]), run([5, 2])
+    for (o1, r1), (o2, r2) in zip(full, part):
+        assert torch.equal(o1[[5, 2]], o2) and torch.equal(r1[[5, 2]], r2)
