@@ -20,6 +20,7 @@ One JSON line on stdout (rank 0):
                actions; env-steps/s, e2e with host buffers, FP32-issue roofline from the checker's flop count, CPU
                baseline (fp64 C restatement of the engine, one process per host core)
   sawyer_peg   third section (BASELINE.json configs[3]): the same for the Sawyer peg task (free-joint peg, nv = 15)
+  kitchen      fourth section (configs[4]): batched Franka kitchen step, 11,840 envs per GPU, 40 substeps per env step
 `--impl reference` times that CPU port alone on the same config (the reference itself is Python over
 mujoco-py and cannot run on the GPU box).
 """
@@ -256,6 +257,78 @@ def run_door(dev, rank, world, sm_max_mhz, sm_count, with_cpu, task="sawyer_door
     return out
 
 
+KITCHEN_ENVS, KITCHEN_STEPS, KITCHEN_WARMUP = 11840, 8, 3
+
+
+def run_kitchen(dev, rank, world, sm_max_mhz, sm_count, with_cpu):
+    """Fourth bench section: batched kitchen step (BASELINE.json configs[4]): 11,840 envs per GPU (= 148 SMs x 5 resident
+    environments x 16 waves), random actions after a full reset (400 settle substeps per env)."""
+    import torch
+    import torch.distributed as dist
+
+    from earl_benchmark_b200.distributed import max_over_ranks
+    from earl_benchmark_b200.envs import kitchen
+
+    n = KITCHEN_ENVS
+    env = kitchen.Kitchen(num_envs=n, device=dev, seed=1000 * rank)
+    env.seed(1000 * rank)
+    env.reset()
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(99 + rank)
+    actions = torch.rand((KITCHEN_WARMUP + KITCHEN_STEPS, n, 9), generator=gen, device=dev, dtype=torch.float32) * 2 - 1
+    for t in range(KITCHEN_WARMUP):
+        env.step(actions[t])
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    w0 = env.work_counters()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for t in range(KITCHEN_STEPS):
+        env.step(actions[KITCHEN_WARMUP + t])
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = max_over_ranks(e0.elapsed_time(e1), dev)
+    w1 = env.work_counters()
+    host_a = (torch.rand((n, 9), dtype=torch.float32) * 2 - 1).numpy()
+    t0 = time.perf_counter()
+    for _ in range(2):
+        env.step(host_a)
+    e2e_s = max_over_ranks(time.perf_counter() - t0, dev)
+    out = None
+    if rank == 0:
+        sub = max(1, w1["substeps"] - w0["substeps"])
+        value = n * world * KITCHEN_STEPS / (ms * 1e-3)
+        out = {"metric": "batched env-steps/sec (kitchen, dense, 40 substeps per env step)", "value": value, "unit": UNIT,
+               "envs_per_gpu": n, "steps": KITCHEN_STEPS, "warmup": KITCHEN_WARMUP, "ms_per_step": ms / KITCHEN_STEPS, "dtype": "f32",
+               "gpu_launches": KITCHEN_STEPS,
+               "e2e": {"value": n * world * 2 / e2e_s, "unit": UNIT, "h2d_bytes_per_step": n * 36 * world,
+                       "d2h_bytes_per_step": n * (46 * 8 + 8 + 1 + 1) * world, "steps": 2},
+               "work": {"newton_iterations_per_substep": (w1["newton_iterations"] - w0["newton_iterations"]) / sub,
+                        "constraint_rows_per_substep": (w1["constraint_rows"] - w0["constraint_rows"]) / sub,
+                        "contacts_per_substep": (w1["contacts"] - w0["contacts"]) / sub,
+                        "bad_states": w1["bad_states"] - w0["bad_states"],
+                        "overflow_states": w1["overflow_states"] - w0["overflow_states"]},
+               "kernel": "mjk_task_kernel (one warp per env, 5 envs per SM in flight, model tables in global memory)"}
+        if with_cpu:
+            procs = os.cpu_count() or 1
+            rate, flops, wall = door_cpu_rate(procs, steps_per_proc=1500, task="kitchen")
+            peak = sm_count * 128 * 2 * (sm_max_mhz or 1965.0) * 1e6 / 1e12
+            ach = flops * (value / world) / 1e12
+            out["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": procs, "kind": "port",
+                                   "sample": f"{procs} processes x 1500 env steps of the same random-action workload, fp64 C "
+                                             f"restatement of the engine + pinned task logic (not MuJoCo), {wall:.1f} s"}
+            out["roofline"] = {"bound": "fp32", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+                               "algorithmic_flops_per_env_step": flops,
+                               "peak_source": f"{sm_count} SMs x 128 lanes x 2 x {sm_max_mhz or 1965.0:.0f} MHz (nominal FP32 FMA issue)",
+                               "note": "first device version of this capacity set: 5 warps per SM, 2,974 candidate pairs tested per "
+                                       "substep; latency bound"}
+    del env
+    return out
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -389,13 +462,15 @@ def run_ours(args):
                "kernel": "earl::tabletop_step_tma_kernel<3,256>  (cp.async.bulk pipeline)"}
         del a_b, o_b, r_b, d_b, tb, lb
 
-    door = peg = None
+    door = peg = kit = None
     if not args.profile and not args.no_door:
         props = torch.cuda.get_device_properties(dev)
         door = run_door(dev, rank, world, (clocks or {}).get("sm_max_mhz"), props.multi_processor_count,
                         with_cpu=(world == 1 and not args.no_cpu_baseline))
         peg = run_door(dev, rank, world, (clocks or {}).get("sm_max_mhz"), props.multi_processor_count,
                        with_cpu=(world == 1 and not args.no_cpu_baseline), task="sawyer_peg")
+        kit = run_kitchen(dev, rank, world, (clocks or {}).get("sm_max_mhz"), props.multi_processor_count,
+                          with_cpu=(world == 1 and not args.no_cpu_baseline))
 
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
@@ -425,6 +500,8 @@ def run_ours(args):
             line["sawyer_door"] = door
         if peg is not None:
             line["sawyer_peg"] = peg
+        if kit is not None:
+            line["kitchen"] = kit
         if world == 1 and not args.no_cpu_baseline and not args.profile:
             threads = os.cpu_count() or 1
             rate, n_sample, el = cpu_port_rate(n, min(args.steps, 200), threads, budget_s=15.0)

@@ -14,9 +14,23 @@ sys.path.insert(0, REPO)
 
 def main(seed, steps, task="sawyer_door"):
     from earl_benchmark_b200.mjcf.compile import Model
-    from oracle.engine import SawyerDoorOracle, SawyerPegOracle
+    from oracle.engine import KitchenOracle, SawyerDoorOracle, SawyerPegOracle
     model = Model.load(os.path.join(REPO, "earl_benchmark_b200", "models", task + ".npz"))
     rs = np.random.RandomState(seed)
+    if task == "kitchen":
+        o = KitchenOracle(model)
+        o.seed(seed)
+        np.random.seed(seed)
+        o.reset()
+        acts = rs.uniform(-1, 1, (steps, 9))
+        for a in acts[:3]:
+            o.step(a)
+        f0 = o.e.flops
+        t0 = time.perf_counter()
+        for a in acts:
+            o.step(a)
+        print(json.dumps({"seconds": time.perf_counter() - t0, "steps": steps, "flops_per_env_step": (o.e.flops - f0) / steps}))
+        return
     if task == "sawyer_door":
         o = SawyerDoorOracle(model)
         o.reset(door_angle=-np.pi / 3 + rs.uniform(0, np.pi / 20))
