@@ -218,7 +218,11 @@ class Kitchen:
     def _draw_configs(self, count):
         """reset_model's np.random.randint(6) per environment, in environment order (kitchen.py:122-124)."""
         if self._task == 'all_pairs':
-            idx = self._np_random.randint(self._initial_states['all_pairs'].shape[0], count)
+            k = self._initial_states['all_pairs'].shape[0]
+            if count == self.num_envs:   # full reset: every shard consumes the global stream and keeps its slice (SURVEY 8e)
+                idx = self._np_random.randint(k, self._total_envs)[self._env_offset:self._env_offset + self.num_envs]
+            else:
+                idx = self._np_random.randint(k, count)
             return self._initial_states['all_pairs'][idx, 9:], idx
         return np.tile(self._initial_states[self._task][9:], (count, 1)), np.zeros(count, np.int32)
 

@@ -174,3 +174,14 @@ def test_sawyer_reset_draws_do_not_depend_on_the_number_of_shards():
     whole_p = peg_draws(total, 0)
     lo, hi = shard_range(total, 1, 2)
     assert np.array_equal(peg_draws(hi - lo, lo), whole_p[lo:hi])
+    # kitchen: np.random.randint(6) per env and one PCG64 observation-noise stream per GLOBAL env index
+    from earl_benchmark_b200.envs import kitchen as kt
+    whole_k = kt.Kitchen(num_envs=total, seed=5)._draw_configs(total)[1]
+    np.random.seed(5)
+    assert whole_k.tolist() == [np.random.randint(6) for _ in range(total)]
+    for world in (2, 3):
+        parts = []
+        for r in range(world):
+            lo, hi = shard_range(total, r, world)
+            parts.append(kt.Kitchen(num_envs=hi - lo, seed=5, env_offset=lo, total_envs=total)._draw_configs(hi - lo)[1])
+        assert np.array_equal(np.concatenate(parts), whole_k)
