@@ -42,7 +42,10 @@ int failf(int code, const char* fmt, ...) {
       return failf(EARL_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__);    \
   } while (0)
 
-constexpr int kWPB = 5;  // warps (= environments in flight) per block
+#ifndef MJK_WPB
+#define MJK_WPB 5
+#endif
+constexpr int kWPB = MJK_WPB;  // warps (= environments in flight) per block
 constexpr size_t kWorkStride = (sizeof(Work) + 15) & ~size_t(15);
 constexpr size_t kSmemBytes = kWPB * kWorkStride;
 static_assert(kSmemBytes <= 227 * 1024, "workspaces exceed the 227 KB of shared memory per block");

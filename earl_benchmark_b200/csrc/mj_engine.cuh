@@ -139,7 +139,8 @@ struct Model {
   real geom_solref[MAXG][2], geom_solimp[MAXG][5], geom_solmix[MAXG], geom_invweight0[MAXG][2], geom_rbound[MAXG];
   real geom_obb_size[MAXG][3], geom_obb_off[MAXG][3];  // bounding box in the geom frame (box: itself; cylinder: r,r,h; mesh: hull AABB)
   // candidate collision pairs (compile-time filtered: contype/conaffinity, same body, parent-child)
-  int pair_g1[MAXPAIR], pair_g2[MAXPAIR];
+  unsigned char pair_g1[MAXPAIR], pair_g2[MAXPAIR];  // geom indices
+  static_assert(MAXG <= 256, "pair tables hold geom indices in one byte");
   // task constants
   int obs_hand_site, obs_ree_site, obs_lee_site, obs_obj_geom, obs_obj_site;
   real mocap_low[3], mocap_high[3], action_scale, success_radius;
