@@ -92,7 +92,7 @@ constexpr int kNQ = 23, kRobot = 9, kObj = 14, kObs = 46, kAct = 9, kSites = 8;
 struct TaskArgs {
   int n, frame_skip;
   unsigned flags;
-  long long horizon;
+  long long horizon, goal_change_frequency;
   double goal[kNQ], init_qpos[kNQ], pos_noise_amp[kNQ], pos_bound[kRobot][2], vel_bound[kRobot][2];
   double midpoint[3], mocap_low[3], mocap_high[3], noise_ratio;
   int site[kSites];
@@ -103,6 +103,7 @@ struct TaskArgs {
   double* sites;                    // [N,8,3] site positions of the last forward pass
   unsigned long long* rng;          // [N,4]   PCG64 state hi, lo, inc hi, lo
   unsigned* steps_since_reset;
+  unsigned* steps_since_goal_change;
   long long* num_interventions;
   double* lifelong_return;
   unsigned long long* work;         // 7 counters
@@ -269,9 +270,24 @@ mjk_task_kernel(const Model* __restrict__ gm, const real* __restrict__ hull, con
           const unsigned st = a.steps_since_reset[env] + 1;  // PersistentStateWrapper.step (persistent_state_wrapper.py:22-31)
           a.steps_since_reset[env] = st;
           done_out[env] = (long long)st >= a.horizon;
-          if (a.flags & EARL_FLAG_LIFELONG) a.lifelong_return[env] += rew;   // LifelongWrapper.step (lifelong_wrapper.py:30-44)
+          if (a.flags & EARL_FLAG_LIFELONG) {              // LifelongWrapper.step (lifelong_wrapper.py:30-44)
+            a.lifelong_return[env] += rew;
+            const unsigned sg = a.steps_since_goal_change[env] + 1;
+            if (a.goal_change_frequency > 0 && (long long)sg >= a.goal_change_frequency) {
+              // reset_goal() (a single goal: nothing changes) and env._get_obs(): a second noisy observation, returned
+              // instead of the first and cached for the next control; the reward stays the one already computed
+              a.steps_since_goal_change[env] = 0;
+              kitchen_observe(a, w, g, a.noise_ratio, last_qp, obs);
+              for (int k = 0; k < kRobot; ++k) a.last_qp[(size_t)env * kRobot + k] = last_qp[k];
+              r[0] = (unsigned long long)(g.state >> 64); r[1] = (unsigned long long)g.state;
+              if (orow) for (int k = 0; k < kObs; ++k) orow[k] = obs[k];
+            } else {
+              a.steps_since_goal_change[env] = sg;
+            }
+          }
         } else {
           a.steps_since_reset[env] = 0;                     // PersistentStateWrapper.reset (:17-20)
+          a.steps_since_goal_change[env] = 0;               // LifelongWrapper.reset (:25-28)
           a.num_interventions[env] += 1;
         }
         c_it += w.acc_iter; c_rows += w.acc_rows; c_con += w.acc_con; c_bad += (w.bad & 1) ? 1 : 0; c_over += (w.bad & 14) ? 1 : 0; c_env += 1;
@@ -362,7 +378,7 @@ int earl_mjk_engine_substeps(earl_mjk_engine* e, int32_t num_envs, int32_t nsub,
 }  // extern "C"
 
 // ------------------------------------------------------------------------------------------------ task-level ABI
-static_assert(sizeof(earl_mjk_config) == 976, "earl_mjk_config layout (mirrored by envs/kitchen.py::MjkConfig)");
+static_assert(sizeof(earl_mjk_config) == 984, "earl_mjk_config layout (mirrored by envs/kitchen.py::MjkConfig)");
 struct earl_mjk_handle {
   earl_mjk_engine* eng = nullptr;
   TaskArgs a{};
@@ -410,7 +426,7 @@ int earl_mjk_create(const earl_mjk_config* cfg, const void* model_blob, size_t m
   for (int k = 0; k < kSites; ++k)
     if (cfg->site[k] < 0 || cfg->site[k] >= m.nsite) { earl_mjk_destroy(h); return failf(EARL_ERR_INVALID, "site index out of range"); }
   TaskArgs& a = h->a;
-  a.n = cfg->num_envs; a.frame_skip = cfg->frame_skip; a.flags = cfg->flags; a.horizon = cfg->episode_horizon;
+  a.n = cfg->num_envs; a.frame_skip = cfg->frame_skip; a.flags = cfg->flags; a.horizon = cfg->episode_horizon; a.goal_change_frequency = cfg->goal_change_frequency;
   memcpy(a.goal, cfg->goal, sizeof a.goal); memcpy(a.init_qpos, cfg->init_qpos, sizeof a.init_qpos);
   memcpy(a.pos_noise_amp, cfg->pos_noise_amp, sizeof a.pos_noise_amp);
   memcpy(a.pos_bound, cfg->pos_bound, sizeof a.pos_bound); memcpy(a.vel_bound, cfg->vel_bound, sizeof a.vel_bound);
@@ -422,7 +438,7 @@ int earl_mjk_create(const earl_mjk_config* cfg, const void* model_blob, size_t m
   int rc = 0;
   if ((rc = h->alloc(&a.qpos, n * kNQ)) || (rc = h->alloc(&a.qvel, n * kNQ)) || (rc = h->alloc(&a.warm, n * kNQ)) ||
       (rc = h->alloc(&a.mocap, n * 3)) || (rc = h->alloc(&a.last_qp, n * kRobot)) || (rc = h->alloc(&a.sites, n * kSites * 3)) ||
-      (rc = h->alloc(&a.rng, n * 4)) || (rc = h->alloc(&a.steps_since_reset, n)) || (rc = h->alloc(&a.num_interventions, n)) ||
+      (rc = h->alloc(&a.rng, n * 4)) || (rc = h->alloc(&a.steps_since_reset, n)) || (rc = h->alloc(&a.steps_since_goal_change, n)) || (rc = h->alloc(&a.num_interventions, n)) ||
       (rc = h->alloc(&a.lifelong_return, n)) || (rc = h->alloc(&a.work, 8))) {
     earl_mjk_destroy(h);
     return rc;

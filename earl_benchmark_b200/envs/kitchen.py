@@ -89,7 +89,7 @@ REWARD_SITES = ("knob1_site", "knob2_site", "knob3_site", "knob4_site", "light_s
 
 class MjkConfig(C.Structure):   # earl_mjk_config (include/earl_mj_kitchen_b200.h)
     _fields_ = [("num_envs", C.c_int32), ("device", C.c_int32), ("flags", C.c_uint32), ("frame_skip", C.c_int32),
-                ("episode_horizon", C.c_int64), ("goal", C.c_double * 23), ("init_qpos", C.c_double * 23),
+                ("episode_horizon", C.c_int64), ("goal_change_frequency", C.c_int64), ("goal", C.c_double * 23), ("init_qpos", C.c_double * 23),
                 ("pos_noise_amp", C.c_double * 23), ("pos_bound", C.c_double * 18), ("vel_bound", C.c_double * 18),
                 ("midpoint", C.c_double * 3), ("mocap_low", C.c_double * 3), ("mocap_high", C.c_double * 3),
                 ("noise_ratio", C.c_double), ("site", C.c_int32 * 8)]
@@ -173,7 +173,8 @@ class Kitchen:
         if episode_horizon is not None:
             self._episode_horizon = int(episode_horizon)
         if lifelong is not None:
-            self._lifelong = bool(lifelong)      # one goal: the periodic reset_goal() of LifelongWrapper changes nothing
+            self._lifelong = bool(lifelong)      # one goal: the periodic reset_goal() changes nothing, but the _get_obs() that
+            # follows it draws a second noisy observation (lifelong_wrapper.py:36-42): done in the step kernel
         if goal_change_frequency is not None:
             self._goal_change_frequency = int(goal_change_frequency)
 
@@ -184,6 +185,7 @@ class Kitchen:
         cfg.num_envs, cfg.device, cfg.frame_skip = self.num_envs, self.device.index or 0, FRAME_SKIP
         cfg.flags = _lib.FLAG_LIFELONG if self._lifelong else 0
         cfg.episode_horizon = self._episode_horizon
+        cfg.goal_change_frequency = self._goal_change_frequency if self._lifelong else 0
         cfg.goal[:] = self.goal.tolist()
         cfg.init_qpos[:] = self.init_qpos.tolist()
         cfg.pos_noise_amp[:] = POS_NOISE_AMP.tolist()

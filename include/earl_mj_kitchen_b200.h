@@ -46,6 +46,7 @@ typedef struct {
   uint32_t flags;                 /* EARL_FLAG_LIFELONG */
   int32_t frame_skip;             /* 40 (KitchenV0.__init__, kitchen_multitask_v0.py:38) */
   int64_t episode_horizon;        /* PersistentStateWrapper(episode_horizon) */
+  int64_t goal_change_frequency;  /* LifelongWrapper(goal_change_frequency), lifelong_wrapper.py:19-24; 0 = unused */
   double goal[23];                /* ENV/kitchen.py:28-52 */
   double init_qpos[23];           /* kitchen_multitask_v0.py:65-70 */
   double pos_noise_amp[23];       /* franka/robot/franka_config.xml:17-45 */
@@ -71,7 +72,9 @@ EARL_API int earl_mjk_reset(earl_mjk_handle* h, const int32_t* env_ids_dev, int3
 /* One PersistentStateWrapper.step of every environment: KitchenV0.step (kitchen_multitask_v0.py:91-125: action clip and
  * scale, mocap update, Robot_VelAct control from the LAST NOISY observation, 40 x mj_step), the noisy observation
  * (franka_robot.py:137-168), Kitchen._get_reward_n_score / is_successful (ENV/kitchen.py:141-183), counters and horizon
- * done.  actions f32 [N,9]; obs f64 [N,46]; reward f64 [N]; done u8 [N]; success u8 [N] or NULL. */
+ * done.  With EARL_FLAG_LIFELONG also LifelongWrapper.step (lifelong_wrapper.py:30-44): lifelong_return += reward and,
+ * every goal_change_frequency steps, reset_goal() (one goal: no change) followed by env._get_obs() -- a SECOND noisy
+ * observation (46 more draws), which is the one returned and the one the next control is computed from.  actions f32 [N,9]; obs f64 [N,46]; reward f64 [N]; done u8 [N]; success u8 [N] or NULL. */
 EARL_API int earl_mjk_step(earl_mjk_handle* h, const float* actions_dev, double* obs_dev, double* reward_dev, uint8_t* done_dev,
                            uint8_t* success_dev, void* stream);
 /* sim state as host arrays (synchronous): qpos, qvel, qacc_warmstart f64 [N,23], mocap_pos f64 [N,3], last noisy robot

@@ -52,7 +52,7 @@ def test_kitchen_loader_surface():
     s = g.bit_generator.state["state"]
     assert int(st[0, 0]) == s["state"] >> 64 and int(st[0, 1]) == s["state"] & ((1 << 64) - 1) and int(st[0, 3]) == s["inc"] & ((1 << 64) - 1)
     import ctypes
-    assert ctypes.sizeof(kitchen.MjkConfig) == 976
+    assert ctypes.sizeof(kitchen.MjkConfig) == 984
 
 
 def test_states_and_demos(golden_dir):

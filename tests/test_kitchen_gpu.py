@@ -121,12 +121,25 @@ def test_loader_wrappers_counters_and_reset_draws():
     tr.reset(mask=[True, False, True, False])
     assert tr.num_interventions.tolist() == [2, 1, 2, 1] and tr.steps_since_reset.tolist() == [0, 3, 0, 3]
     assert bool(torch.all(tr.is_successful(ob) == info["success"]))
-    ll = eb.EARLEnvs("kitchen", reward_type="dense", setup_as_lifelong_learning=True, num_envs=2, seed=2).get_envs()
-    ll.reset()
+    ll = eb.EARLEnvs("kitchen", reward_type="dense", setup_as_lifelong_learning=True, num_envs=2, seed=2,
+                     goal_change_frequency=2).get_envs()
+    ll.seed(2)
+    ll.reset(config_index=[0, 0])
+    # LifelongWrapper on the checker: every 2nd step reset_goal() + env._get_obs() = a SECOND noisy observation, which is
+    # returned and cached for the next control (lifelong_wrapper.py:36-42)
+    k = _oracle(2)
+    k.logic.reset_state = lambda: (np.concatenate([KL.INIT_QPOS[:9], KL.ALL_PAIRS[0, 9:]]), 0)
+    k.reset()
     tot = torch.zeros(2, dtype=torch.float64, device="cuda")
-    for t in range(3):
-        ob, r, done, info = ll.step(torch.zeros((2, 9), device="cuda"))
+    rs = np.random.RandomState(4)
+    for t in range(5):
+        a = rs.uniform(-1, 1, (2, 9)).astype(np.float32)
+        ob, r, done, info = ll.step(torch.from_numpy(a).cuda())
         tot += r
+        ob_ref, r_ref, _ = k.step(a[0])
+        if t % 2 == 1:
+            ob_ref = k.logic.observe(k.e.qpos)
+        assert np.abs(ob[0].cpu().numpy() - ob_ref).max() < 1e-4 and abs(float(r[0]) - r_ref) < 1e-3
     assert torch.equal(ll.lifelong_return, tot)
 
 
