@@ -675,10 +675,12 @@ MJ_HD real impedance(const real* solimp, real pos, real margin) {
 // aref / R / D of row r from (solref, solimp, pos, margin, diagApprox); mj_makeImpedance + mj_referenceConstraint
 // `imp_pos` < 0: the impedance is evaluated at the row's own violation; >= 0: at this violation (vector residuals: the
 // six rows of a weld share the impedance of the residual's Euclidean norm, engine_core_constraint.c getposdim)
+// `vel_known`: J qvel of the row when the caller has it for free (rows with one or two non-zero Jacobian entries)
 MJ_FN void finish_row(const Model& m, Work& w, int r, const real* solref, const real* solimp, real margin, real diag, real* R_out,
-                      real imp_pos = -1.0f) {
+                      real imp_pos = -1.0f, const real* vel_known = nullptr) {
   real vel = 0;
-  for (int k = 0; k < m.nv; ++k) vel += w.J[r][k] * w.qvel[k];
+  if (vel_known) vel = *vel_known;
+  else for (int k = 0; k < m.nv; ++k) vel += w.J[r][k] * w.qvel[k];
   const real imp = impedance(solimp, imp_pos >= 0 ? imp_pos : w.e_pos[r], margin);
   const real dmax = clampr(solimp[1], MINIMP, MAXIMP);
   real k, b;
@@ -756,52 +758,88 @@ MJ_FN void make_constraints(const Model& m, Work& w, int lane) {
       finish_row(m, w, r + k, m.weld_solref[wi], m.weld_solimp[wi], 0.0f, m.weld_invweight[wi][k >= 3], nullptr, cnorm);
     r += 6;
   }
-  // --- joint equalities q1 - q1_0 = poly(q2 - q2_0) (mj_instantiateEquality, mjEQ_JOINT)
-  for (int e = 0; KITCHEN_ROWS && e < m.neq; ++e) {
-    if (r >= MAXEFC) { if (lane == 0) w.bad |= 8; break; }
-    const int q1 = m.eq_qposadr[e][0], q2 = m.eq_qposadr[e][1], d1 = m.eq_dofadr[e][0], d2 = m.eq_dofadr[e][1];
-    const real dif = w.qpos[q2] - m.qpos0[q2];
-    real pw = 1, cpos = w.qpos[q1] - m.qpos0[q1], deriv = 0;
-    for (int k = 0; k < 5; ++k) {
-      cpos -= m.eq_polycoef[e][k] * pw;
-      if (k < 4) deriv += (k + 1) * m.eq_polycoef[e][k + 1] * pw;
-      pw *= dif;
+  // --- joint equalities q1 - q1_0 = poly(q2 - q2_0) (mj_instantiateEquality, mjEQ_JOINT): one lane per equality
+  if (KITCHEN_ROWS && m.neq > 0) {
+    if (r + m.neq > MAXEFC) { if (lane == 0) w.bad |= 8; }
+    else {
+      for (int e = lane; e < m.neq; e += NL) {
+        const int q1 = m.eq_qposadr[e][0], q2 = m.eq_qposadr[e][1], d1 = m.eq_dofadr[e][0], d2 = m.eq_dofadr[e][1];
+        const real dif = w.qpos[q2] - m.qpos0[q2];
+        real pw = 1, cpos = w.qpos[q1] - m.qpos0[q1], deriv = 0;
+        for (int k = 0; k < 5; ++k) {
+          cpos -= m.eq_polycoef[e][k] * pw;
+          if (k < 4) deriv += (k + 1) * m.eq_polycoef[e][k + 1] * pw;
+          pw *= dif;
+        }
+        const int row = r + e;
+        for (int c = 0; c < nv; ++c) w.J[row][c] = c == d1 ? 1.0f : (c == d2 ? -deriv : 0.0f);
+        w.e_pos[row] = cpos;
+        w.e_type[row] = ROW_EQ;
+        const real vel = w.qvel[d1] - deriv * w.qvel[d2];
+        finish_row(m, w, row, m.eq_solref[e], m.eq_solimp[e], 0.0f, m.eq_invweight[e], nullptr, -1.0f, &vel);
+      }
+      r += m.neq;
     }
-    for (int c = lane; c < nv; c += NL) w.J[r][c] = c == d1 ? 1.0f : (c == d2 ? -deriv : 0.0f);
-    if (lane == 0) { w.e_pos[r] = cpos; w.e_type[r] = ROW_EQ; }
     wsync<NL>();
-    if (lane == 0) finish_row(m, w, r, m.eq_solref[e], m.eq_solimp[e], 0.0f, m.eq_invweight[e], nullptr);
-    ++r;
   }
-  // --- dof friction loss (mj_instantiateFriction): one row per dof with frictionloss > 0, residual 0
-  for (int i = 0; KITCHEN_ROWS && i < nv; ++i) {
-    if (!(m.dof_frictionloss[i] > 0)) continue;
-    if (r >= MAXEFC) { if (lane == 0) w.bad |= 8; break; }
-    for (int c = lane; c < nv; c += NL) w.J[r][c] = c == i ? 1.0f : 0.0f;
-    if (lane == 0) { w.e_pos[r] = 0; w.e_type[r] = ROW_FRICTION; }
-    wsync<NL>();
-    if (lane == 0) {
-      finish_row(m, w, r, m.dof_solref_friction[i], m.dof_solimp_friction[i], 0.0f, m.dof_invweight0[i], nullptr);
-      w.e_pos[r] = m.dof_frictionloss[i];  // from here on e_pos of a friction row is its force bound
+  // --- dof friction loss (mj_instantiateFriction): one row per dof with frictionloss > 0, residual 0; one lane per dof
+  if (KITCHEN_ROWS) {
+    int nf = 0;
+    for (int i = 0; i < nv; ++i) nf += m.dof_frictionloss[i] > 0;
+    if (r + nf > MAXEFC) { if (lane == 0 && nf) w.bad |= 8; }
+    else if (nf) {
+      for (int i = lane; i < nv; i += NL) {
+        if (!(m.dof_frictionloss[i] > 0)) continue;
+        int k = 0;
+        for (int j = 0; j < i; ++j) k += m.dof_frictionloss[j] > 0;
+        const int row = r + k;
+        for (int c = 0; c < nv; ++c) w.J[row][c] = c == i ? 1.0f : 0.0f;
+        w.e_pos[row] = 0;
+        w.e_type[row] = ROW_FRICTION;
+        const real vel = w.qvel[i];
+        finish_row(m, w, row, m.dof_solref_friction[i], m.dof_solimp_friction[i], 0.0f, m.dof_invweight0[i], nullptr, -1.0f, &vel);
+        w.e_pos[row] = m.dof_frictionloss[i];  // from here on e_pos of a friction row is its force bound
+      }
+      r += nf;
     }
-    ++r;
+    wsync<NL>();
   }
-  // --- joint limits (hinge / slide); row allocation is uniform across lanes
-  for (int j = 0; j < m.njnt; ++j) {
-    if (!m.jnt_limited[j] || m.jnt_type[j] < 2) continue;
-    const int qa = m.jnt_qposadr[j], da = m.jnt_dofadr[j];
-    for (int side = 0; side < 2; ++side) {
-      const real dist = side == 0 ? w.qpos[qa] - m.jnt_range[j][0] : m.jnt_range[j][1] - w.qpos[qa];
-      if (dist < m.jnt_margin[j] && r >= MAXEFC && lane == 0) w.bad |= 8;
-      if (dist < m.jnt_margin[j] && r < MAXEFC) {
-        for (int c = lane; c < nv; c += NL) w.J[r][c] = (c == da) ? (side == 0 ? 1.0f : -1.0f) : 0.0f;
-        if (lane == 0) { w.e_pos[r] = dist; w.e_type[r] = ROW_LIMIT; }
-        wsync<NL>();
-        if (lane == 0) finish_row(m, w, r, m.jnt_solref[j], m.jnt_solimp[j], m.jnt_margin[j], m.dof_invweight0[da], nullptr);
-        ++r;
+  // --- joint limits (hinge / slide): candidates (joint, side) in order, one lane each; rows are allocated by a prefix
+  // count over the active ones, so the row order is that of the serial loop
+  const int ncand = 2 * m.njnt;
+  for (int base = 0; base < ncand; base += NL) {
+    const int idx = base + lane, j = idx >> 1, side = idx & 1;
+    bool act = false;
+    real dist = 0;
+    if (idx < ncand && m.jnt_limited[j] && m.jnt_type[j] >= 2) {
+      const int qa = m.jnt_qposadr[j];
+      dist = side == 0 ? w.qpos[qa] - m.jnt_range[j][0] : m.jnt_range[j][1] - w.qpos[qa];
+      act = dist < m.jnt_margin[j];
+    }
+#if defined(__CUDA_ARCH__)
+    const unsigned mask = NL > 1 ? __ballot_sync(0xffffffffu, act) : (act ? 1u : 0u);
+    const int before = __popc(mask & ((1u << lane) - 1u)), cnt = __popc(mask);
+#else
+    const int before = 0, cnt = act ? 1 : 0;
+#endif
+    if (act) {
+      const int row = r + before;
+      if (row < MAXEFC) {
+        const int da = m.jnt_dofadr[j];
+        const real sgn = side == 0 ? 1.0f : -1.0f;
+        for (int c = 0; c < nv; ++c) w.J[row][c] = c == da ? sgn : 0.0f;
+        w.e_pos[row] = dist;
+        w.e_type[row] = ROW_LIMIT;
+        const real vel = sgn * w.qvel[da];
+        finish_row(m, w, row, m.jnt_solref[j], m.jnt_solimp[j], m.jnt_margin[j], m.dof_invweight0[da], nullptr, -1.0f, &vel);
+      } else {
+        w.bad |= 8;
       }
     }
+    r += cnt;
+    if (r > MAXEFC) r = MAXEFC;
   }
+  wsync<NL>();
   w.nefc = r;
   wsync<NL>();
 }
