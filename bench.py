@@ -20,7 +20,7 @@ One JSON line on stdout (rank 0):
                actions; env-steps/s, e2e with host buffers, FP32-issue roofline from the checker's flop count, CPU
                baseline (fp64 C restatement of the engine, one process per host core)
   sawyer_peg   third section (BASELINE.json configs[3]): the same for the Sawyer peg task (free-joint peg, nv = 15)
-  kitchen      fourth section (configs[4]): batched Franka kitchen step, 11,840 envs per GPU, 40 substeps per env step
+  kitchen      fourth section (configs[4]): batched Franka kitchen step, 14,208 envs per GPU, 40 substeps per env step
 `--impl reference` times that CPU port alone on the same config (the reference itself is Python over
 mujoco-py and cannot run on the GPU box).
 """
@@ -257,11 +257,11 @@ def run_door(dev, rank, world, sm_max_mhz, sm_count, with_cpu, task="sawyer_door
     return out
 
 
-KITCHEN_ENVS, KITCHEN_STEPS, KITCHEN_WARMUP = 11840, 8, 3
+KITCHEN_ENVS, KITCHEN_STEPS, KITCHEN_WARMUP = 14208, 8, 3
 
 
 def run_kitchen(dev, rank, world, sm_max_mhz, sm_count, with_cpu):
-    """Fourth bench section: batched kitchen step (BASELINE.json configs[4]): 11,840 envs per GPU (= 148 SMs x 5 resident
+    """Fourth bench section: batched kitchen step (BASELINE.json configs[4]): 14,208 envs per GPU (= 148 SMs x 6 resident
     environments x 16 waves), random actions after a full reset (400 settle substeps per env)."""
     import torch
     import torch.distributed as dist
@@ -311,7 +311,7 @@ def run_kitchen(dev, rank, world, sm_max_mhz, sm_count, with_cpu):
                         "contacts_per_substep": (w1["contacts"] - w0["contacts"]) / sub,
                         "bad_states": w1["bad_states"] - w0["bad_states"],
                         "overflow_states": w1["overflow_states"] - w0["overflow_states"]},
-               "kernel": "mjk_task_kernel (one warp per env, 5 envs per SM in flight, model tables in global memory)"}
+               "kernel": "mjk_task_kernel (one warp per env, 6 envs per SM in flight, model tables in global memory)"}
         if with_cpu:
             procs = os.cpu_count() or 1
             rate, flops, wall = door_cpu_rate(procs, steps_per_proc=1500, task="kitchen")
@@ -323,7 +323,7 @@ def run_kitchen(dev, rank, world, sm_max_mhz, sm_count, with_cpu):
             out["roofline"] = {"bound": "fp32", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
                                "algorithmic_flops_per_env_step": flops,
                                "peak_source": f"{sm_count} SMs x 128 lanes x 2 x {sm_max_mhz or 1965.0:.0f} MHz (nominal FP32 FMA issue)",
-                               "note": "first device version of this capacity set: 5 warps per SM, 2,974 candidate pairs tested per "
+                               "note": "first device version of this capacity set: 6 warps per SM, 2,974 candidate pairs tested per "
                                        "substep; latency bound"}
     del env
     return out

@@ -1,7 +1,7 @@
 // earl_mj_kitchen.cu -- the kitchen capacity set of the articulated-body engine (24 dofs, 128 geoms, 192 rows, 24
 // contacts; joint-equality / friction-loss / pyramidal rows, capsule geoms) and its ENGINE-LEVEL entry points
-// (include/earl_mj_kitchen_b200.h).  One warp per environment; the 40.7 KB workspace of an environment lives in shared
-// memory (5 environments in flight per SM), the 62 KB model stays in global memory (L1 / L2 resident: every block reads
+// (include/earl_mj_kitchen_b200.h).  One warp per environment; the 37.1 KB workspace of an environment lives in shared
+// memory (6 environments in flight per SM), the 37 KB model stays in global memory (L1 / L2 resident: every block reads
 // the same tables).  No CPU fallback.
 #define MJ_CAPSET_KITCHEN 1
 #define mj mjk  // engine namespace of this translation unit: no symbol is shared with the door / peg capacity sets
@@ -43,7 +43,7 @@ int failf(int code, const char* fmt, ...) {
   } while (0)
 
 #ifndef MJK_WPB
-#define MJK_WPB 5
+#define MJK_WPB 6
 #endif
 constexpr int kWPB = MJK_WPB;  // warps (= environments in flight) per block
 constexpr size_t kWorkStride = (sizeof(Work) + 15) & ~size_t(15);

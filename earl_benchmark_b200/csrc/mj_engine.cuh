@@ -72,7 +72,7 @@ constexpr int MAXEFC = 192; // constraint rows (6 weld + 5 equality + 23 frictio
 constexpr int MAXCON = 24;  // contacts
 constexpr int MAXHIT = 64;  // candidate pairs that survive the broad phase in one substep
 constexpr int MAXPAIR = 4096; // candidate geom pairs
-constexpr int MAXMG = 96;    // geoms on moving bodies (their world poses are recomputed every substep)
+constexpr int MAXMG = 64;    // geoms on moving bodies (their world poses are recomputed every substep)
 #else
 #if defined(MJ_CAPSET_LARGE)
 constexpr int MAXEFC = 96;  // constraint rows
@@ -187,7 +187,7 @@ struct Work {
     struct { real c_mass[MAXB], c_com[MAXB][3], c_I[MAXB][6]; } crb;
   };
   real e_pos[MAXEFC], e_aref[MAXEFC], e_D[MAXEFC], e_R[MAXEFC], e_jar[MAXEFC], e_jv[MAXEFC], e_force[MAXEFC];
-  int e_type[MAXEFC], e_state[MAXEFC];
+  unsigned char e_type[MAXEFC], e_state[MAXEFC];
   // collision
   // world poses of the geoms on moving bodies: written and read by the collision phase only, so the same storage
   // holds the cone Hessian blocks (dim x dim, dim <= 4; middle zone) that only the solve phase touches
