@@ -69,7 +69,7 @@ mjk_substeps_kernel(const Model* __restrict__ gm, const real* __restrict__ hull,
       for (int k = 0; k < 3; ++k) w.mocap_pos[k] = mocap_pos[(size_t)env * 3 + k];
       w.mocap_quat[0] = mocap_quat.x; w.mocap_quat[1] = mocap_quat.y; w.mocap_quat[2] = mocap_quat.z; w.mocap_quat[3] = mocap_quat.w;
       for (int k = 0; k < m.nu; ++k) w.ctrl[k] = ctrl[(size_t)env * m.nu + k];
-      w.bad = 0; w.acc_iter = w.acc_rows = w.acc_con = w.acc_mpr = w.acc_sup = 0;
+      w.bad = 0; w.acc_iter = w.acc_rows = w.acc_con = w.acc_mpr = w.acc_sup = 0; w.broad_valid = 0;
     }
     __syncwarp();
     for (int s = 0; s < nsub; ++s) substep<32>(m, hull, w, lane);
@@ -191,7 +191,7 @@ __device__ __forceinline__ void task_load(const TaskArgs& a, Work& w, int env, i
   if (lane == 0) {
     for (int k = 0; k < 3; ++k) w.mocap_pos[k] = a.mocap[(size_t)env * 3 + k];
     w.mocap_quat[0] = a.mocap_quat.x; w.mocap_quat[1] = a.mocap_quat.y; w.mocap_quat[2] = a.mocap_quat.z; w.mocap_quat[3] = a.mocap_quat.w;
-    w.bad = 0; w.acc_iter = w.acc_rows = w.acc_con = w.acc_mpr = w.acc_sup = 0;
+    w.bad = 0; w.acc_iter = w.acc_rows = w.acc_con = w.acc_mpr = w.acc_sup = 0; w.broad_valid = 0;
   }
   __syncwarp();
 }
@@ -230,7 +230,7 @@ mjk_task_kernel(const Model* __restrict__ gm, const real* __restrict__ hull, con
       if (lane == 0) {
         for (int k = 0; k < 3; ++k) w.mocap_pos[k] = a.midpoint[k];
         w.mocap_quat[0] = a.mocap_quat.x; w.mocap_quat[1] = a.mocap_quat.y; w.mocap_quat[2] = a.mocap_quat.z; w.mocap_quat[3] = a.mocap_quat.w;
-        w.bad = 0; w.acc_iter = w.acc_rows = w.acc_con = w.acc_mpr = w.acc_sup = 0;
+        w.bad = 0; w.acc_iter = w.acc_rows = w.acc_con = w.acc_mpr = w.acc_sup = 0; w.broad_valid = 0;
       }
       __syncwarp();
     } else {

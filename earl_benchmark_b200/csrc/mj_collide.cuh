@@ -613,6 +613,7 @@ MJ_FN void compact_append(Work& w, int item, int flag, int lane) {
 #if defined(__CUDA_ARCH__)
   if (NL > 1) {
     const unsigned mask = __ballot_sync(0xffffffffu, flag);
+    if (mask == 0) return;  // nothing to append in this pass (the common case): no shared-memory traffic, no barriers
     const int base = w.nhit;
     const int pos = base + __popc(mask & ((1u << lane) - 1u));
     if (flag && pos < MAXHIT) w.hit_list[pos] = (unsigned short)item;
@@ -628,51 +629,119 @@ MJ_FN void compact_append(Work& w, int item, int flag, int lane) {
   }
 }
 
+// same for the cached candidate list of the loose broad phase; an overflow invalidates the cache (exactness first)
+template <int NL>
+MJ_FN void cand_append(Work& w, int item, int flag, int lane) {
+#if defined(__CUDA_ARCH__)
+  if (NL > 1) {
+    const unsigned mask = __ballot_sync(0xffffffffu, flag);
+    if (mask == 0) return;
+    const int base = w.ncand;
+    const int pos = base + __popc(mask & ((1u << lane) - 1u));
+    if (flag && pos < MAXCAND) w.cand_list[pos] = (unsigned short)item;
+    __syncwarp();
+    if (lane == 0) { const int n = base + __popc(mask); w.ncand = n < MAXCAND ? n : MAXCAND; if (n > MAXCAND) w.broad_valid = 0; }
+    __syncwarp();
+    return;
+  }
+#endif
+  if (flag) {
+    if (w.ncand < MAXCAND) w.cand_list[w.ncand++] = (unsigned short)item;
+    else w.broad_valid = 0;
+  }
+}
+
+// exact broad-phase test of candidate pair p (`slack` = 0), or its loose form (bounding spheres / plane distance inflated by
+// `slack`, no box culls) used to build the cached candidate list
+MJ_HD int pair_test(const Model& m, const Work& w, int p, real slack) {
+  const int ga = m.pair_g1[p], gb = m.pair_g2[p];
+  const real margin = fmaxf(m.geom_margin[ga], m.geom_margin[gb]) + slack;
+  const int t1 = m.geom_type[ga], t2 = m.geom_type[gb];
+  const real* pa = gpos(m, w, ga);
+  const real* pb = gpos(m, w, gb);
+  real rel[3];
+  sub3(rel, pb, pa);
+  int hit;
+  if (t1 == GEOM_PLANE) {
+    const real* Rp = gmat(m, w, ga);
+    const real n[3] = {Rp[2], Rp[5], Rp[8]};
+    return t2 != GEOM_PLANE && dot3(rel, n) <= m.geom_rbound[gb] + margin;
+  }
+  const real bound = m.geom_rbound[ga] + m.geom_rbound[gb] + margin;
+  hit = dot3(rel, rel) <= bound * bound;  // MuJoCo's bounding-sphere test
+  if (slack > 0) return hit;
+  // exact cull: a geom whose bounding sphere stays clear of the other geom's box cannot touch it
+  if (hit && t1 == GEOM_BOX) {
+    const real r = m.geom_rbound[gb] + margin;
+    hit = point_box_dist2(pb, pa, gmat(m, w, ga), m.geom_size[ga]) <= r * r;
+  }
+  if (hit && t2 == GEOM_BOX) {
+    const real r = m.geom_rbound[ga] + margin;
+    hit = point_box_dist2(pa, pb, gmat(m, w, gb), m.geom_size[gb]) <= r * r;
+  }
+  if (hit) {  // bounding-box cull
+    const real* Ra = gmat(m, w, ga);
+    const real* Rb = gmat(m, w, gb);
+    real ca[3], cb[3];
+    mulmatvec3(ca, Ra, m.geom_obb_off[ga]);
+    mulmatvec3(cb, Rb, m.geom_obb_off[gb]);
+    for (int k = 0; k < 3; ++k) { ca[k] += pa[k]; cb[k] += pb[k]; }
+    hit = !obb_separated(ca, Ra, m.geom_obb_size[ga], cb, Rb, m.geom_obb_size[gb], margin);
+  }
+  return hit;
+}
+
 template <int NL>
 MJ_FN void collide(const Model& m, const real* hull, Work& w, int lane) {
   geom_poses<NL>(m, w, lane);
   if (lane == 0) { w.ncon = 0; w.nhit = 0; }
   wsync<NL>();
-  // broad phase, lane-parallel over the candidate pairs (already ordered by geom type on the host)
-  for (int p0 = 0; p0 < m.npair; p0 += NL) {
-    const int p = p0 + lane;
-    int hit = 0;
-    if (p < m.npair) {
-      const int ga = m.pair_g1[p], gb = m.pair_g2[p];
-      const real margin = fmaxf(m.geom_margin[ga], m.geom_margin[gb]);
-      const int t1 = m.geom_type[ga], t2 = m.geom_type[gb];
-      const real* pa = gpos(m, w, ga);
-      const real* pb = gpos(m, w, gb);
-      real rel[3];
-      sub3(rel, pb, pa);
-      if (t1 == GEOM_PLANE) {
-        const real* Rp = gmat(m, w, ga);
-        const real n[3] = {Rp[2], Rp[5], Rp[8]};
-        hit = t2 != GEOM_PLANE && dot3(rel, n) <= m.geom_rbound[gb] + margin;
-      } else {
-        const real bound = m.geom_rbound[ga] + m.geom_rbound[gb] + margin;
-        hit = dot3(rel, rel) <= bound * bound;  // MuJoCo's bounding-sphere test
-        // exact cull: a geom whose bounding sphere stays clear of the other geom's box cannot touch it
-        if (hit && t1 == GEOM_BOX) {
-          const real r = m.geom_rbound[gb] + margin;
-          hit = point_box_dist2(pb, pa, gmat(m, w, ga), m.geom_size[ga]) <= r * r;
-        }
-        if (hit && t2 == GEOM_BOX) {
-          const real r = m.geom_rbound[ga] + margin;
-          hit = point_box_dist2(pa, pb, gmat(m, w, gb), m.geom_size[gb]) <= r * r;
-        }
-        if (hit) {  // bounding-box cull
-          const real* Ra = gmat(m, w, ga);
-          const real* Rb = gmat(m, w, gb);
-          real ca[3], cb[3];
-          mulmatvec3(ca, Ra, m.geom_obb_off[ga]);
-          mulmatvec3(cb, Rb, m.geom_obb_off[gb]);
-          for (int k = 0; k < 3; ++k) { ca[k] += pa[k]; cb[k] += pb[k]; }
-          hit = !obb_separated(ca, Ra, m.geom_obb_size[ga], cb, Rb, m.geom_obb_size[gb], margin);
-        }
+  if (BROAD_CACHE) {
+    // Cached broad phase (kitchen: 2,974 candidate pairs).  A loose pass over ALL pairs (bounding spheres inflated by
+    // BROAD_SLACK) builds a candidate list that stays a superset of the exact hits for as long as no geom centre has
+    // moved by more than BROAD_SLACK / 2: the travel since the last loose pass is bounded rigorously from the joint
+    // motion, sum_i lever_i |h qvel_i| with lever_i = reach of dof i's subtree (host, Model::dof_lever), and the list
+    // is rebuilt when the bound is used up.  Every substep then runs the EXACT tests on the candidates only, in pair
+    // order, so the hit list -- hence the contacts -- is identical to testing all pairs.
+    real step = 0;
+    for (int i = lane; i < m.nv; i += NL) step += m.dof_lever[i] * mabs(m.timestep * w.qvel[i]);
+    step = wsum<NL>(step);
+    const real travel = w.broad_travel + step;
+    const bool rebuild = !w.broad_valid || travel > 0.5f * BROAD_SLACK;
+    wsync<NL>();
+    if (rebuild) {
+      if (lane == 0) { w.ncand = 0; w.broad_valid = 1; w.broad_travel = 0; }
+      wsync<NL>();
+      for (int p0 = 0; p0 < m.npair; p0 += NL) {
+        const int p = p0 + lane;
+        const int hit = p < m.npair ? pair_test(m, w, p, BROAD_SLACK) : 0;
+        cand_append<NL>(w, p, hit, lane);
+      }
+      wsync<NL>();
+    } else if (lane == 0) {
+      w.broad_travel = travel;
+    }
+    wsync<NL>();
+    if (w.broad_valid) {
+      const int nc = w.ncand;
+      for (int c0 = 0; c0 < nc; c0 += NL) {
+        const int c = c0 + lane;
+        const int p = c < nc ? (int)w.cand_list[c] : 0;
+        const int hit = c < nc ? pair_test(m, w, p, 0.0f) : 0;
+        compact_append<NL>(w, p, hit, lane);
+      }
+    } else {  // candidate list overflowed: this substep tests every pair
+      for (int p0 = 0; p0 < m.npair; p0 += NL) {
+        const int p = p0 + lane;
+        compact_append<NL>(w, p, p < m.npair ? pair_test(m, w, p, 0.0f) : 0, lane);
       }
     }
-    compact_append<NL>(w, p, hit, lane);
+  } else {
+    // broad phase, lane-parallel over the candidate pairs (already ordered by geom type on the host)
+    for (int p0 = 0; p0 < m.npair; p0 += NL) {
+      const int p = p0 + lane;
+      compact_append<NL>(w, p, p < m.npair ? pair_test(m, w, p, 0.0f) : 0, lane);
+    }
   }
   wsync<NL>();
   // narrow phase: surviving pairs one after the other, uniform across the warp

@@ -62,9 +62,14 @@ constexpr int MAXEQ = 8;    // joint equalities
 // those branches at compile time (they cost 3.5 % of the step when left in)
 #if defined(MJ_CAPSET_KITCHEN)
 constexpr bool KITCHEN_ROWS = true;
+constexpr bool BROAD_CACHE = true;   // cached broad phase (mj_collide.cuh: collide)
+constexpr int MAXCAND = 160;         // cached candidate pairs
 #else
 constexpr bool KITCHEN_ROWS = false;
+constexpr bool BROAD_CACHE = false;
+constexpr int MAXCAND = 1;
 #endif
+constexpr float BROAD_SLACK = 0.03f;  // inflation of the cached broad phase (m)
 // Two capacity sets are compiled from these sources (earl_mj_small.cu / earl_mj_large.cu): the workspace of one
 // environment lives in shared memory, so rows x dofs and contacts decide how many environments one SM keeps in flight.
 #if defined(MJ_CAPSET_KITCHEN)
@@ -116,6 +121,7 @@ struct Model {
   int dof_body[MAXV], dof_rot[MAXV], dof_parent[MAXV];
   real dof_damping[MAXV], dof_armature[MAXV], dof_invweight0[MAXV];
   real dof_frictionloss[MAXV], dof_solref_friction[MAXV][2], dof_solimp_friction[MAXV][5];
+  real dof_lever[MAXV];  // bound on the motion of any geom centre per unit motion of the dof (cached broad phase)
   real qpos0[MAXQ];
   // joint equalities q1 - q1_0 = poly(q2 - q2_0) and the friction-cone type (blob version 2: kitchen)
   int neq, cone_elliptic;
@@ -197,6 +203,10 @@ struct Work {
   };
   int nhit;
   unsigned short hit_list[MAXHIT];
+  // cached broad phase (BROAD_CACHE): candidates of the last loose pass and the travel bound used up since
+  unsigned short cand_list[MAXCAND];
+  int ncand, broad_valid;
+  real broad_travel;
   // contacts
   real con_pos[MAXCON][3], con_frame[MAXCON][9], con_dist[MAXCON], con_fri[MAXCON][5], con_mu[MAXCON];
   int con_g1[MAXCON], con_g2[MAXCON], con_dim[MAXCON], con_row[MAXCON];

@@ -9,6 +9,7 @@
 #include <string>
 #include <vector>
 
+#include <algorithm>
 #include <cmath>
 
 #include "mj_collide.cuh"
@@ -324,6 +325,37 @@ inline bool build_model(const void* blob, size_t nbytes, const TaskSpec& task, H
     } else {
       m.dof_rot[da] = m.jnt_type[j] == 3;
       m.dof_parent[da] = pd;
+    }
+  }
+  // dof_lever (cached broad phase): how far any geom CENTRE of the dof's subtree can move per unit motion of the dof.
+  // reach[b] bounds the distance from body b's origin to every geom centre of its subtree in every configuration.
+  {
+    std::vector<double> reach(nb, 0.0);
+    auto norm3 = [](const real* v) { return std::sqrt((double)v[0] * v[0] + (double)v[1] * v[1] + (double)v[2] * v[2]); };
+    for (int g = 0; g < ng; ++g) {
+      const int b = m.geom_body[g];
+      if (b > 0) reach[b] = std::max(reach[b], norm3(m.geom_pos[g]));
+    }
+    for (int b = nb - 1; b > 0; --b) {  // parents precede children
+      const int pb = m.body_parent[b], j = m.body_jnt[b];
+      if (pb <= 0) continue;
+      double ext = norm3(m.body_pos[b]) + reach[b];
+      if (j >= 0) {
+        ext += 2.0 * norm3(m.jnt_pos[j]);
+        if (m.jnt_type[j] == 2) ext += std::max(std::fabs((double)m.jnt_range[j][0]), std::fabs((double)m.jnt_range[j][1]));
+        if (m.jnt_type[j] == 2 && !m.jnt_limited[j]) ext += 1e3;  // unlimited slide: no bound, the cache never holds
+      }
+      reach[pb] = std::max(reach[pb], ext);
+    }
+    for (int j = 0; j < m.njnt; ++j) {
+      const int da = m.jnt_dofadr[j], b = m.jnt_body[j];
+      if (m.jnt_type[j] == 0) {
+        for (int k = 0; k < 3; ++k) { m.dof_lever[da + k] = 1.0f; m.dof_lever[da + 3 + k] = (real)reach[b]; }
+      } else if (m.jnt_type[j] == 3) {
+        m.dof_lever[da] = (real)(norm3(m.jnt_pos[j]) + reach[b]);
+      } else {
+        m.dof_lever[da] = 1.0f;
+      }
     }
   }
   // bounding boxes in the geom frames (broad-phase cull)

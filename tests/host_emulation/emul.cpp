@@ -40,6 +40,7 @@ void emu_set_state(void* h, const double* qpos, const double* qvel, const double
   for (int k = 0; k < 3; ++k) e->w.mocap_pos[k] = mocap_pos[k];
   for (int k = 0; k < 4; ++k) e->w.mocap_quat[k] = (real)mocap_quat[k];
   for (int k = 0; k < m.nu; ++k) e->w.ctrl[k] = (real)ctrl[k];
+  e->w.broad_valid = 0;  // a new state: the cached broad-phase candidates are stale
 }
 void emu_get_state(void* h, double* qpos, double* qvel, double* warm, double* mocap_pos) {
   Emu* e = static_cast<Emu*>(h);

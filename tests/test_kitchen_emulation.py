@@ -91,3 +91,43 @@ def test_contact_rich_substep_parity(pair):
     # isolated substeps where the two Newton solves stop on different sides of a friction-loss / pyramid branch are
     # larger (worst seen 9e-2 on a wrist dof); they are bounded, not hidden
     assert p50 < 1e-5 and p99 < 1e-4 and p999 < 1e-3 and dv.max() < 0.5, (p50, p99, p999, dv.max())
+
+
+def test_cached_broad_phase_is_exact(pair):
+    """40 substeps in one go (the candidate cache of the broad phase is live and rebuilt when its travel bound is used up)
+    against the same 40 substeps with the state re-loaded before each (cache invalid: every substep tests all 2,974
+    pairs): bitwise identical states and contact sets, in free motion and deep in the cabinets."""
+    m, em = pair
+    em2 = Emu(m, kitchen_task(m), capset="kitchen")
+    k = KitchenOracle(m)
+    k.seed(3)
+    np.random.seed(2)
+    k.reset()
+    e = k.e
+    target = e.site_xpos("slide_site").copy()
+    checked = 0
+    for t in range(96):
+        d = target - e.site_xpos("end_effector")
+        if t >= 70:
+            d = np.array([0.5, 0.0, 0.0])
+        a = np.zeros(9)
+        a[:3] = np.clip(d * 10, -1, 1) * 0.5
+        mocap, ctrl = k.logic.control(a, e.mocap_pos.copy())
+        e.mocap_pos[:], e.ctrl[:] = mocap, ctrl
+        if t % 8 == 7:
+            _sync(em, e)
+            _sync(em2, e)
+            em.substeps(KL.FRAME_SKIP)
+            for _ in range(KL.FRAME_SKIP):
+                q, v, w, mp = em2.get_state()
+                em2.set_state(q, v, w, mp, mocap_quat=e.mocap_quat, ctrl=e.ctrl)
+                em2.substeps(1)
+            s1, s2 = em.get_state(), em2.get_state()
+            assert all(np.array_equal(x, y) for x, y in zip(s1, s2)), t
+            c1, c2 = em.contacts(), em2.contacts()
+            assert all(np.array_equal(x, y) for x, y in zip(c1, c2))
+            assert em.info("bad") == 0
+            checked += 1
+        e.step(KL.FRAME_SKIP)
+        k.logic.observe(e.qpos)
+    assert checked == 12
