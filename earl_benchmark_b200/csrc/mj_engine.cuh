@@ -69,7 +69,10 @@ constexpr bool KITCHEN_ROWS = false;
 constexpr bool BROAD_CACHE = false;
 constexpr int MAXCAND = 1;
 #endif
-constexpr float BROAD_SLACK = 0.03f;  // inflation of the cached broad phase (m)
+#ifndef MJ_BROAD_SLACK
+#define MJ_BROAD_SLACK 0.015f
+#endif
+constexpr float BROAD_SLACK = MJ_BROAD_SLACK;  // inflation of the cached broad phase (m)
 // Two capacity sets are compiled from these sources (earl_mj_small.cu / earl_mj_large.cu): the workspace of one
 // environment lives in shared memory, so rows x dofs and contacts decide how many environments one SM keeps in flight.
 #if defined(MJ_CAPSET_KITCHEN)
