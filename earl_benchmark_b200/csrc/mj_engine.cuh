@@ -244,7 +244,7 @@ MJ_HD void wsync() {
 // caches instead of each walking a different part of a large program
 template <int NL>
 MJ_HD void bsync() {
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDA_ARCH__) && !defined(MJ_NO_PHASE_BARRIERS)
   if (NL > 1) __syncthreads();
 #endif
 }
