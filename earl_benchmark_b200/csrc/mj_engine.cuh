@@ -53,7 +53,7 @@ constexpr int MAXV = 16;    // dofs
 constexpr int MAXQ = 20;    // generalized coordinates
 constexpr int MAXJ = 12;    // joints
 constexpr int MAXG = 32;    // geoms kept on the device
-constexpr int MAXS = 8;     // sites kept on the device
+constexpr int MAXS = 12;    // sites kept on the device
 #endif
 constexpr int MAXU = 2;     // actuators
 constexpr int MAXW = 1;     // welds
@@ -154,6 +154,7 @@ struct Model {
   int obs_hand_site, obs_ree_site, obs_lee_site, obs_obj_geom, obs_obj_site;
   real mocap_low[3], mocap_high[3], action_scale, success_radius;
   real obj_init_pos[3], hand_init_pos[3];
+  int grasp_site, lpad_site, rpad_site, corner_site[4];  // dense peg reward
 };
 
 // ------------------------------------------------------------------------------------------------ per-env record
@@ -216,6 +217,7 @@ struct Work {
   // task layer
   real action[4], obs7[8];
   unsigned steps, flags, goalrow;
+  real spare[3];  // record floats 61..63: self.obj_init_pos of the last reset (dense peg reward)
   // diagnostics
   int solver_iter;
   int bad;  // bit 0: numerical failure (non-positive pivot); capacity overflows: bit 1 candidate pairs, bit 2 contacts, bit 3 rows

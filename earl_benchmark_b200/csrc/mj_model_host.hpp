@@ -34,6 +34,7 @@ struct TaskSpec {
   float success_radius;    // 0.02 door (sawyer_door.py:177), 0.05 peg (sawyer_peg.py:305)
   float obj_init_pos[3];   // dense door reward (sawyer_door.py:150)
   float hand_init_pos[3];  // dense door reward (sawyer_door.py:156)
+  int32_t grasp_site, lpad_site, rpad_site, corner_site[4];  // dense peg reward (sawyer_peg.py:231-299); -1 when unused
 };
 
 class BlobReader {
@@ -418,6 +419,12 @@ inline bool build_model(const void* blob, size_t nbytes, const TaskSpec& task, H
   m.action_scale = task.action_scale;
   m.success_radius = task.success_radius;
   for (int k = 0; k < 3; ++k) { m.obj_init_pos[k] = task.obj_init_pos[k]; m.hand_init_pos[k] = task.hand_init_pos[k]; }
+  m.grasp_site = task.grasp_site; m.lpad_site = task.lpad_site; m.rpad_site = task.rpad_site;
+  for (int k = 0; k < 4; ++k) m.corner_site[k] = task.corner_site[k];
+  {
+    const int ids[7] = {task.grasp_site, task.lpad_site, task.rpad_site, task.corner_site[0], task.corner_site[1], task.corner_site[2], task.corner_site[3]};
+    for (int k = 0; k < 7; ++k) if (ids[k] >= ns) return bad("task spec: dense-reward site index out of range");
+  }
   if (task.hand_site < 0 || task.hand_site >= ns || task.ree_site < 0 || task.ree_site >= ns || task.lee_site < 0 ||
       task.lee_site >= ns || (task.obj_geom < 0 && (task.obj_site < 0 || task.obj_site >= ns)) || task.obj_geom >= ng)
     return bad("task spec: observation site / geom index out of range");

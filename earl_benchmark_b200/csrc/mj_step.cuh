@@ -158,5 +158,89 @@ MJ_HD real door_dense_reward(const Model& m, const real* obs7, const real* targe
   return 3.0f * tolerance_gaussian(d_to, 0.25f * TARGET_RADIUS, m_hand) + 6.0f * tolerance_gaussian(d_ot, TARGET_RADIUS, m_in);
 }
 
+
+// metaworld reward_utils [metaworld@master, not under /root/reference; formulas as in SURVEY.md Appendix C]:
+// tolerance(x, bounds=(lower, upper), margin, sigmoid='long_tail', value_at_margin=0.1)
+MJ_HD real tolerance_long_tail(real x, real lower, real upper, real margin) {
+  if (x >= lower && x <= upper) return 1.0f;
+  if (margin == 0) return 0.0f;
+  const real d = (x < lower ? lower - x : x - upper) / margin;
+  return 1.0f / (d * d * 9.0f + 1.0f);  // scale^2 = 1 / 0.1 - 1
+}
+// hamacher_product(a, b) = ab / (a + b - ab), 0 when the denominator is 0
+MJ_HD real hamacher(real a, real b) {
+  const real den = a + b - a * b;
+  return den > 0 ? a * b / den : 0.0f;
+}
+// rect_prism_tolerance(curr, zero, one): inside the prism spanned by the corners `zero` and `one` the product of the
+// normalised coordinates (0 at `zero`, 1 at `one`), outside 1
+MJ_HD real rect_prism_tolerance(const real* curr, const real* zero, const real* one) {
+  real prod = 1;
+  for (int k = 0; k < 3; ++k) {
+    const bool in = one[k] >= zero[k] ? (zero[k] <= curr[k] && curr[k] <= one[k]) : (one[k] <= curr[k] && curr[k] <= zero[k]);
+    if (!in) return 1.0f;
+    prod *= (curr[k] - zero[k]) / (one[k] - zero[k]);
+  }
+  return prod;
+}
+
+// SawyerPegV2.compute_reward, dense branch (reference earl_benchmark/envs/sawyer_peg.py:231-299) with metaworld's
+// SawyerXYZEnv._gripper_caging_reward(high_density=True).  obs7 = [hand(3), gripper, pegHead(3)]; obj_init = the peg
+// position the last reset wrote (self.obj_init_pos), head_init = self.peg_head_pos_init, init_tcp = self.init_tcp.
+MJ_FN real peg_dense_reward(const Model& m, const Work& w, const real* obs7, const real* target, real grip_action, const real* obj_init,
+                            const real* head_init, const real* init_tcp) {
+  real head[3], grasp[3], obj[3], zero[3], one[3], lp[3], rp[3], ree[3], lee[3];
+  site_xpos(m, w, m.obs_obj_site, head);
+  site_xpos(m, w, m.grasp_site, grasp);
+  real tto = 0, ott = 0, ipm = 0;
+  const real scale[3] = {1.0f, 2.0f, 2.0f};
+  for (int k = 0; k < 3; ++k) {
+    obj[k] = obs7[4 + k] - head[k] + grasp[k];
+    const real a = obj[k] - obs7[k], b = (obs7[4 + k] - target[k]) * scale[k], c = (head_init[k] - target[k]) * scale[k];
+    tto += a * a; ott += b * b; ipm += c * c;
+  }
+  tto = sqrtf(tto); ott = sqrtf(ott); ipm = sqrtf(ipm);
+  real in_place = tolerance_long_tail(ott, 0.0f, m.success_radius, ipm);
+  real cb[2];
+  for (int q = 0; q < 2; ++q) {
+    site_xpos(m, w, m.corner_site[2 * q], zero);      // bottom right corner: reward 0
+    site_xpos(m, w, m.corner_site[2 * q + 1], one);   // top left corner: reward 1
+    cb[q] = rect_prism_tolerance(obs7 + 4, zero, one);
+  }
+  in_place = hamacher(in_place, hamacher(cb[1], cb[0]));
+  const bool lifted = tto < 0.08f && obs7[3] > 0 && obj[2] - 0.01f > obj_init[2];
+  real grasped;
+  if (lifted) {
+    grasped = 1.0f;
+  } else {  // _gripper_caging_reward(action, obj, object_reach_radius=0.01, obj_radius=0.0075, pad_success_thresh=0.03, xz_thresh=0.005)
+    const real obj_radius = 0.0075f, pad_thresh = 0.03f, xz_thresh = 0.005f;
+    site_xpos(m, w, m.lpad_site, lp);
+    site_xpos(m, w, m.rpad_site, rp);
+    const real pad_y[2] = {lp[1], rp[1]};
+    real cy[2];
+    for (int q = 0; q < 2; ++q) {
+      const real to_obj = fabsf(pad_y[q] - obj[1]), to_init = fabsf(pad_y[q] - obj_init[1]);
+      cy[q] = tolerance_long_tail(to_obj, obj_radius, pad_thresh, fabsf(to_init - pad_thresh));
+    }
+    const real caging_y = hamacher(cy[0], cy[1]);
+    site_xpos(m, w, m.obs_ree_site, ree);
+    site_xpos(m, w, m.obs_lee_site, lee);
+    const real tx = 0.5f * (ree[0] + lee[0]), tz = 0.5f * (ree[2] + lee[2]);
+    const real mx = obj_init[0] - init_tcp[0], mz = obj_init[2] - init_tcp[2];
+    real xz_margin = sqrtf(mx * mx + mz * mz) - xz_thresh;
+    if (xz_margin < 0) xz_margin = 0;  // the reference raises ValueError for a negative margin; never reached from a reset pose
+    const real dx = tx - obj[0], dz = tz - obj[2];
+    const real caging_xz = tolerance_long_tail(sqrtf(dx * dx + dz * dz), 0.0f, xz_thresh, xz_margin);
+    const real closed = fminf(fmaxf(0.0f, grip_action), 1.0f);
+    const real caging = hamacher(caging_y, caging_xz);
+    const real gripping = caging > 0.97f ? closed : 0.0f;
+    grasped = 0.5f * (hamacher(caging, gripping) + caging);  // high_density
+  }
+  real reward = hamacher(grasped, in_place);
+  if (lifted) reward += 1.0f + 5.0f * in_place;
+  if (ott <= m.success_radius) reward = 10.0f;
+  return reward;
+}
+
 }  // namespace mj
 }  // namespace earl

@@ -51,6 +51,8 @@ def task_spec(model, max_newton=0, hand_init_pos=(0.0, 0.4, 0.2)):
     t.success_radius = 0.02                           # is_successful(), sawyer_door.py:177
     t.obj_init_pos[:] = [0.1, 0.95, 0.1]              # dense reward margins (sawyer_door.py:36,150,156); float32 in the reference
     t.hand_init_pos[:] = [float(x) for x in hand_init_pos]
+    t.grasp_site = t.lpad_site = t.rpad_site = -1
+    t.corner_site[:] = [-1] * 4
     return t
 
 

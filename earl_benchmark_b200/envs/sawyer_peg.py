@@ -58,6 +58,13 @@ def task_spec(model, max_newton=0):
     t.mocap_high[:] = [0.5, 1.0, 0.5]
     t.action_scale = 1.0 / 100
     t.success_radius = 0.05                                 # TARGET_RADIUS (sawyer_peg.py:62,305)
+    # dense reward (sawyer_peg.py:231-299): pegGrasp, the pad body frames of metaworld's _gripper_caging_reward and the four
+    # corner sites of the block's two no-go prisms
+    names = model.names["site"]
+    sid = lambda n: names.index(n) if n in names else -1  # noqa: E731
+    t.grasp_site, t.lpad_site, t.rpad_site = sid("pegGrasp"), sid("body:leftpad"), sid("body:rightpad")
+    t.corner_site[:] = [sid("bottom_right_corner_collision_box_1"), sid("top_left_corner_collision_box_1"),
+                        sid("bottom_right_corner_collision_box_2"), sid("top_left_corner_collision_box_2")]
     return t
 
 
@@ -66,6 +73,7 @@ class SawyerPegV2(SawyerBatchedEnv):
     MODEL_FILE = "sawyer_peg.npz"
     SUCCESS_RADIUS = 0.05
     TARGET_RADIUS = 0.05
+    HAS_DENSE_REWARD = True   # sawyer_peg.py:231-299 with metaworld's reward_utils / _gripper_caging_reward restated (unpinned)
 
     def __init__(self, reward_type="dense", reset_at_goal=False, wide_init=False, **batched):
         super().__init__(reward_type=reward_type, reset_at_goal=reset_at_goal, **batched)
@@ -121,6 +129,13 @@ class SawyerPegV2(SawyerBatchedEnv):
             return np.broadcast_to(self.goal_states[0], (self.num_envs, 7)).copy()
         k = self._np_random.randint(self.initial_states.shape[0], self.num_envs)
         return self.initial_states[k].copy()
+
+    def compute_reward(self, obs, actions=None):
+        """Sparse: on caller-supplied observations (cold path).  Dense: the reference's compute_reward reads simulator state
+        (sites, pad bodies, init_tcp) besides `obs`, so it only exists for the states the step kernel produces."""
+        if self._reward_type == "dense":
+            raise NotImplementedError("SawyerPegV2: the dense reward is computed by step() (it needs simulator state, not only obs)")
+        return super().compute_reward(obs, actions)
 
     def reset(self, mask=None, peg_pos=None):
         """reset() of every env (or those in `mask`); `peg_pos` [N,3] overrides the random draw."""

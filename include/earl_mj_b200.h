@@ -23,7 +23,7 @@ typedef struct {
   int32_t env_kind;         /* EARL_ENV_SAWYER_DOOR or EARL_ENV_SAWYER_PEG */
   int32_t num_envs;
   int32_t device;
-  uint32_t flags;           /* EARL_FLAG_EVAL_STATS | EARL_FLAG_LIFELONG | EARL_FLAG_DENSE_REWARD (door only) */
+  uint32_t flags;           /* EARL_FLAG_EVAL_STATS | EARL_FLAG_LIFELONG | EARL_FLAG_DENSE_REWARD */
   int64_t episode_horizon;  /* PersistentStateWrapper(episode_horizon), persistent_state_wrapper.py:10-12 */
   int64_t goal_change_frequency; /* LifelongWrapper(goal_change_frequency), lifelong_wrapper.py:19-24; 0 = unused */
 } earl_mj_config;
@@ -44,6 +44,11 @@ typedef struct {
   float success_radius;     /* 0.02 door (sawyer_door.py:177), 0.05 peg (sawyer_peg.py:305) */
   float obj_init_pos[3];    /* dense door reward: self.obj_init_pos (sawyer_door.py:36,150) */
   float hand_init_pos[3];   /* dense door reward: self.hand_init_pos (sawyer_door.py:37-40,156) */
+  /* dense peg reward (sawyer_peg.py:231-299); -1 when unused */
+  int32_t grasp_site;       /* site 'pegGrasp' */
+  int32_t lpad_site;        /* frame of body 'leftpad'  (get_body_com in metaworld's _gripper_caging_reward) */
+  int32_t rpad_site;        /* frame of body 'rightpad' */
+  int32_t corner_site[4];   /* bottom_right_corner_collision_box_1, top_left_..._1, bottom_right_..._2, top_left_..._2 */
 } earl_mj_task;
 
 /* model_blob: the serialized structure-of-arrays model written by earl_benchmark_b200.mjcf.compile.Model.to_blob()

@@ -197,9 +197,12 @@ class SawyerPegOracle:
         self.e.reset()
         self.reset_hand()
         p = self.OBJ_INIT if peg_pos is None else np.asarray(peg_pos, np.float64)
+        self.init_tcp = self._tcp_center()                        # _reset_hand: self.init_tcp = self.tcp_center
         self.e.qpos[self.peg_qadr:self.peg_qadr + 3] = p          # _set_obj_xyz: qpos[9:12] = pos, qvel[9:15] = 0
         self.e.qvel[self.peg_dadr:self.peg_dadr + 6] = 0
         self.e.forward()
+        self.obj_init_pos = p.copy()                              # sawyer_peg.py:215-217
+        self.peg_head_pos_init = self.e.site_xpos("pegHead")
         return self.obs()
 
     def obs(self):
@@ -207,6 +210,71 @@ class SawyerPegOracle:
         hand = e.site_xpos("body:hand")
         grip = np.clip(np.linalg.norm(e.site_xpos("rightEndEffector") - e.site_xpos("leftEndEffector")) / 0.1, 0.0, 1.0)
         return np.concatenate([hand, [grip], e.site_xpos("pegHead"), self.goal])
+
+    # ---- dense reward (reference earl_benchmark/envs/sawyer_peg.py:231-299).  metaworld's reward_utils and
+    # SawyerXYZEnv._gripper_caging_reward are NOT under /root/reference: restated from SURVEY.md Appendix C and the
+    # published metaworld sources (parity unpinned).
+    @staticmethod
+    def _tolerance_long_tail(x, lower, upper, margin, value_at_margin=0.1):
+        if lower <= x <= upper:
+            return 1.0
+        if margin == 0:
+            return 0.0
+        d = (lower - x if x < lower else x - upper) / margin
+        scale = np.sqrt(1 / value_at_margin - 1)
+        return 1 / ((d * scale) ** 2 + 1)
+
+    @staticmethod
+    def _hamacher(a, b):
+        den = a + b - a * b
+        return a * b / den if den > 0 else 0.0
+
+    @staticmethod
+    def _rect_prism_tolerance(curr, zero, one):
+        def in_range(a, b, c):
+            return b <= a <= c if c >= b else c <= a <= b
+        if all(in_range(curr[k], zero[k], one[k]) for k in range(3)):
+            diff = one - zero
+            return float(np.prod((curr - zero) / diff))
+        return 1.0
+
+    def _tcp_center(self):
+        return 0.5 * (self.e.site_xpos("rightEndEffector") + self.e.site_xpos("leftEndEffector"))
+
+    def _caging(self, action, obj_pos, obj_radius=0.0075, pad_success_thresh=0.03, xz_thresh=0.005):
+        e = self.e
+        pad_y = np.array([e.site_xpos("body:leftpad")[1], e.site_xpos("body:rightpad")[1]])
+        to_obj, to_init = np.abs(pad_y - obj_pos[1]), np.abs(pad_y - self.obj_init_pos[1])
+        margin = np.abs(to_init - pad_success_thresh)
+        cy = [self._tolerance_long_tail(to_obj[i], obj_radius, pad_success_thresh, margin[i]) for i in range(2)]
+        caging_y = self._hamacher(*cy)
+        tcp = self._tcp_center()
+        xz_margin = max(np.linalg.norm(self.obj_init_pos[[0, 2]] - self.init_tcp[[0, 2]]) - xz_thresh, 0.0)
+        caging_xz = self._tolerance_long_tail(np.linalg.norm(tcp[[0, 2]] - obj_pos[[0, 2]]), 0.0, xz_thresh, xz_margin)
+        closed = min(max(0.0, float(action[-1])), 1.0)
+        caging = self._hamacher(caging_y, caging_xz)
+        gripping = closed if caging > 0.97 else 0.0
+        return 0.5 * (self._hamacher(caging, gripping) + caging)        # high_density=True
+
+    def dense_reward(self, obs, action):
+        e = self.e
+        tcp, tcp_opened, obj_head, target = obs[:3], obs[3], obs[4:7], obs[11:14]
+        obj = obs[4:7] - e.site_xpos("pegHead") + e.site_xpos("pegGrasp")
+        tcp_to_obj = np.linalg.norm(obj - tcp)
+        scale = np.array([1.0, 2.0, 2.0])
+        obj_to_target = np.linalg.norm((obj_head - target) * scale)
+        in_place = self._tolerance_long_tail(obj_to_target, 0.0, self.TARGET_RADIUS, np.linalg.norm((self.peg_head_pos_init - target) * scale))
+        cb = [self._rect_prism_tolerance(obj_head, e.site_xpos(f"bottom_right_corner_collision_box_{q}"),
+                                         e.site_xpos(f"top_left_corner_collision_box_{q}")) for q in (1, 2)]
+        in_place = self._hamacher(in_place, self._hamacher(cb[1], cb[0]))
+        lifted = tcp_to_obj < 0.08 and tcp_opened > 0 and obj[2] - 0.01 > self.obj_init_pos[2]
+        grasped = 1.0 if lifted else self._caging(action, obj)
+        reward = self._hamacher(grasped, in_place)
+        if lifted:
+            reward += 1.0 + 5 * in_place
+        if obj_to_target <= self.TARGET_RADIUS:
+            reward = 10.0
+        return reward
 
     def step(self, action):
         a = np.clip(np.asarray(action, np.float64), -1, 1)

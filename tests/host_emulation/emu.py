@@ -15,7 +15,8 @@ class TaskSpec(C.Structure):
     _fields_ = [("frame_skip", C.c_int32), ("hand_site", C.c_int32), ("ree_site", C.c_int32), ("lee_site", C.c_int32),
                 ("obj_geom", C.c_int32), ("obj_site", C.c_int32), ("max_newton", C.c_int32), ("obj_qpos_count", C.c_int32),
                 ("mocap_low", C.c_float * 3), ("mocap_high", C.c_float * 3), ("action_scale", C.c_float),
-                ("success_radius", C.c_float), ("obj_init_pos", C.c_float * 3), ("hand_init_pos", C.c_float * 3)]
+                ("success_radius", C.c_float), ("obj_init_pos", C.c_float * 3), ("hand_init_pos", C.c_float * 3),
+                ("grasp_site", C.c_int32), ("lpad_site", C.c_int32), ("rpad_site", C.c_int32), ("corner_site", C.c_int32 * 4)]
 
 
 _LIBS = {}
@@ -106,6 +107,8 @@ class Emu:
 def door_task(model, max_newton=0):
     t = TaskSpec()
     t.frame_skip, t.max_newton, t.obj_qpos_count = 5, max_newton, 1
+    t.grasp_site = t.lpad_site = t.rpad_site = -1
+    t.corner_site[:] = [-1] * 4
     t.hand_site, t.ree_site, t.lee_site = model.site_id("body:hand"), model.site_id("rightEndEffector"), model.site_id("leftEndEffector")
     t.obj_geom, t.obj_site = model.geom_id("handle"), -1
     t.mocap_low[:] = [-0.5, 0.40, 0.05]
@@ -117,6 +120,8 @@ def door_task(model, max_newton=0):
 def peg_task(model, max_newton=0):
     t = TaskSpec()
     t.frame_skip, t.max_newton, t.obj_qpos_count = 5, max_newton, 3
+    t.grasp_site = t.lpad_site = t.rpad_site = -1
+    t.corner_site[:] = [-1] * 4
     t.hand_site, t.ree_site, t.lee_site = model.site_id("body:hand"), model.site_id("rightEndEffector"), model.site_id("leftEndEffector")
     t.obj_geom, t.obj_site = -1, model.site_id("pegHead")
     t.mocap_low[:] = [-0.5, 0.40, 0.05]
@@ -130,6 +135,8 @@ def kitchen_task(model, max_newton=0):
     `substeps` is meaningful, the Sawyer observation fields point at a valid site)."""
     t = TaskSpec()
     t.frame_skip, t.max_newton, t.obj_qpos_count = 40, max_newton, 0
+    t.grasp_site = t.lpad_site = t.rpad_site = -1
+    t.corner_site[:] = [-1] * 4
     t.hand_site = t.ree_site = t.lee_site = model.site_id("end_effector")
     t.obj_geom, t.obj_site = -1, model.site_id("slide_site")
     t.mocap_low[:] = [-0.7, -0.1, 1.8]

@@ -42,7 +42,7 @@ def test_struct_layouts_match_header():
     assert ctypes.sizeof(_lib.EarlConfig) == 40
     assert ctypes.sizeof(_lib.TabletopModel) == 8 + 4 * 8 + 6 * 8 + 256 * 6 * 8
     assert ctypes.sizeof(_lib.MjConfig) == 32
-    assert ctypes.sizeof(_lib.MjTask) == 8 * 4 + 8 * 4 + 6 * 4
+    assert ctypes.sizeof(_lib.MjTask) == 8 * 4 + 8 * 4 + 6 * 4 + 7 * 4
 
 
 def test_no_cpu_fallback_without_gpu():
@@ -54,6 +54,23 @@ def test_no_cpu_fallback_without_gpu():
     with pytest.raises(_lib.EarlError) as ei:
         tr.reset()
     assert ei.value.code == -2  # EARL_ERR_CUDA: fails loudly, no silent CPU path
+
+
+def test_kitchen_has_no_cpu_fallback_either():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is visible")
+    import numpy as np
+    from earl_benchmark_b200.envs import kitchen
+    env = kitchen.Kitchen(num_envs=2)           # construction is lazy: host constants only
+    assert env.get_init_states().shape == (6, 23)
+    with pytest.raises(_lib.EarlError) as ei:
+        env.reset()
+    assert ei.value.code == -2                  # EARL_ERR_CUDA
+    from earl_benchmark_b200.kitchen_engine import KitchenEngine
+    with pytest.raises(_lib.EarlError):
+        KitchenEngine("cuda:0")
+    assert np.array_equal(env.get_next_goal(), kitchen.goal_states[0])
 
 
 def test_product_package_never_imports_the_oracle():

@@ -175,3 +175,22 @@ def test_recorded_weld_lag_vs_documented_and_calibrated_weld():
     assert 0.0315 < lag_demo[6:].max() < 0.0355, lag_demo               # recorded: 32-34 mm
     assert 0.0275 < lags["documented"][6:].max() < 0.0300, lags         # 2 * 0.02 s * 0.74 m/s - staleness
     assert np.abs(lags["calibrated"][3:] - lag_demo[3:]).max() < 2e-3, (lags, lag_demo)
+
+
+def test_peg_dense_reward_building_blocks(peg_oracle):
+    """metaworld reward_utils as restated for the dense peg reward (sawyer_peg.py:231-299): known values and limits."""
+    o = peg_oracle
+    assert o._tolerance_long_tail(0.03, 0.0, 0.05, 1.0) == 1.0                      # inside the bounds
+    assert abs(o._tolerance_long_tail(1.05, 0.0, 0.05, 1.0) - 0.1) < 1e-12         # value_at_margin at one margin
+    assert o._tolerance_long_tail(0.2, 0.0, 0.05, 0.0) == 0.0
+    assert o._hamacher(1.0, 0.3) == pytest.approx(0.3) and o._hamacher(0.0, 0.0) == 0.0 and o._hamacher(0.5, 0.5) == pytest.approx(1 / 3)
+    zero, one = np.array([0.1, -0.11, 0.01]), np.array([-0.1, -0.15, 0.096])
+    assert o._rect_prism_tolerance(np.array([0.3, 0.0, 0.0]), zero, one) == 1.0     # outside the prism
+    assert o._rect_prism_tolerance(one.copy(), zero, one) == pytest.approx(1.0)
+    assert o._rect_prism_tolerance(0.5 * (zero + one), zero, one) == pytest.approx(0.125)
+    ob = o.reset()
+    r = o.dense_reward(ob, np.zeros(4))
+    assert 0.0 <= r < 1.0                                                           # far from the goal, nothing grasped
+    ob2 = ob.copy()
+    ob2[4:7] = ob2[11:14]                                                           # peg head at the target
+    assert o.dense_reward(ob2, np.zeros(4)) == 10.0

@@ -30,9 +30,11 @@ def test_unknown_env_is_keyerror_like_reference():
         eb.EARLEnvs("no_such_env")
 
 
-def test_unbuilt_envs_fail_loudly():
-    with pytest.raises(NotImplementedError):
-        eb.EARLEnvs("sawyer_peg", reward_type="dense")
+def test_every_task_of_the_loader_is_built():
+    """All four tasks of EARLEnvs construct (lazily: no device work before the first reset), dense peg reward included."""
+    for name, rt in (("tabletop_manipulation", "sparse"), ("sawyer_door", "dense"), ("sawyer_peg", "dense"), ("kitchen", "dense")):
+        tr, ev = eb.EARLEnvs(name, reward_type=rt, num_envs=2).get_envs()
+        assert tr.num_envs == 2
 
 
 def test_kitchen_loader_surface():

@@ -93,3 +93,40 @@ def test_loader_surface_and_reset_draws():
         assert bool(d.all()) == (t + 1 >= 4)
     assert train.total_steps == 5 and int(train.num_interventions[0]) == 1
     assert ev.env._episode_horizon == 200
+
+
+def test_dense_reward_matches_checker(oracle):
+    """reward_type='dense' (sawyer_peg.py:231-299: long-tail tolerances, collision-box prisms, gripper caging with
+    high_density): the step kernel against the checker's numpy restatement along open-loop rollouts that hover over the
+    peg, close the gripper on it and lift."""
+    n = 6
+    env = sawyer_peg.SawyerPegV2(reward_type="dense", num_envs=n, device="cuda:0")
+    pegs = np.array([[0.0, 0.6, 0.02], [0.05, 0.55, 0.02], [0.1, 0.65, 0.02], [0.15, 0.6, 0.02], [0.02, 0.68, 0.02], [0.2, 0.5, 0.02]])
+    env.reset(peg_pos=pegs)
+    rs = np.random.RandomState(2)
+    T = 40
+    acts = np.zeros((T, n, 4), np.float32)
+    for i in range(n):
+        # move over the peg grasp point, descend, close, lift; plus noise
+        acts[:, i, :3] = rs.uniform(-0.3, 0.3, (T, 3))
+        acts[:12, i, 0] += np.sign(pegs[i, 0] + 0.03) * 0.6
+        acts[:12, i, 1] += np.sign(pegs[i, 1] - 0.6) * 0.6
+        acts[8:24, i, 2] -= 0.9
+        acts[:20, i, 3] = -1.0
+        acts[20:, i, 3] = 1.0
+        acts[30:, i, 2] += 1.2
+    dev = []
+    for t in range(T):
+        ob, r, d, info = env.step(torch.from_numpy(acts[t]).cuda())
+        dev.append((ob.cpu().numpy().copy(), r.cpu().numpy().copy()))
+    worst, rmax, rmin = 0.0, -1e9, 1e9
+    for i in (0, 2, 5):
+        oracle.reset(peg_pos=pegs[i])
+        for t in range(T):
+            ob, _ = oracle.step(acts[t, i])
+            r_ref = oracle.dense_reward(ob, acts[t, i])
+            assert np.abs(ob - dev[t][0][i]).max() < 2e-4
+            worst = max(worst, abs(r_ref - dev[t][1][i]))
+            rmax, rmin = max(rmax, r_ref), min(rmin, r_ref)
+    print("peg dense reward: max |device - checker| %.2e over rewards in [%.3f, %.3f]" % (worst, rmin, rmax))
+    assert worst < 2e-3 and rmax > rmin + 0.01

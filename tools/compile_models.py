@@ -30,8 +30,10 @@ def sawyer_peg():
     spec = parser.load(os.path.join(MW, "sawyer_peg_insertion_side.xml"))
     # reset_model() moves the block to goal_states[0][4:] - (0.03, 0, 0.13) (reference envs/sawyer_peg.py:195-197)
     box_pos = np.array([-0.3 + 0.03, 0.6, 0.0 + 0.13]) - np.array([0.03, 0.0, 0.13])
-    return C.compile_model(spec, body_pos_overrides={"box": box_pos}, frame_sites=("hand",),
-                           keep_sites=("rightEndEffector", "leftEndEffector", "pegHead", "pegGrasp"))
+    return C.compile_model(spec, body_pos_overrides={"box": box_pos}, frame_sites=("hand", "leftpad", "rightpad"),
+                           keep_sites=("rightEndEffector", "leftEndEffector", "pegHead", "pegGrasp",
+                                       "bottom_right_corner_collision_box_1", "top_left_corner_collision_box_1",
+                                       "bottom_right_corner_collision_box_2", "top_left_corner_collision_box_2"))
 
 
 def kitchen():
