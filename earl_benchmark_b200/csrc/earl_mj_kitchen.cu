@@ -9,6 +9,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -69,7 +70,7 @@ mjk_substeps_kernel(const Model* __restrict__ gm, const real* __restrict__ hull,
       for (int k = 0; k < 3; ++k) w.mocap_pos[k] = mocap_pos[(size_t)env * 3 + k];
       w.mocap_quat[0] = mocap_quat.x; w.mocap_quat[1] = mocap_quat.y; w.mocap_quat[2] = mocap_quat.z; w.mocap_quat[3] = mocap_quat.w;
       for (int k = 0; k < m.nu; ++k) w.ctrl[k] = ctrl[(size_t)env * m.nu + k];
-      w.bad = 0; w.acc_iter = w.acc_rows = w.acc_con = w.acc_mpr = w.acc_sup = 0; w.broad_valid = 0;
+      w.bad = 0; w.acc_iter = w.acc_rows = w.acc_con = w.acc_mpr = w.acc_sup = 0; w.broad_valid = 0; w.acc_rebuild = 0;
     }
     __syncwarp();
     for (int s = 0; s < nsub; ++s) substep<32>(m, hull, w, lane);
@@ -107,6 +108,7 @@ struct TaskArgs {
   long long* num_interventions;
   double* lifelong_return;
   unsigned long long* work;         // 7 counters
+  int* cost;                        // [N] estimated cost of the last env step (visiting order of the next one)
   float4 mocap_quat;
 };
 
@@ -191,7 +193,7 @@ __device__ __forceinline__ void task_load(const TaskArgs& a, Work& w, int env, i
   if (lane == 0) {
     for (int k = 0; k < 3; ++k) w.mocap_pos[k] = a.mocap[(size_t)env * 3 + k];
     w.mocap_quat[0] = a.mocap_quat.x; w.mocap_quat[1] = a.mocap_quat.y; w.mocap_quat[2] = a.mocap_quat.z; w.mocap_quat[3] = a.mocap_quat.w;
-    w.bad = 0; w.acc_iter = w.acc_rows = w.acc_con = w.acc_mpr = w.acc_sup = 0; w.broad_valid = 0;
+    w.bad = 0; w.acc_iter = w.acc_rows = w.acc_con = w.acc_mpr = w.acc_sup = 0; w.broad_valid = 0; w.acc_rebuild = 0;
   }
   __syncwarp();
 }
@@ -230,7 +232,7 @@ mjk_task_kernel(const Model* __restrict__ gm, const real* __restrict__ hull, con
       if (lane == 0) {
         for (int k = 0; k < 3; ++k) w.mocap_pos[k] = a.midpoint[k];
         w.mocap_quat[0] = a.mocap_quat.x; w.mocap_quat[1] = a.mocap_quat.y; w.mocap_quat[2] = a.mocap_quat.z; w.mocap_quat[3] = a.mocap_quat.w;
-        w.bad = 0; w.acc_iter = w.acc_rows = w.acc_con = w.acc_mpr = w.acc_sup = 0; w.broad_valid = 0;
+        w.bad = 0; w.acc_iter = w.acc_rows = w.acc_con = w.acc_mpr = w.acc_sup = 0; w.broad_valid = 0; w.acc_rebuild = 0;
       }
       __syncwarp();
     } else {
@@ -260,7 +262,10 @@ mjk_task_kernel(const Model* __restrict__ gm, const real* __restrict__ hull, con
         for (int k = 0; k < kRobot; ++k) a.last_qp[(size_t)env * kRobot + k] = last_qp[k];
         unsigned long long* r = a.rng + (size_t)env * 4;
         r[0] = (unsigned long long)(g.state >> 64); r[1] = (unsigned long long)g.state;
-        double* orow = obs_out ? obs_out + (size_t)slot * kObs : nullptr;
+        double* orow = obs_out ? obs_out + (size_t)(mode == 0 ? env : slot) * kObs : nullptr;
+        // estimated warp instructions above the contact-free baseline: loose broad-phase passes (~9k each), extra Newton
+        // iterations (~6k), contacts (~1.5k per contact and substep), portal-refinement support calls (~0.3k)
+        a.cost[env] = 9000 * w.acc_rebuild + 6000 * (w.acc_iter - a.frame_skip) + 1500 * w.acc_con + 300 * w.acc_sup;
         if (orow) for (int k = 0; k < kObs; ++k) orow[k] = obs[k];
         if (mode == 0) {
           bool ok;
@@ -301,6 +306,32 @@ mjk_task_kernel(const Model* __restrict__ gm, const real* __restrict__ hull, con
     atomicAdd(&a.work[2], c_it); atomicAdd(&a.work[3], c_rows); atomicAdd(&a.work[4], c_con);
     atomicAdd(&a.work[5], c_bad); atomicAdd(&a.work[6], c_over);
   }
+}
+
+
+// Visiting order of the next env step: environments bucketed by the estimated cost of the step they just took, most
+// expensive bucket first, so the warps of a block (which meet at block-wide phase barriers) carry similar work.
+constexpr int kBuckets = 32;
+__global__ void mjk_bucket_kernel(const int* cost, int n, int width, unsigned char* bucket, int* rank, unsigned* counts) {
+  const int env = blockIdx.x * blockDim.x + threadIdx.x;
+  if (env >= n) return;
+  int b = cost[env] <= 0 ? 0 : 1 + cost[env] / width;
+  b = b > kBuckets - 1 ? kBuckets - 1 : b;
+  bucket[env] = (unsigned char)b;
+  rank[env] = (int)atomicAdd(&counts[b], 1u);
+}
+__global__ void mjk_order_kernel(const unsigned char* bucket, const int* rank, int n, unsigned* counts, int* order) {
+  __shared__ unsigned base[kBuckets];
+  if (threadIdx.x == 0) {
+    unsigned acc = 0;
+    for (int b = kBuckets - 1; b >= 0; --b) { base[b] = acc; acc += counts[b]; }
+  }
+  __syncthreads();
+  for (int env = blockIdx.x * blockDim.x + threadIdx.x; env < n; env += gridDim.x * blockDim.x) order[base[bucket[env]] + rank[env]] = env;
+}
+__global__ void mjk_iota_kernel(int* order, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) order[i] = i;
 }
 
 }  // namespace
@@ -384,6 +415,11 @@ struct earl_mjk_handle {
   TaskArgs a{};
   int64_t total_steps = 0;
   bool seeded = false;
+  int* d_order = nullptr;           // visiting order of the next step (cost-sorted)
+  unsigned char* d_bucket = nullptr;
+  int* d_rank = nullptr;
+  unsigned* d_counts = nullptr;
+  int bucket_width = 60000;  // flat between 40k and 160k (measured); EARL_MJK_BUCKET_WIDTH overrides
   std::vector<void*> owned;
   template <typename T>
   int alloc(T** ptr, size_t count) {
@@ -439,11 +475,15 @@ int earl_mjk_create(const earl_mjk_config* cfg, const void* model_blob, size_t m
   if ((rc = h->alloc(&a.qpos, n * kNQ)) || (rc = h->alloc(&a.qvel, n * kNQ)) || (rc = h->alloc(&a.warm, n * kNQ)) ||
       (rc = h->alloc(&a.mocap, n * 3)) || (rc = h->alloc(&a.last_qp, n * kRobot)) || (rc = h->alloc(&a.sites, n * kSites * 3)) ||
       (rc = h->alloc(&a.rng, n * 4)) || (rc = h->alloc(&a.steps_since_reset, n)) || (rc = h->alloc(&a.steps_since_goal_change, n)) || (rc = h->alloc(&a.num_interventions, n)) ||
-      (rc = h->alloc(&a.lifelong_return, n)) || (rc = h->alloc(&a.work, 8))) {
+      (rc = h->alloc(&a.lifelong_return, n)) || (rc = h->alloc(&a.work, 8)) || (rc = h->alloc(&a.cost, n)) || (rc = h->alloc(&h->d_order, n)) ||
+      (rc = h->alloc(&h->d_bucket, n)) || (rc = h->alloc(&h->d_rank, n)) || (rc = h->alloc(&h->d_counts, kBuckets))) {
     earl_mjk_destroy(h);
     return rc;
   }
   CU(cudaFuncSetAttribute(mjk_task_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+  mjk_iota_kernel<<<(cfg->num_envs + 255) / 256, 256>>>(h->d_order, cfg->num_envs);
+  CU(cudaGetLastError());
+  if (const char* e = getenv("EARL_MJK_BUCKET_WIDTH")) h->bucket_width = atoi(e) > 0 ? atoi(e) : h->bucket_width;
   *out = h;
   return 0;
 }
@@ -482,7 +522,13 @@ int earl_mjk_step(earl_mjk_handle* h, const float* actions_dev, double* obs_dev,
   CU(cudaSetDevice(h->eng->device));
   h->a.mocap_quat = make_float4(h->eng->mocap_quat[0], h->eng->mocap_quat[1], h->eng->mocap_quat[2], h->eng->mocap_quat[3]);
   h->total_steps += 1;
-  return launch_task(h, 0, nullptr, h->a.n, actions_dev, nullptr, obs_dev, reward_dev, done_dev, success_dev, stream);
+  if (int rc = launch_task(h, 0, h->d_order, h->a.n, actions_dev, nullptr, obs_dev, reward_dev, done_dev, success_dev, stream)) return rc;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  CU(cudaMemsetAsync(h->d_counts, 0, kBuckets * sizeof(unsigned), s));
+  mjk_bucket_kernel<<<(h->a.n + 255) / 256, 256, 0, s>>>(h->a.cost, h->a.n, h->bucket_width, h->d_bucket, h->d_rank, h->d_counts);
+  mjk_order_kernel<<<64, 256, 0, s>>>(h->d_bucket, h->d_rank, h->a.n, h->d_counts, h->d_order);
+  CU(cudaGetLastError());
+  return 0;
 }
 
 int earl_mjk_get_state(earl_mjk_handle* h, double* qpos_host, double* qvel_host, double* warm_host, double* mocap_host, double* last_qp_host,

@@ -710,7 +710,7 @@ MJ_FN void collide(const Model& m, const real* hull, Work& w, int lane) {
     const bool rebuild = !w.broad_valid || travel > 0.5f * BROAD_SLACK;
     wsync<NL>();
     if (rebuild) {
-      if (lane == 0) { w.ncand = 0; w.broad_valid = 1; w.broad_travel = 0; }
+      if (lane == 0) { w.ncand = 0; w.broad_valid = 1; w.broad_travel = 0; w.acc_rebuild += 1; }
       wsync<NL>();
       for (int p0 = 0; p0 < m.npair; p0 += NL) {
         const int p = p0 + lane;

@@ -209,7 +209,7 @@ struct Work {
   unsigned short hit_list[MAXHIT];
   // cached broad phase (BROAD_CACHE): candidates of the last loose pass and the travel bound used up since
   unsigned short cand_list[MAXCAND];
-  int ncand, broad_valid;
+  int ncand, broad_valid, acc_rebuild;  // acc_rebuild: loose passes of the current env step (scheduling cost estimate)
   real broad_travel;
   // contacts
   real con_pos[MAXCON][3], con_frame[MAXCON][9], con_dist[MAXCON], con_fri[MAXCON][5], con_mu[MAXCON];
