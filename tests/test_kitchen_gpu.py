@@ -118,6 +118,9 @@ def test_loader_wrappers_counters_and_reset_draws():
         ob, r, done, info = tr.step(a)
         assert done.tolist() == [t == 2] * 4 and tr.steps_since_reset.tolist() == [t + 1] * 4
     assert tr.total_steps == 3
+    ob_last, r_last = ob.clone(), r.clone()
+    cr = tr.compute_reward(ob_last)
+    assert np.abs(cr - r_last.cpu().numpy()).max() < 1e-9
     tr.reset(mask=[True, False, True, False])
     assert tr.num_interventions.tolist() == [2, 1, 2, 1] and tr.steps_since_reset.tolist() == [0, 3, 0, 3]
     assert bool(torch.all(tr.is_successful(ob) == info["success"]))
