@@ -48,28 +48,24 @@ goal_states = np.array([[-4.1336253e-01, -1.6970085e+00, 1.4286385e+00, -2.50053
 shaped_reward_tasks = ['microwave', 'light_switch', 'slide_cabinet', 'hinge_cabinet']
 
 
-def convert_to_initial_state(component_names, values):
-    new_init_state = goal_states[0].copy()
-    for name, val in zip(component_names, values):
-        new_init_state[component_to_state_idx[name]] = np.array(val)
-    return new_init_state
+# :54-85 -- object configurations the reference resets to: the goal state with one or two components displaced
+# (values from d4rl's kitchen_envs.py, as cited there)
+_DISPLACED = {'microwave': [-0.7], 'light_switch': [-0.69, -0.05], 'slide_cabinet': [0.37], 'hinge_cabinet': [0., 1.45]}
+_PAIR_NAMES = {'micro_hinge': ('microwave', 'hinge_cabinet'), 'micro_slide': ('microwave', 'slide_cabinet'),
+               'micro_light': ('microwave', 'light_switch'), 'light_slide': ('light_switch', 'slide_cabinet'),
+               'light_hinge': ('light_switch', 'hinge_cabinet'), 'slide_hinge': ('slide_cabinet', 'hinge_cabinet')}
 
 
-# :59-85
-initial_states = {}
-initial_states['microwave'] = convert_to_initial_state(['microwave'], [[-0.7]])
-initial_states['light_switch'] = convert_to_initial_state(['light_switch'], [[-0.69, -0.05]])
-initial_states['slide_cabinet'] = convert_to_initial_state(['slide_cabinet'], [[0.37]])
-initial_states['hinge_cabinet'] = convert_to_initial_state(['hinge_cabinet'], [[0., 1.45]])
-initial_states['micro_hinge'] = convert_to_initial_state(['microwave', 'hinge_cabinet'], [[-0.7], [0., 1.45]])
-initial_states['micro_slide'] = convert_to_initial_state(['microwave', 'slide_cabinet'], [[-0.7], [0.37]])
-initial_states['micro_light'] = convert_to_initial_state(['microwave', 'light_switch'], [[-0.7], [-0.69, -0.05]])
-initial_states['light_slide'] = convert_to_initial_state(['light_switch', 'slide_cabinet'], [[-0.69, -0.05], [0.37]])
-initial_states['light_hinge'] = convert_to_initial_state(['light_switch', 'hinge_cabinet'], [[-0.69, -0.05], [0., 1.45]])
-initial_states['slide_hinge'] = convert_to_initial_state(['slide_cabinet', 'hinge_cabinet'], [[0.37], [0., 1.45]])
-initial_states['all_pairs'] = np.array([initial_states['micro_hinge'].copy(), initial_states['micro_slide'].copy(),
-                                        initial_states['micro_light'].copy(), initial_states['light_slide'].copy(),
-                                        initial_states['light_hinge'].copy(), initial_states['slide_hinge'].copy()])
+def _displaced_state(*components):
+    state = goal_states[0].copy()
+    for name in components:
+        state[component_to_state_idx[name]] = _DISPLACED[name]
+    return state
+
+
+initial_states = {name: _displaced_state(name) for name in _DISPLACED}
+initial_states.update({key: _displaced_state(*pair) for key, pair in _PAIR_NAMES.items()})
+initial_states['all_pairs'] = np.array([initial_states[key] for key in _PAIR_NAMES])   # order of kitchen.py:80-85
 
 # ADEPT/franka/kitchen_multitask_v0.py:65-70
 INIT_QPOS = np.array([1.48388023e-01, -1.76848573e+00, 1.84390296e+00, -2.47685760e+00, 2.60252026e-01, 7.12533105e-01,
