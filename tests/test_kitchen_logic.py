@@ -77,3 +77,19 @@ def test_goal_reaching_branches(gold):
     assert r == float(gold["near_goal_reward"])
     assert k.success(ob) is True and bool(gold["near_goal_success"]) is True
     assert r > 0          # several components inside their 0.01-per-index band: the +1 branch fired
+
+
+def test_product_constants_match_the_reference(gold):
+    """envs/kitchen.py carries its own copy of the task constants (the product never imports the checker): same values as
+    the reference's objects at run time."""
+    from earl_benchmark_b200.envs import kitchen as kt
+    assert np.array_equal(kt.goal_states, gold["goal_states"])
+    assert np.array_equal(kt.initial_states["all_pairs"], gold["all_pairs"])
+    assert np.array_equal(kt.INIT_QPOS, gold["init_qpos"])
+    assert np.array_equal(kt.POS_NOISE_AMP, gold["pos_noise_amp"][:23])
+    assert np.array_equal(kt.POS_BOUND, gold["pos_bound"][:9]) and np.array_equal(kt.VEL_BOUND, gold["vel_bound"][:9])
+    assert np.array_equal(kt.MIDPOINT, gold["midpoint_pos"])
+    assert np.array_equal(np.stack([kt.MOCAP_LOW, kt.MOCAP_HIGH]), gold["mocap_clip"])
+    assert kt.FRAME_SKIP == int(gold["frame_skip"]) and kt.NOISE_RATIO == float(gold["noise_ratio"])
+    # reward sites in component order (kitchen.py:15-25 with :149-156)
+    assert kt.REWARD_SITES == tuple(KL.TASK_SITE[name] for name, _ in KL.COMPONENTS)
