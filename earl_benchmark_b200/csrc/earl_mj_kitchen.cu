@@ -483,6 +483,7 @@ int earl_mjk_create(const earl_mjk_config* cfg, const void* model_blob, size_t m
   CU(cudaFuncSetAttribute(mjk_task_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
   mjk_iota_kernel<<<(cfg->num_envs + 255) / 256, 256>>>(h->d_order, cfg->num_envs);
   CU(cudaGetLastError());
+  CU(cudaDeviceSynchronize());  // the first step may be enqueued on any stream
   if (const char* e = getenv("EARL_MJK_BUCKET_WIDTH")) h->bucket_width = atoi(e) > 0 ? atoi(e) : h->bucket_width;
   *out = h;
   return 0;
