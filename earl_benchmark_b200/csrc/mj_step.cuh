@@ -5,6 +5,12 @@
 #include "mj_collide.cuh"
 #include "mj_engine.cuh"
 
+// which of the four block-wide phase barriers of a substep are kept (bit 0: top, 1: after the collision phase, 2: before
+// the solve, 3: after it); all four by default (measured: profiles/r01/README.md)
+#ifndef MJ_BSYNC_MASK
+#define MJ_BSYNC_MASK 15
+#endif
+
 namespace earl {
 namespace mj {
 
@@ -12,14 +18,14 @@ namespace mj {
 template <int NL>
 MJ_FN void substep(const Model& m, const real* hull, Work& w, int lane) {
   const int nv = m.nv;
-  bsync<NL>();
+  if (MJ_BSYNC_MASK & 1) bsync<NL>();
   MJ_PHASE_BEGIN(w);
   kinematics<NL>(m, w, lane);
   MJ_PHASE_END(w, 0);
   mass_matrix<NL>(m, w, lane);
   MJ_PHASE_END(w, 1);
   collide<NL>(m, hull, w, lane);
-  bsync<NL>();
+  if (MJ_BSYNC_MASK & 2) bsync<NL>();
 #if defined(MJ_TRACE_DEVICE) && defined(__CUDA_ARCH__)
   if (threadIdx.x == 0)
     for (int c = 0; c < w.ncon; ++c)
@@ -49,10 +55,10 @@ MJ_FN void substep(const Model& m, const real* hull, Work& w, int lane) {
     }
   }
   wsync<NL>();
-  bsync<NL>();
+  if (MJ_BSYNC_MASK & 4) bsync<NL>();
   MJ_PHASE_END(w, 5);
   solve<NL>(m, w, lane);
-  bsync<NL>();
+  if (MJ_BSYNC_MASK & 8) bsync<NL>();
   MJ_PHASE_END(w, 6);
   if (lane == 0) { w.acc_iter += w.solver_iter; w.acc_rows += w.nefc; w.acc_con += w.ncon; }
   // mj_Euler: implicit in joint damping
