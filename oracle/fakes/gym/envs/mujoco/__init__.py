@@ -22,8 +22,8 @@ class _State:
 
 
 class _Model:
-    nq = 5
-    nv = 5
+    def __init__(self, nq=5, nv=5):
+        self.nq, self.nv = nq, nv
 
 
 class _Sim:
@@ -50,10 +50,24 @@ class _Sim:
         self.data.qvel[:] = 0.0
 
 
+def _count_dofs(model_path):
+    """nq of the tabletop models = their named slide joints outside XML comments (5 for
+    tabletop_manipulation.xml, 9 for tabletop_manipulation_3obj.xml)."""
+    import re
+    try:
+        text = open(model_path).read()
+    except OSError:
+        return 5
+    text = re.sub(r"<!--.*?-->", "", text, flags=re.S)
+    return len(re.findall(r"<joint\s+name=", text)) or 5
+
+
 class MujocoEnv(Env):
     def __init__(self, model_path, frame_skip):
         self.frame_skip = frame_skip
-        self.sim = _Sim()
+        nq = _count_dofs(model_path)
+        self.sim = _Sim(nq, nq)
+        self.sim.model.nq = self.sim.model.nv = nq
         self.model = self.sim.model
         self.data = self.sim.data
         self.viewer = None
