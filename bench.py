@@ -331,6 +331,69 @@ def run_kitchen(dev, rank, world, sm_max_mhz, sm_count, with_cpu):
     return out
 
 
+TT3_ENVS = 1 << 22           # per GPU: 288 MB of state, so state, actions and outputs all stream from HBM
+TT3_ALG_BYTES = 194           # read action 12 + qpos 64 + meta 8; write fist 16 + meta 8 + obs 80 + reward 4 + done 1
+                              # + success 1 (+ 16 for the dragged object of the envs that hold one: not counted)
+
+
+def run_tt3(dev, rank, world, with_e2e):
+    """Three-object tabletop section (reference envs/tabletop_manipulation_3obj.py): batched step at
+    4,194,304 envs per GPU, random actions, sparse reward, reset-free horizon never reached."""
+    import torch
+    import torch.distributed as dist
+
+    from earl_benchmark_b200.distributed import max_over_ranks
+    from earl_benchmark_b200.envs.tabletop_manipulation_3obj import TabletopManipulation
+    from earl_benchmark_b200.wrappers import PersistentStateWrapper
+
+    n, warm, steps = TT3_ENVS, 20, 200
+    env = PersistentStateWrapper(TabletopManipulation(reward_type="sparse", num_envs=n, device=dev, seed=rank), TRAIN_HORIZON)
+    env.reset()
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(977 + rank)
+    actions = torch.rand((8, n, 3), generator=gen, device=dev, dtype=torch.float32) * 2 - 1
+    obs = torch.empty((4, n, 20), device=dev, dtype=torch.float32)
+    rew = torch.empty((4, n), device=dev, dtype=torch.float32)
+    done = torch.empty((4, n), device=dev, dtype=torch.uint8)
+    succ = torch.empty((4, n), device=dev, dtype=torch.uint8)
+    env.rollout_into(actions, warm, obs, rew, done, succ)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    l0 = env.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    env.rollout_into(actions, steps, obs, rew, done, succ)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = max_over_ranks(e0.elapsed_time(e1), dev)
+    _, att = env.get_state()
+    out = {"workload": "tabletop_manipulation_3obj sparse reward, reset-free, random actions", "envs_per_gpu": n, "steps": steps,
+           "warmup": warm, "value": n * world * steps / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / steps,
+           "gpu_launches": env.launch_count - l0, "kernel": "tt3_step_kernel (one thread per env, shared-memory tiles, PDL)",
+           "algorithmic_bytes_per_env_step": TT3_ALG_BYTES,
+           "achieved": TT3_ALG_BYTES * n / (ms * 1e-3 / steps) / 1e9,
+           "holding_fraction": float((att > 0).float().mean()),
+           "l2": "inputs larger than L2: state 288 MB, action ring 8 x 50 MB, output ring 4 x 360 MB"}
+    if with_e2e:
+        m = 1 << 20
+        del env, obs, rew, done, succ, actions
+        e = PersistentStateWrapper(TabletopManipulation(reward_type="sparse", num_envs=m, device=dev, seed=rank), TRAIN_HORIZON)
+        e.reset()
+        ha = [torch.rand((m, 3), dtype=torch.float32).mul_(2).sub_(1).pin_memory() for _ in range(4)]
+        for t in range(3):
+            e.step(ha[t % 4])
+        t0 = time.perf_counter()
+        k = 20
+        for t in range(k):
+            e.step(ha[t % 4])
+        el = time.perf_counter() - t0
+        out["e2e"] = {"value": m * k / el, "unit": UNIT, "envs": m, "steps": k, "h2d_bytes_per_step": m * 12,
+                      "d2h_bytes_per_step": m * (80 + 4 + 1 + 1),
+                      "api": "PersistentStateWrapper.step(pinned host actions) -> host obs/reward/done/success"}
+    return out
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -464,9 +527,10 @@ def run_ours(args):
                "kernel": "earl::tabletop_step_tma_kernel<3,256>  (cp.async.bulk pipeline)"}
         del a_b, o_b, r_b, d_b, tb, lb
 
-    door = peg = kit = None
+    door = peg = kit = tt3 = None
     if not args.profile and not args.no_door:
         props = torch.cuda.get_device_properties(dev)
+        tt3 = run_tt3(dev, rank, world, with_e2e=(world == 1))
         door = run_door(dev, rank, world, (clocks or {}).get("sm_max_mhz"), props.multi_processor_count,
                         with_cpu=(world == 1 and not args.no_cpu_baseline))
         peg = run_door(dev, rank, world, (clocks or {}).get("sm_max_mhz"), props.multi_processor_count,
@@ -498,6 +562,9 @@ def run_ours(args):
                 "clocks": clocks}
         if big is not None:
             line["hbm_bound_check"] = big
+        if tt3 is not None:
+            tt3["frac"] = tt3["achieved"] / peak
+            line["tabletop_3obj"] = tt3
         if door is not None:
             line["sawyer_door"] = door
         if peg is not None:

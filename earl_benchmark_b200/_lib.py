@@ -34,6 +34,14 @@ class TabletopModel(C.Structure):
                 ("initial_state", C.c_double * 6), ("goal_table", (C.c_double * 6) * 256)]
 
 
+class Tt3Config(C.Structure):
+    """earl_tt3_config (include/earl_tt3_b200.h)"""
+    _fields_ = [("num_envs", C.c_int32), ("device", C.c_int32), ("flags", C.c_uint32), ("num_goals", C.c_int32),
+                ("episode_horizon", C.c_int64), ("threshold", C.c_double), ("move_distance", C.c_double),
+                ("clip", C.c_double), ("success_radius", C.c_double), ("initial_state", C.c_double * 10),
+                ("goal_table", (C.c_double * 10) * 16)]
+
+
 class MjConfig(C.Structure):
     """earl_mj_config (include/earl_mj_b200.h)"""
     _fields_ = [("env_kind", C.c_int32), ("num_envs", C.c_int32), ("device", C.c_int32), ("flags", C.c_uint32),
@@ -83,6 +91,20 @@ SIGNATURES = [
     ("earl_rng_tabletop_goal_rows", None, [_VP, _VP, _U32, _I64, _VP]),
     ("earl_rng_np_randint", None, [_VP, _U32, _I64, _VP]),
     ("earl_rng_np_uniform", None, [_VP, C.c_double, C.c_double, _I64, _VP]),
+    # include/earl_tt3_b200.h: three-object tabletop
+    ("earl_tt3_create", C.c_int, [C.POINTER(Tt3Config), _SZ, C.POINTER(_VP)]),
+    ("earl_tt3_destroy", C.c_int, [_VP]),
+    ("earl_tt3_reset", C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP]),
+    ("earl_tt3_set_goal", C.c_int, [_VP, _VP, _VP, _VP]),
+    ("earl_tt3_step", C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP, _VP]),
+    ("earl_tt3_rollout", C.c_int, [_VP, _VP, _I32, _I32, _VP, _VP, _VP, _VP, _I32, _VP]),
+    ("earl_tt3_step_host", C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP]),
+    ("earl_tt3_get_obs", C.c_int, [_VP, _VP, _VP]),
+    ("earl_tt3_compute_reward", C.c_int, [_VP, _VP, _I64, _VP, _VP, _VP]),
+    ("earl_tt3_counters", C.c_int, [_VP, C.POINTER(_I64), _VP, _VP, _VP]),
+    ("earl_tt3_get_state", C.c_int, [_VP, _VP, _VP, _VP]),
+    ("earl_tt3_set_state", C.c_int, [_VP, _VP, _VP, _VP]),
+    ("earl_tt3_launch_count", _I64, [_VP]),
     # include/earl_mj_b200.h
     ("earl_mj_create", C.c_int, [C.POINTER(MjConfig), C.c_char_p, _SZ, C.POINTER(MjTask), C.POINTER(_VP)]),
     ("earl_mj_destroy", C.c_int, [_VP]),

@@ -1,0 +1,586 @@
+// earl_tt3.cu -- three-object tabletop task (include/earl_tt3_b200.h): kernels + C ABI.
+//
+// Replaces earl_benchmark/envs/tabletop_manipulation_3obj.py (cited below as 3OBJ:line) under
+// earl_benchmark/wrappers/persistent_state_wrapper.py (PSW:line).  One thread per environment; the task is
+// HBM-bound integer/fp64 bookkeeping (no tensor cores):
+//   * state: four double2 planes [4][N] (fist, object A, B, C) + one uint2 {flags, steps_since_reset} per env,
+//     read and written with fully coalesced 16 / 8-byte accesses;
+//   * actions [N,3] f32 and observations [N,20] f32 are row-major at the boundary: a block moves its 256-env
+//     tile through shared memory so the global accesses are contiguous float4 (3 KB in, 20 KB out per block);
+//   * algorithmic bytes per env-step: read 12 + 64 + 8 = 84, write 64 + 8 + 80 + 4 + 1 + 1 = 158  (242 B).
+// Compiled with --fmad=false: every fp64 / fp32 operation below rounds exactly where numpy rounds; the one
+// fused operation numpy's BLAS performs (the 2-element fp64 dot) is written as an explicit fma.
+// There is no CPU fallback in this file.
+#include "../../include/earl_tt3_b200.h"
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+namespace earl {
+int set_error(int code, const char* msg);  // earl_b200.cu
+}
+
+namespace {
+
+constexpr int kBlock = 256;
+constexpr int kObs = 20, kAct = 3;
+
+struct T3Params {
+  double2* q[4];          // [N] each: fist, object A, B, C
+  uint2* meta;            // [N] {flags, steps_since_reset}
+  long long* interventions;  // [N]
+  const float* goal_f32;  // [G,10] fp32 casts of the goal table (what _get_obs emits)
+  const double* goal_f64; // [G,10]
+  const float* actions;   // [N,3]
+  float* obs;             // [N,20]
+  float* reward;          // [N]
+  uint8_t* done;          // [N]
+  uint8_t* success;       // [N] or null
+  int n;
+  int first;              // launch covers envs [first, first+count), first % 256 == 0
+  int count;
+  int dense;
+  unsigned long long horizon;
+  double act_lo, act_span, threshold, clip, success_radius;
+  double init_qpos[8];
+};
+
+__device__ __forceinline__ void pdl_wait_prior_grid() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
+__device__ __forceinline__ double clipd(double x, double lo, double hi) {  // np.clip: NaN propagates
+  return x < lo ? lo : (x > hi ? hi : x);
+}
+
+// np.linalg.norm of an fp32 vector as numpy's BLAS evaluates it: fp32 products, accumulated in index order
+// in fp64, rounded to fp32, fp32 sqrt
+template <int K>
+__device__ __forceinline__ float norm_f32(const float (&d)[K]) {
+  double s = 0.0;
+#pragma unroll
+  for (int k = 0; k < K; ++k) s = __dadd_rn(s, (double)__fmul_rn(d[k], d[k]));
+  return __fsqrt_rn((float)s);
+}
+
+// is_successful (3OBJ:161-165): ||obs[0:8] - obs[10:18]|| <= 0.4, fp32 norm against the fp64 constant
+__device__ __forceinline__ bool t3_success(const float (&o)[8], const float* g, double radius) {
+  float d[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) d[k] = __fsub_rn(o[k], g[k]);
+  return (double)norm_f32(d) <= radius;
+}
+
+// dense reward (3OBJ:150-157): fp32 norms and squares, fp64 from the division by 0.01 on (numpy 1.22 promotion)
+__device__ __forceinline__ double t3_dense(const float (&o)[8], const float* g) {
+  float d6[6];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) d6[k] = __fsub_rn(o[2 + k], g[2 + k]);
+  double r = (double)(-norm_f32(d6));
+#pragma unroll
+  for (int j = 1; j < 4; ++j) {
+    float d2[2] = {__fsub_rn(o[2 * j], g[2 * j]), __fsub_rn(o[2 * j + 1], g[2 * j + 1])};
+    const float nk = norm_f32(d2);
+    r += 2.0 * exp((double)(-__fmul_rn(nk, nk)) / 0.01);
+  }
+  return r;
+}
+
+__device__ __forceinline__ float marker(uint32_t att) {  // attached_object tuples, 3OBJ:31-37
+  return att == 0 ? -1.0f : 0.5f * (float)(att - 1);
+}
+
+// stage one env's observation row (20 floats = 5 float4) in the block's tile: slot 5*t + j is conflict-free
+// for 16-byte shared-memory accesses (5 is odd)
+__device__ __forceinline__ void stage_obs(float4* tile, int t, const float (&o)[8], float m, const float* g) {
+  tile[5 * t + 0] = make_float4(o[0], o[1], o[2], o[3]);
+  tile[5 * t + 1] = make_float4(o[4], o[5], o[6], o[7]);
+  tile[5 * t + 2] = make_float4(m, m, g[0], g[1]);
+  tile[5 * t + 3] = make_float4(g[2], g[3], g[4], g[5]);
+  tile[5 * t + 4] = make_float4(g[6], g[7], g[8], g[9]);
+}
+
+// contiguous float4 copy of the block's observation tile to global memory
+__device__ __forceinline__ void flush_obs(const float4* tile, float* obs, int base, int n) {
+  const int rows = min(kBlock, n - base);
+  float4* dst = reinterpret_cast<float4*>(obs + (size_t)base * kObs);
+  for (int k = threadIdx.x; k < rows * 5; k += kBlock) dst[k] = tile[k];
+}
+
+__global__ void __launch_bounds__(kBlock) tt3_step_kernel(const __grid_constant__ T3Params p) {
+  __shared__ float4 s_obs[kBlock * 5];
+  __shared__ float4 s_act4[kBlock * kAct / 4];
+  float* s_act = reinterpret_cast<float*>(s_act4);
+  const int end = p.first + p.count;
+  const int base = p.first + blockIdx.x * kBlock;
+  const int t = threadIdx.x;
+  const int i = base + t;
+  const int rows = min(kBlock, end - base);
+  pdl_wait_prior_grid();  // nothing is read before the previous grid in the stream (the previous step, or the
+                          // caller's action producer) has completed and flushed
+  {  // actions of the tile: contiguous 16-byte loads (base * 12 B is 16-byte aligned since base % 256 == 0)
+    const float4* src = reinterpret_cast<const float4*>(p.actions + (size_t)base * kAct);
+    const int full = rows * kAct / 4;
+    if (t < full) s_act4[t] = __ldcs(src + t);
+    const int rem = rows * kAct - full * 4;
+    if (t < rem) s_act[full * 4 + t] = p.actions[(size_t)base * kAct + full * 4 + t];
+  }
+  __syncthreads();
+  if (i < end) {
+    double2 f = p.q[0][i];
+    double2 ob[3] = {p.q[1][i], p.q[2][i], p.q[3][i]};
+    uint2 m = p.meta[i];
+    uint32_t att = m.x & 3u;
+    const uint32_t row = (m.x >> 8) & 0xffu;
+    // 3OBJ:88-90: clip to [-1,1] in fp64, then lb + (a + 1) * 0.5 * (ub - lb)
+    double a[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+      a[k] = __dadd_rn(p.act_lo, __dmul_rn(__dmul_rn(__dadd_rn(clipd((double)s_act[kAct * t + k], -1.0, 1.0), 1.0), 0.5), p.act_span));
+    if (a[2] > 0.0) {  // 3OBJ:98-108: the closest object within the threshold, dict order breaks ties
+      if (att == 0) {
+        double held = INFINITY;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const double dx = __dsub_rn(f.x, ob[k].x), dy = __dsub_rn(f.y, ob[k].y);
+          const double dist = __dsqrt_rn(__fma_rn(dy, dy, __dmul_rn(dx, dx)));
+          if (dist < p.threshold && dist < held) {
+            att = k + 1;
+            held = dist;
+          }
+        }
+      }
+    } else {
+      att = 0;  // 3OBJ:109-110
+    }
+    const double nfx = clipd(__dadd_rn(f.x, a[0]), -p.clip, p.clip);  // 3OBJ:112-113
+    const double nfy = clipd(__dadd_rn(f.y, a[1]), -p.clip, p.clip);
+    if (att) {  // 3OBJ:114-119
+      const double ddx = __dsub_rn(nfx, f.x), ddy = __dsub_rn(nfy, f.y);
+#pragma unroll
+      for (int k = 0; k < 3; ++k)
+        if (att == (uint32_t)(k + 1)) {
+          ob[k].x = clipd(__dadd_rn(ob[k].x, ddx), -p.clip, p.clip);
+          ob[k].y = clipd(__dadd_rn(ob[k].y, ddy), -p.clip, p.clip);
+          p.q[1 + k][i] = ob[k];
+        }
+    }
+    p.q[0][i] = make_double2(nfx, nfy);
+    // 3OBJ:49-54
+    const float o[8] = {(float)nfx, (float)nfy, (float)ob[0].x, (float)ob[0].y,
+                        (float)ob[1].x, (float)ob[1].y, (float)ob[2].x, (float)ob[2].y};
+    float g[10];
+    {
+      const float2* gr = reinterpret_cast<const float2*>(p.goal_f32 + row * 10);
+#pragma unroll
+      for (int k = 0; k < 5; ++k) {
+        const float2 v = __ldg(gr + k);
+        g[2 * k] = v.x;
+        g[2 * k + 1] = v.y;
+      }
+    }
+    stage_obs(s_obs, t, o, marker(att), g);
+    const bool succ = t3_success(o, g, p.success_radius);
+    const float rew = p.dense ? (float)t3_dense(o, g) : (succ ? 1.0f : 0.0f);  // 3OBJ:146-159
+    // PSW:22-31
+    const uint32_t steps = m.y == 0xffffffffu ? m.y : m.y + 1u;
+    p.meta[i] = make_uint2((m.x & ~3u) | att, steps);
+    __stcs(p.reward + i, rew);
+    p.done[i] = (unsigned long long)steps >= p.horizon ? 1 : 0;
+    if (p.success) p.success[i] = succ ? 1 : 0;
+  }
+  __syncthreads();
+  flush_obs(s_obs, p.obs, base, end);
+}
+
+// PSW:17-20 + 3OBJ:67-84 for the masked envs; also serves reset_goal (state untouched) and _get_obs
+// mode 0: reset, 1: set goal only, 2: observation only
+__global__ void __launch_bounds__(kBlock) tt3_reset_kernel(const __grid_constant__ T3Params p, const uint8_t* mask,
+                                                           const int32_t* goal_idx, const double* init_qpos, int mode,
+                                                           int num_goals) {
+  const int i = blockIdx.x * kBlock + threadIdx.x;
+  if (i >= p.n) return;
+  const bool on = !mask || mask[i];
+  uint2 m = p.meta[i];
+  if (on && mode <= 1) {
+    int row = goal_idx ? goal_idx[i] : 0;
+    row = row < 0 ? 0 : (row >= num_goals ? num_goals - 1 : row);
+    m.x = (m.x & ~0xff00u) | ((uint32_t)row << 8);
+    if (mode == 0) {
+      m.x &= ~3u;
+      m.y = 0;
+      p.interventions[i] += 1;
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        p.q[k][i] = init_qpos ? make_double2(init_qpos[(size_t)i * 8 + 2 * k], init_qpos[(size_t)i * 8 + 2 * k + 1])
+                              : make_double2(p.init_qpos[2 * k], p.init_qpos[2 * k + 1]);
+    }
+    p.meta[i] = m;
+  }
+  if (p.obs && on) {
+    float* o = p.obs + (size_t)i * kObs;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const double2 v = p.q[k][i];
+      o[2 * k] = (float)v.x;
+      o[2 * k + 1] = (float)v.y;
+    }
+    o[8] = o[9] = marker(m.x & 3u);
+    const float* g = p.goal_f32 + ((m.x >> 8) & 0xffu) * 10;
+#pragma unroll
+    for (int k = 0; k < 10; ++k) o[10 + k] = g[k];
+  }
+}
+
+// compute_reward / is_successful on caller observations (3OBJ:146-165)
+__global__ void __launch_bounds__(kBlock) tt3_reward_kernel(const float* obs, long long num, float* reward, uint8_t* success,
+                                                            int dense, double radius) {
+  const long long i = (long long)blockIdx.x * kBlock + threadIdx.x;
+  if (i >= num) return;
+  const float* r = obs + i * kObs;
+  float o[8], g[10];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) o[k] = r[k];
+#pragma unroll
+  for (int k = 0; k < 10; ++k) g[k] = r[10 + k];
+  const bool succ = t3_success(o, g, radius);
+  if (reward) reward[i] = dense ? (float)t3_dense(o, g) : (succ ? 1.0f : 0.0f);
+  if (success) success[i] = succ ? 1 : 0;
+}
+
+__global__ void __launch_bounds__(kBlock) tt3_state_kernel(const __grid_constant__ T3Params p, double* qpos_out, int32_t* att_out,
+                                                           const double* qpos_in, const int32_t* att_in) {
+  const int i = blockIdx.x * kBlock + threadIdx.x;
+  if (i >= p.n) return;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    if (qpos_in) p.q[k][i] = make_double2(qpos_in[(size_t)i * 8 + 2 * k], qpos_in[(size_t)i * 8 + 2 * k + 1]);
+    if (qpos_out) {
+      const double2 v = p.q[k][i];
+      qpos_out[(size_t)i * 8 + 2 * k] = v.x;
+      qpos_out[(size_t)i * 8 + 2 * k + 1] = v.y;
+    }
+  }
+  if (att_in) {
+    uint2 m = p.meta[i];
+    const int a = att_in[i];
+    m.x = (m.x & ~3u) | (uint32_t)(a < 0 ? 0 : (a > 3 ? 3 : a));
+    p.meta[i] = m;
+  }
+  if (att_out) att_out[i] = (int32_t)(p.meta[i].x & 3u);
+}
+
+__global__ void __launch_bounds__(kBlock) tt3_counters_kernel(const __grid_constant__ T3Params p, long long* interventions,
+                                                              uint32_t* steps) {
+  const int i = blockIdx.x * kBlock + threadIdx.x;
+  if (i >= p.n) return;
+  if (interventions) interventions[i] = p.interventions[i];
+  if (steps) steps[i] = p.meta[i].y;
+}
+
+thread_local char g_msg[512];
+
+int fail(int code, const char* fmt, const char* a = "", long long b = 0) {
+  snprintf(g_msg, sizeof(g_msg), fmt, a, b);
+  return earl::set_error(code, g_msg);
+}
+
+#define CU(call)                                                                  \
+  do {                                                                            \
+    cudaError_t e_ = (call);                                                      \
+    if (e_ != cudaSuccess) return fail(EARL_ERR_CUDA, "%s (earl_tt3.cu:%lld)", cudaGetErrorString(e_), __LINE__); \
+  } while (0)
+
+}  // namespace
+
+struct earl_tt3_handle {
+  earl_tt3_config cfg{};
+  T3Params p{};
+  int64_t total_steps = 0;
+  int64_t launches = 0;
+  bool pdl = true;
+  std::vector<void*> owned;
+  float* d_act = nullptr;
+  float* d_obs = nullptr;
+  float* d_rew = nullptr;
+  uint8_t* d_done = nullptr;
+  uint8_t* d_succ = nullptr;
+  cudaStream_t in_stream = nullptr, out_stream = nullptr;
+  static constexpr int kMaxChunks = 8;
+  cudaEvent_t chunk_ev[kMaxChunks] = {};
+
+  template <typename T>
+  int alloc(T** ptr, size_t count, bool zero = true) {
+    void* q = nullptr;
+    if (cudaMalloc(&q, count * sizeof(T) + 16) != cudaSuccess) {
+      cudaGetLastError();
+      return fail(EARL_ERR_NOMEM, "cudaMalloc of %s%lld bytes failed", "", (long long)(count * sizeof(T)));
+    }
+    owned.push_back(q);
+    if (zero && cudaMemset(q, 0, count * sizeof(T)) != cudaSuccess) return fail(EARL_ERR_CUDA, "cudaMemset failed%s", "");
+    *ptr = static_cast<T*>(q);
+    return 0;
+  }
+};
+
+namespace {
+
+int check(const earl_tt3_handle* h) {
+  if (!h) return fail(EARL_ERR_INVALID, "null handle%s", "");
+  CU(cudaSetDevice(h->cfg.device));
+  return 0;
+}
+
+int grid_for(long long n) { return (int)((n + kBlock - 1) / kBlock); }
+
+int launch_step(earl_tt3_handle* h, int first, int count, const float* actions, float* obs, float* reward, uint8_t* done,
+                uint8_t* success, cudaStream_t s) {
+  T3Params p = h->p;
+  p.first = first;
+  p.count = count;
+  p.actions = actions;
+  p.obs = obs;
+  p.reward = reward;
+  p.done = done;
+  p.success = success;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid_for(count));
+  cfg.blockDim = dim3(kBlock);
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = h->pdl ? 1 : 0;
+  CU(cudaLaunchKernelEx(&cfg, tt3_step_kernel, p));
+  h->launches += 1;
+  return 0;
+}
+
+bool aligned16(const void* q) { return ((uintptr_t)q & 15u) == 0; }
+
+}  // namespace
+
+extern "C" {
+
+int earl_tt3_create(const earl_tt3_config* cfg, size_t cfg_nbytes, earl_tt3_handle** out) {
+  if (!cfg || !out) return fail(EARL_ERR_INVALID, "null argument%s", "");
+  if (cfg_nbytes != sizeof(earl_tt3_config)) return fail(EARL_ERR_INVALID, "earl_tt3_config size mismatch%s (%lld)", "", (long long)cfg_nbytes);
+  if (cfg->num_envs < 1) return fail(EARL_ERR_INVALID, "num_envs must be >= 1%s", "");
+  if (cfg->num_goals < 1 || cfg->num_goals > EARL_TT3_MAX_GOALS) return fail(EARL_ERR_INVALID, "num_goals out of range%s", "");
+  if (cfg->flags & ~(uint32_t)EARL_FLAG_DENSE_REWARD) return fail(EARL_ERR_UNSUPPORTED, "unsupported flag for the three-object tabletop%s", "");
+  if (cfg->episode_horizon < 1) return fail(EARL_ERR_INVALID, "episode_horizon must be >= 1%s", "");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || cfg->device < 0 || cfg->device >= ndev) {
+    cudaGetLastError();
+    return fail(EARL_ERR_CUDA, "no usable CUDA device %s(requested %lld); there is no CPU fallback", "", (long long)cfg->device);
+  }
+  CU(cudaSetDevice(cfg->device));
+  earl_tt3_handle* h = new (std::nothrow) earl_tt3_handle();
+  if (!h) return fail(EARL_ERR_NOMEM, "out of host memory%s", "");
+  h->cfg = *cfg;
+  const size_t n = (size_t)cfg->num_envs;
+  T3Params& p = h->p;
+  int rc = 0;
+  for (int k = 0; k < 4 && !rc; ++k) rc = h->alloc(&p.q[k], n);
+  if (!rc) rc = h->alloc(&p.meta, n);
+  if (!rc) rc = h->alloc(&p.interventions, n);
+  float* gf = nullptr;
+  double* gd = nullptr;
+  if (!rc) rc = h->alloc(&gf, (size_t)EARL_TT3_MAX_GOALS * 10);
+  if (!rc) rc = h->alloc(&gd, (size_t)EARL_TT3_MAX_GOALS * 10);
+  if (rc) {
+    earl_tt3_destroy(h);
+    return rc;
+  }
+  float g32[EARL_TT3_MAX_GOALS][10];
+  for (int r = 0; r < EARL_TT3_MAX_GOALS; ++r)
+    for (int k = 0; k < 10; ++k) g32[r][k] = (float)cfg->goal_table[r][k];
+  if (cudaMemcpy(gf, g32, sizeof(g32), cudaMemcpyHostToDevice) != cudaSuccess ||
+      cudaMemcpy(gd, cfg->goal_table, sizeof(cfg->goal_table), cudaMemcpyHostToDevice) != cudaSuccess) {
+    earl_tt3_destroy(h);
+    return fail(EARL_ERR_CUDA, "goal table upload failed%s", "");
+  }
+  p.goal_f32 = gf;
+  p.goal_f64 = gd;
+  p.n = cfg->num_envs;
+  p.first = 0;
+  p.count = cfg->num_envs;
+  p.dense = (cfg->flags & EARL_FLAG_DENSE_REWARD) ? 1 : 0;
+  p.horizon = (unsigned long long)cfg->episode_horizon;
+  p.act_lo = -cfg->move_distance;
+  p.act_span = cfg->move_distance - (-cfg->move_distance);
+  p.threshold = cfg->threshold;
+  p.clip = cfg->clip;
+  p.success_radius = cfg->success_radius;
+  for (int k = 0; k < 8; ++k) p.init_qpos[k] = cfg->initial_state[k];
+  const char* e = getenv("EARL_TT_PDL");
+  h->pdl = !(e && e[0] == '0');
+  *out = h;
+  return 0;
+}
+
+int earl_tt3_destroy(earl_tt3_handle* h) {
+  if (!h) return 0;
+  cudaSetDevice(h->cfg.device);
+  cudaDeviceSynchronize();
+  for (void* q : h->owned) cudaFree(q);
+  if (h->in_stream) cudaStreamDestroy(h->in_stream);
+  if (h->out_stream) cudaStreamDestroy(h->out_stream);
+  for (auto& ev : h->chunk_ev)
+    if (ev) cudaEventDestroy(ev);
+  delete h;
+  return 0;
+}
+
+int earl_tt3_reset(earl_tt3_handle* h, const uint8_t* mask_dev, const int32_t* goal_idx_dev, const double* init_qpos_dev,
+                   float* obs_out_dev, void* stream) {
+  if (int rc = check(h)) return rc;
+  T3Params p = h->p;
+  p.obs = obs_out_dev;
+  tt3_reset_kernel<<<grid_for(p.n), kBlock, 0, (cudaStream_t)stream>>>(p, mask_dev, goal_idx_dev, init_qpos_dev, 0, h->cfg.num_goals);
+  CU(cudaGetLastError());
+  h->launches += 1;
+  return 0;
+}
+
+int earl_tt3_set_goal(earl_tt3_handle* h, const uint8_t* mask_dev, const int32_t* goal_idx_dev, void* stream) {
+  if (int rc = check(h)) return rc;
+  T3Params p = h->p;
+  p.obs = nullptr;
+  tt3_reset_kernel<<<grid_for(p.n), kBlock, 0, (cudaStream_t)stream>>>(p, mask_dev, goal_idx_dev, nullptr, 1, h->cfg.num_goals);
+  CU(cudaGetLastError());
+  h->launches += 1;
+  return 0;
+}
+
+int earl_tt3_step(earl_tt3_handle* h, const float* actions_dev, float* obs_dev, float* reward_dev, uint8_t* done_dev,
+                  uint8_t* success_dev, void* stream) {
+  if (int rc = check(h)) return rc;
+  if (!actions_dev || !obs_dev || !reward_dev || !done_dev) return fail(EARL_ERR_INVALID, "null device buffer%s", "");
+  if (!aligned16(actions_dev) || !aligned16(obs_dev)) return fail(EARL_ERR_INVALID, "actions and obs must be 16-byte aligned%s", "");
+  if (int rc = launch_step(h, 0, h->p.n, actions_dev, obs_dev, reward_dev, done_dev, success_dev, (cudaStream_t)stream)) return rc;
+  h->total_steps += 1;
+  return 0;
+}
+
+int earl_tt3_rollout(earl_tt3_handle* h, const float* actions_dev, int32_t action_ring, int32_t num_steps, float* obs_dev,
+                     float* reward_dev, uint8_t* done_dev, uint8_t* success_dev, int32_t out_ring, void* stream) {
+  if (int rc = check(h)) return rc;
+  if (!actions_dev || !obs_dev || !reward_dev || !done_dev || action_ring < 1 || out_ring < 1 || num_steps < 0)
+    return fail(EARL_ERR_INVALID, "bad rollout argument%s", "");
+  const size_t n = (size_t)h->p.n;
+  if (!aligned16(actions_dev) || !aligned16(obs_dev) || ((n * kAct * sizeof(float)) & 15u) && action_ring > 1)
+    return fail(EARL_ERR_INVALID, "rollout buffers must keep every slot 16-byte aligned%s", "");
+  for (int t = 0; t < num_steps; ++t) {
+    const size_t a = (size_t)(t % action_ring), o = (size_t)(t % out_ring);
+    if (int rc = launch_step(h, 0, (int)n, actions_dev + a * n * kAct, obs_dev + o * n * kObs, reward_dev + o * n, done_dev + o * n,
+                             success_dev ? success_dev + o * n : nullptr, (cudaStream_t)stream))
+      return rc;
+    h->total_steps += 1;
+  }
+  return 0;
+}
+
+int earl_tt3_step_host(earl_tt3_handle* h, const float* actions_host, float* obs_host, float* reward_host, uint8_t* done_host,
+                       uint8_t* success_host) {
+  if (int rc = check(h)) return rc;
+  if (!actions_host || !obs_host || !reward_host || !done_host) return fail(EARL_ERR_INVALID, "null host buffer%s", "");
+  const size_t n = (size_t)h->p.n;
+  if (!h->d_act) {
+    int rc = h->alloc(&h->d_act, n * kAct, false);
+    if (!rc) rc = h->alloc(&h->d_obs, n * kObs, false);
+    if (!rc) rc = h->alloc(&h->d_rew, n, false);
+    if (!rc) rc = h->alloc(&h->d_done, n, false);
+    if (!rc) rc = h->alloc(&h->d_succ, n, false);
+    if (rc) return rc;
+    CU(cudaStreamCreateWithFlags(&h->in_stream, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&h->out_stream, cudaStreamNonBlocking));
+    for (auto& ev : h->chunk_ev) CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  }
+  // chunked pipeline over the full-duplex PCIe link: the upload of chunk c+1 overlaps the kernel and the
+  // downloads of chunk c
+  CU(cudaDeviceSynchronize());  // order after whatever the caller enqueued on its own streams
+  int chunks = (int)(n / (128 * 1024));
+  chunks = chunks < 1 ? 1 : (chunks > earl_tt3_handle::kMaxChunks ? earl_tt3_handle::kMaxChunks : chunks);
+  const size_t per = ((n / chunks + 255) / 256) * 256;
+  cudaStream_t si = h->in_stream, so = h->out_stream;
+  int c = 0;
+  for (size_t off = 0; off < n; off += per, ++c) {
+    const size_t cnt = off + per <= n ? per : n - off;
+    CU(cudaMemcpyAsync(h->d_act + off * kAct, actions_host + off * kAct, cnt * kAct * sizeof(float), cudaMemcpyHostToDevice, si));
+    CU(cudaEventRecord(h->chunk_ev[c], si));
+    CU(cudaStreamWaitEvent(so, h->chunk_ev[c], 0));
+    if (int rc = launch_step(h, (int)off, (int)cnt, h->d_act, h->d_obs, h->d_rew, h->d_done, success_host ? h->d_succ : nullptr, so))
+      return rc;
+    CU(cudaMemcpyAsync(obs_host + off * kObs, h->d_obs + off * kObs, cnt * kObs * sizeof(float), cudaMemcpyDeviceToHost, so));
+    CU(cudaMemcpyAsync(reward_host + off, h->d_rew + off, cnt * sizeof(float), cudaMemcpyDeviceToHost, so));
+    CU(cudaMemcpyAsync(done_host + off, h->d_done + off, cnt, cudaMemcpyDeviceToHost, so));
+    if (success_host) CU(cudaMemcpyAsync(success_host + off, h->d_succ + off, cnt, cudaMemcpyDeviceToHost, so));
+  }
+  h->total_steps += 1;
+  CU(cudaStreamSynchronize(so));
+  return 0;
+}
+
+int earl_tt3_get_obs(earl_tt3_handle* h, float* obs_dev, void* stream) {
+  if (int rc = check(h)) return rc;
+  if (!obs_dev) return fail(EARL_ERR_INVALID, "null obs%s", "");
+  T3Params p = h->p;
+  p.obs = obs_dev;
+  tt3_reset_kernel<<<grid_for(p.n), kBlock, 0, (cudaStream_t)stream>>>(p, nullptr, nullptr, nullptr, 2, h->cfg.num_goals);
+  CU(cudaGetLastError());
+  h->launches += 1;
+  return 0;
+}
+
+int earl_tt3_compute_reward(earl_tt3_handle* h, const float* obs_dev, int64_t num_obs, float* reward_dev, uint8_t* success_dev,
+                            void* stream) {
+  if (int rc = check(h)) return rc;
+  if (!obs_dev || num_obs < 0) return fail(EARL_ERR_INVALID, "bad observation buffer%s", "");
+  if (num_obs == 0) return 0;
+  tt3_reward_kernel<<<grid_for(num_obs), kBlock, 0, (cudaStream_t)stream>>>(obs_dev, (long long)num_obs, reward_dev, success_dev,
+                                                                           h->p.dense, h->p.success_radius);
+  CU(cudaGetLastError());
+  h->launches += 1;
+  return 0;
+}
+
+int earl_tt3_counters(earl_tt3_handle* h, int64_t* total_steps_host, int64_t* num_interventions_dev, uint32_t* steps_since_reset_dev,
+                      void* stream) {
+  if (int rc = check(h)) return rc;
+  if (total_steps_host) *total_steps_host = h->total_steps;
+  if (num_interventions_dev || steps_since_reset_dev) {
+    tt3_counters_kernel<<<grid_for(h->p.n), kBlock, 0, (cudaStream_t)stream>>>(h->p, (long long*)num_interventions_dev,
+                                                                              steps_since_reset_dev);
+    CU(cudaGetLastError());
+    h->launches += 1;
+  }
+  return 0;
+}
+
+int earl_tt3_get_state(earl_tt3_handle* h, double* qpos_dev, int32_t* attached_dev, void* stream) {
+  if (int rc = check(h)) return rc;
+  tt3_state_kernel<<<grid_for(h->p.n), kBlock, 0, (cudaStream_t)stream>>>(h->p, qpos_dev, attached_dev, nullptr, nullptr);
+  CU(cudaGetLastError());
+  h->launches += 1;
+  return 0;
+}
+
+int earl_tt3_set_state(earl_tt3_handle* h, const double* qpos_dev, const int32_t* attached_dev, void* stream) {
+  if (int rc = check(h)) return rc;
+  tt3_state_kernel<<<grid_for(h->p.n), kBlock, 0, (cudaStream_t)stream>>>(h->p, nullptr, nullptr, qpos_dev, attached_dev);
+  CU(cudaGetLastError());
+  h->launches += 1;
+  return 0;
+}
+
+int64_t earl_tt3_launch_count(const earl_tt3_handle* h) { return h ? h->launches : 0; }
+
+}  // extern "C"

@@ -9,7 +9,7 @@ import pytest
 from conftest import REPO
 from earl_benchmark_b200 import _lib, build
 
-HEADERS = [os.path.join(REPO, "include", f) for f in ("earl_b200.h", "earl_mj_b200.h", "earl_mj_kitchen_b200.h")]
+HEADERS = [os.path.join(REPO, "include", f) for f in ("earl_b200.h", "earl_tt3_b200.h", "earl_mj_b200.h", "earl_mj_kitchen_b200.h")]
 
 
 def header_symbols():
@@ -42,6 +42,7 @@ def test_struct_layouts_match_header():
     assert ctypes.sizeof(_lib.EarlConfig) == 40
     assert ctypes.sizeof(_lib.TabletopModel) == 8 + 4 * 8 + 6 * 8 + 256 * 6 * 8
     assert ctypes.sizeof(_lib.MjConfig) == 32
+    assert ctypes.sizeof(_lib.Tt3Config) == 16 + 8 + 4 * 8 + 10 * 8 + 16 * 10 * 8
     assert ctypes.sizeof(_lib.MjTask) == 8 * 4 + 8 * 4 + 6 * 4 + 7 * 4
 
 

@@ -1,0 +1,191 @@
+"""Three-object tabletop on the B200 (csrc/earl_tt3.cu through include/earl_tt3_b200.h) against
+  * outputs of the UNMODIFIED reference class (tests/golden/tabletop3_ref_rollouts.npz, oracle/gen_golden_3obj.py),
+  * the numpy restatement oracle/tabletop3.py on seeded batched rollouts,
+  * size-independent properties at 1,048,576 envs.
+Bar: bit-exact for state, observations, sparse reward, success, done and counters; dense reward within 2e-6
+relative (the reference evaluates it in fp64 after fp32 norms, the device returns the fp32 cast)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import REPO
+from oracle import tabletop3
+
+pytestmark = pytest.mark.gpu
+
+GOLD = np.load(os.path.join(REPO, "tests", "golden", "tabletop3_ref_rollouts.npz"))
+
+
+def make(n, horizon=None, **kw):
+    from earl_benchmark_b200.envs.tabletop_manipulation_3obj import TabletopManipulation
+    from earl_benchmark_b200.wrappers import PersistentStateWrapper
+    env = TabletopManipulation(num_envs=n, device="cuda:0", **kw)
+    return PersistentStateWrapper(env, horizon) if horizon else env
+
+
+def gold(prefix):
+    return {k[len(prefix) + 1:]: GOLD[k] for k in GOLD.files if k.startswith(prefix + "_")}
+
+
+@pytest.mark.parametrize("prefix,horizon,reward_type,n", [("sparse", 900, "sparse", 33), ("dense", 700, "dense", 1)])
+def test_replay_of_the_reference_rollout(prefix, horizon, reward_type, n):
+    g = gold(prefix)
+    env = make(n, horizon, reward_type=reward_type)
+    o = env.reset().cpu().numpy()
+    assert np.array_equal(o, np.broadcast_to(g["obs"][0], (n, 20)))
+    for t in range(len(g["actions"])):
+        a = torch.from_numpy(np.broadcast_to(g["actions"][t], (n, 3)).copy()).cuda()
+        o, r, d, info = env.step(a)
+        o, r, d, s = o.cpu().numpy(), r.cpu().numpy(), d.cpu().numpy(), info["success"].cpu().numpy()
+        assert (o == o[0]).all() and (r == r[0]).all()
+        if not g["reset_after"][t]:
+            assert np.array_equal(o[0], g["obs"][t + 1]), t
+        if reward_type == "sparse":
+            assert r[0] == g["reward"][t], t
+        else:
+            assert abs(float(r[0]) - g["reward"][t]) <= 2e-6 * max(1.0, abs(g["reward"][t])), t
+        assert bool(d[0]) == bool(g["done"][t]) and bool(s[0]) == bool(g["success"][t]), t
+        if g["reset_after"][t]:
+            assert np.array_equal(env.reset().cpu().numpy()[0], g["obs"][t + 1])
+        if t % 500 == 499 or t == len(g["actions"]) - 1:
+            q, att = env.get_state()
+            if not g["reset_after"][t]:
+                assert np.array_equal(q.cpu().numpy()[0], g["qpos"][t + 1])          # fp64 state, bit for bit
+                assert int(att[0]) == g["attached"][t + 1]
+            assert env.total_steps == g["total_steps"][t]
+            assert (env.num_interventions.cpu().numpy() == g["num_interventions"][t] + (1 if g["reset_after"][t] else 0)).all()
+
+
+def test_closest_object_attach_cases_from_the_reference():
+    q0, acts = GOLD["attach_q0"], GOLD["attach_actions"]
+    env = make(len(q0), reward_type="sparse")
+    env.reset()
+    env.set_state(qpos=q0, attached=0)
+    o, _, _, _ = env.step(torch.from_numpy(acts).cuda())
+    q, att = env.get_state()
+    assert np.array_equal(att.cpu().numpy(), GOLD["attach_att"])
+    assert np.array_equal(q.cpu().numpy(), GOLD["attach_q1"])
+    assert np.array_equal(o.cpu().numpy(), GOLD["attach_obs"])
+
+
+def test_reset_at_goal_draws_match_the_reference_stream():
+    g = gold("rag")
+    env = make(1, 50, reward_type="sparse", reset_at_goal=True, seed=5)   # the fixture ran np.random.seed(5)
+    o = env.reset().cpu().numpy()[0]
+    assert np.array_equal(o, g["obs"][0])
+    resets = 0
+    for t in range(len(g["actions"])):
+        o, r, d, _ = env.step(torch.from_numpy(g["actions"][t][None]).cuda())
+        assert bool(d[0]) == bool(g["done"][t])
+        if g["reset_after"][t]:
+            assert np.array_equal(env.reset().cpu().numpy()[0], g["obs"][t + 1])
+            resets += 1
+        else:
+            assert np.array_equal(o.cpu().numpy()[0], g["obs"][t + 1]), t
+    assert resets == 8 and int(env.num_interventions[0]) == 9
+
+
+def biased_actions(rs, steps, n):
+    a = rs.uniform(-1.2, 1.2, (steps, n, 3)).astype(np.float32)
+    a[:, : n // 2, 2] = np.where(rs.uniform(size=(steps, n // 2)) < 0.9, 1.0, -1.0)
+    return a
+
+
+@pytest.mark.parametrize("reward_type", ["sparse", "dense"])
+def test_batched_rollout_against_the_checker(reward_type):
+    n, steps, horizon = 5003, 260, 64            # ragged: not a multiple of the 256-env tile
+    rs = np.random.RandomState(11)
+    env = make(n, horizon, reward_type=reward_type)
+    orc = tabletop3.Tabletop3Oracle(n, horizon, dense=reward_type == "dense")
+    # objects scattered around the fist so all three get grasped and dragged
+    q0 = np.concatenate([rs.uniform(-2, 2, (n, 2))] * 4, axis=1) + np.concatenate([np.zeros((n, 2)), rs.uniform(-0.6, 0.6, (n, 6))], axis=1)
+    assert np.array_equal(env.reset(init_qpos=q0).cpu().numpy(), orc.reset(init_qpos=q0))
+    acts = biased_actions(rs, steps, n)
+    seen = set()
+    for t in range(steps):
+        if t % 3 == 2:
+            o, r, d, info = env.step(acts[t])                       # host path (numpy in, numpy out)
+            s = info["success"]
+        else:
+            o, r, d, info = env.step(torch.from_numpy(acts[t]).cuda())
+            o, r, d, s = o.cpu().numpy(), r.cpu().numpy(), d.cpu().numpy(), info["success"].cpu().numpy()
+        o2, r2, d2, s2 = orc.step(acts[t])
+        assert np.array_equal(o, o2), t
+        assert np.array_equal(d, d2) and np.array_equal(s, s2), t
+        if reward_type == "sparse":
+            assert np.array_equal(r.astype(np.float64), r2), t
+        else:
+            assert np.allclose(r, r2, rtol=2e-6, atol=2e-6), t
+        seen |= set(np.unique(orc.att))
+        if d2.any():                                                # reset the finished envs only
+            assert np.array_equal(env.reset(mask=d2).cpu().numpy(), orc.reset(mask=d2))
+    q, att = env.get_state()
+    assert np.array_equal(q.cpu().numpy(), orc.qpos) and np.array_equal(att.cpu().numpy(), orc.att)
+    assert env.total_steps == orc.total_steps == steps
+    assert np.array_equal(env.num_interventions.cpu().numpy(), orc.num_interventions)
+    assert np.array_equal(env.steps_since_reset.cpu().numpy(), orc.steps_since_reset)
+    assert seen == {0, 1, 2, 3}
+    assert env.launch_count >= steps
+
+
+def test_compute_reward_and_is_successful_on_reference_observations():
+    g = gold("dense")
+    env = make(1, reward_type="dense")
+    obs = g["obs"][1:]
+    keep = ~g["reset_after"].astype(bool)
+    r = env.compute_reward(obs)
+    s = env.is_successful(obs)
+    assert np.allclose(r[keep], g["reward"][keep], rtol=2e-6, atol=2e-6)
+    assert np.array_equal(s[keep], g["success"][keep].astype(bool))
+    env2 = make(1, reward_type="sparse")
+    gs = gold("sparse")
+    keep = ~gs["reset_after"].astype(bool)
+    assert np.array_equal(env2.compute_reward(gs["obs"][1:])[keep].astype(np.float64), gs["reward"][keep])
+
+
+def test_rollout_entry_point_equals_single_steps():
+    n, steps = 4096, 40
+    rs = np.random.RandomState(3)
+    acts = torch.from_numpy(biased_actions(rs, 8, n)).cuda()
+    a, b = make(n, 1000, reward_type="sparse"), make(n, 1000, reward_type="sparse")
+    a.reset(), b.reset()
+    obs = torch.empty((4, n, 20), device="cuda")
+    rew = torch.empty((4, n), device="cuda")
+    done = torch.empty((4, n), dtype=torch.uint8, device="cuda")
+    a.rollout_into(acts, steps, obs, rew, done)
+    for t in range(steps):
+        o, r, d, _ = b.step(acts[t % 8])
+    assert torch.equal(obs[(steps - 1) % 4], o) and torch.equal(rew[(steps - 1) % 4], r)
+    assert a.total_steps == b.total_steps == steps
+
+
+def test_full_size_properties():
+    """1,048,576 envs: results do not depend on the batch an env is stepped in, positions stay inside the
+    workspace, only the grasped object moves and it moves with the fist, counters are exact."""
+    n, m, steps = 1 << 20, 4096, 24
+    big, small = make(n, 1 << 40, reward_type="sparse"), make(m, 1 << 40, reward_type="sparse")
+    g = torch.Generator(device="cuda").manual_seed(1234)
+    q0 = (torch.rand((n, 2), generator=g, device="cuda", dtype=torch.float64) * 4 - 2).repeat(1, 4)
+    q0[:, 2:] += torch.rand((n, 6), generator=g, device="cuda", dtype=torch.float64) * 1.2 - 0.6
+    big.reset(init_qpos=q0.cpu().numpy()), small.reset(init_qpos=q0[:m].cpu().numpy())
+    prev, _ = big.get_state()
+    prev = prev.clone()
+    for t in range(steps):
+        a = torch.rand((n, 3), generator=g, device="cuda") * 2.4 - 1.2
+        a[: n // 2, 2] = 1.0
+        ob, rb, db, ib = big.step(a)
+        os_, rs_, ds_, is_ = small.step(a[:m].contiguous())
+        assert torch.equal(ob[:m], os_) and torch.equal(rb[:m], rs_)
+        q, att = big.get_state()
+        assert float(q.abs().max()) <= 2.8
+        moved = (q[:, 2:] != prev[:, 2:]).view(n, 3, 2).any(-1)
+        assert int(moved.sum(1).max()) <= 1
+        held = att.long() - 1
+        rowsel = moved.any(1)
+        assert torch.equal(moved[rowsel].long().argmax(1), held[rowsel])
+        assert torch.equal(ob[:, :8], q.float()) and not bool(db.any())
+        prev = q.clone()
+    assert big.total_steps == steps and int(big.steps_since_reset.min()) == steps
+    assert int(big.num_interventions.min()) == int(big.num_interventions.max()) == 1
