@@ -344,7 +344,7 @@ def run_tt3(dev, rank, world, with_e2e):
 
     from earl_benchmark_b200.distributed import max_over_ranks
     from earl_benchmark_b200.envs.tabletop_manipulation_3obj import TabletopManipulation
-    from earl_benchmark_b200.wrappers import PersistentStateWrapper
+    from earl_benchmark_b200.wrappers.persistent_state_wrapper import PersistentStateWrapper
 
     n, warm, steps = TT3_ENVS, 20, 200
     env = PersistentStateWrapper(TabletopManipulation(reward_type="sparse", num_envs=n, device=dev, seed=rank), TRAIN_HORIZON)

@@ -20,7 +20,7 @@ GOLD = np.load(os.path.join(REPO, "tests", "golden", "tabletop3_ref_rollouts.npz
 
 def make(n, horizon=None, **kw):
     from earl_benchmark_b200.envs.tabletop_manipulation_3obj import TabletopManipulation
-    from earl_benchmark_b200.wrappers import PersistentStateWrapper
+    from earl_benchmark_b200.wrappers.persistent_state_wrapper import PersistentStateWrapper
     env = TabletopManipulation(num_envs=n, device="cuda:0", **kw)
     return PersistentStateWrapper(env, horizon) if horizon else env
 
