@@ -7,7 +7,8 @@
 //     read and written with fully coalesced 16 / 8-byte accesses;
 //   * actions [N,3] f32 and observations [N,20] f32 are row-major at the boundary: a block moves its 256-env
 //     tile through shared memory so the global accesses are contiguous float4 (3 KB in, 20 KB out per block);
-//   * algorithmic bytes per env-step: read 12 + 64 + 8 = 84, write 64 + 8 + 80 + 4 + 1 + 1 = 158  (242 B).
+//   * algorithmic bytes per env-step: read 12 + 64 + 8 = 84, write fist 16 + meta 8 + obs 80 + 4 + 1 + 1 = 110  (194 B;
+//     + 16 for the envs that drag an object: only that plane is written back).
 // Compiled with --fmad=false: every fp64 / fp32 operation below rounds exactly where numpy rounds; the one
 // fused operation numpy's BLAS performs (the 2-element fp64 dot) is written as an explicit fma.
 // There is no CPU fallback in this file.

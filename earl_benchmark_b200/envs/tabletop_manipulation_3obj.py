@@ -191,7 +191,7 @@ class TabletopManipulation:
             init_qpos = q
         iq = None
         if init_qpos is not None:
-            iq = torch.as_tensor(np.ascontiguousarray(np.broadcast_to(np.asarray(init_qpos, np.float64), (self.num_envs, 8)))).to(self.device)
+            iq = torch.as_tensor(np.array(np.broadcast_to(np.asarray(init_qpos, np.float64), (self.num_envs, 8)))).to(self.device)
         self._goal_rows[sel] = rows[sel]
         gi = torch.from_numpy(rows).to(self.device)
         _lib.check(_lib.lib().earl_tt3_reset(self._handle, _ptr(m), gi.data_ptr(), _ptr(iq), 0, _stream()))
@@ -295,7 +295,7 @@ class TabletopManipulation:
         self._ensure()
         q = a = None
         if qpos is not None:
-            q = torch.as_tensor(np.ascontiguousarray(np.broadcast_to(np.asarray(
+            q = torch.as_tensor(np.array(np.broadcast_to(np.asarray(
                 qpos.detach().cpu().numpy() if isinstance(qpos, torch.Tensor) else qpos, np.float64)[..., :8], (self.num_envs, 8)))).to(self.device)
         if attached is not None:
             a = torch.as_tensor(np.broadcast_to(np.asarray(attached, np.int32), (self.num_envs,)).copy()).to(self.device)
