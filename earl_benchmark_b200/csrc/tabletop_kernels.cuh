@@ -97,8 +97,8 @@ __device__ __forceinline__ float norm2_f32(float a, float b) {
   return __fsqrt_rn(__fadd_rn(__fmul_rn(a, a), __fmul_rn(b, b)));
 }
 
-// is_successful on an fp32 observation (tabletop_manipulation.py:197-204): fp32 squared norm in index
-// order, nothing fused; `success_sq` is the exact sqrt-free threshold (see TabletopParams)
+// is_successful on an fp32 observation (tabletop_manipulation.py:197-204): fp32 products summed in index
+// order in fp64 and rounded to fp32 (what np.linalg.norm does), nothing fused; `success_sq` is the exact sqrt-free threshold (see TabletopParams)
 __device__ __forceinline__ bool tt_success(const float4& pos, const float4& g0, bool wide, float success_sq) {
   // pos = obs[0:4]; g0 = obs[6:10] = goal[0:4]
   const float dz = __fsub_rn(pos.z, g0.z), dw = __fsub_rn(pos.w, g0.w);
@@ -106,10 +106,13 @@ __device__ __forceinline__ bool tt_success(const float4& pos, const float4& g0, 
   if (wide) {
     s = __fadd_rn(__fmul_rn(dz, dz), __fmul_rn(dw, dw));
   } else {
+    // numpy's fp32 dot accumulates the fp32 products in fp64 and rounds once (OpenBLAS sdot):
+    // with two terms that equals the fp32 sum above, with four it does not
     const float dx = __fsub_rn(pos.x, g0.x), dy = __fsub_rn(pos.y, g0.y);
-    s = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
-    s = __fadd_rn(s, __fmul_rn(dz, dz));
-    s = __fadd_rn(s, __fmul_rn(dw, dw));
+    double acc = __dadd_rn((double)__fmul_rn(dx, dx), (double)__fmul_rn(dy, dy));
+    acc = __dadd_rn(acc, (double)__fmul_rn(dz, dz));
+    acc = __dadd_rn(acc, (double)__fmul_rn(dw, dw));
+    s = (float)acc;
   }
   return s <= success_sq;
 }

@@ -39,12 +39,19 @@ static inline double clipd(double x, double lo, double hi) {
   return x < lo ? lo : (x > hi ? hi : x);
 }
 
-/* np.linalg.norm on an fp32 vector: fp32 products and sums, fp32 sqrt */
+/* np.linalg.norm on an fp32 vector: fp32 products, accumulated in index order in fp64 (OpenBLAS sdot keeps a
+ * double accumulator: checked against numpy in tests/test_oracle_golden.py), rounded to fp32, fp32 sqrt */
 static inline float norm_f32(const float *d, int n) {
-  float s = d[0] * d[0];
-  for (int i = 1; i < n; ++i) s = s + d[i] * d[i];
-  return sqrtf(s);
+  double s = 0.0;
+  for (int i = 0; i < n; ++i) {
+    float p = d[i] * d[i];
+    s += (double)p;
+  }
+  return sqrtf((float)s);
 }
+
+/* test hook: the norm restatement on caller data */
+float earl_oracle_norm_f32(const float *d, int n) { return norm_f32(d, n); }
 
 /* tabletop_manipulation.py:55-60 */
 static inline void tt_obs(const double *qpos, int attached, const double *goal, float *obs) {

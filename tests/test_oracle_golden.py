@@ -134,3 +134,19 @@ def test_demo_transitions(golden_dir, direction):
     assert np.array_equal(out[:, 4:], d["next_observations"][:, 4:])      # attach flags + goal exact
     assert np.array_equal(rw, d["rewards"][:, 0].astype(np.float64))       # 0 reward mismatches
     assert (obs[:, 4] == 0).mean() > 0.4                                   # demos exercise the attach path
+
+
+def test_fp32_norm_restatement_matches_numpy():
+    """np.linalg.norm of an fp32 vector = fp32 products accumulated in index order in fp64, rounded to fp32, fp32
+    sqrt: the C restatement against numpy itself on random 2- and 4-vectors (the two sizes the task uses)."""
+    import ctypes as C
+    from oracle import loader
+    L = loader.lib()
+    L.earl_oracle_norm_f32.restype = C.c_float
+    L.earl_oracle_norm_f32.argtypes = [C.c_void_p, C.c_int]
+    rs = np.random.RandomState(5)
+    for n in (2, 4):
+        for scale in (3.0, 0.15):
+            x = rs.uniform(-scale, scale, (4000, n)).astype(np.float32)
+            got = np.array([L.earl_oracle_norm_f32(v.ctypes.data, n) for v in x], np.float32)
+            assert np.array_equal(got, np.array([np.linalg.norm(v) for v in x], np.float32))
