@@ -376,6 +376,19 @@ def run_tt3(dev, rank, world, with_e2e):
            "holding_fraction": float((att > 0).float().mean()),
            "l2": "inputs larger than L2: state 288 MB, action ring 8 x 50 MB, output ring 4 x 360 MB"}
     if with_e2e:
+        # CPU baseline of this section: the numpy restatement (oracle/tabletop3.py) on one host core, bounded sample
+        from oracle.tabletop3 import Tabletop3Oracle
+        cn, ck = 1 << 16, 100
+        orc = Tabletop3Oracle(cn, TRAIN_HORIZON)
+        orc.reset()
+        ca = actions[0, :cn].cpu().numpy()
+        orc.step(ca)
+        c0 = time.perf_counter()
+        for _ in range(ck):
+            orc.step(ca)
+        cel = time.perf_counter() - c0
+        out["cpu_baseline"] = {"value": cn * ck / cel, "unit": UNIT, "cores": 1, "kind": "port",
+                               "sample": f"{cn} envs x {ck} steps, vectorised numpy restatement of the reference class, {cel:.2f} s"}
         m = 1 << 20
         del env, obs, rew, done, succ, actions
         e = PersistentStateWrapper(TabletopManipulation(reward_type="sparse", num_envs=m, device=dev, seed=rank), TRAIN_HORIZON)

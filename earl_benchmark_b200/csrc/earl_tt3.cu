@@ -15,6 +15,7 @@
 #include "../../include/earl_tt3_b200.h"
 
 #include <cmath>
+#include <cstdarg>
 #include <cstdio>
 #include <cstring>
 #include <new>
@@ -287,15 +288,18 @@ __global__ void __launch_bounds__(kBlock) tt3_counters_kernel(const __grid_const
 
 thread_local char g_msg[512];
 
-int fail(int code, const char* fmt, const char* a = "", long long b = 0) {
-  snprintf(g_msg, sizeof(g_msg), fmt, a, b);
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_msg, sizeof(g_msg), fmt, ap);
+  va_end(ap);
   return earl::set_error(code, g_msg);
 }
 
 #define CU(call)                                                                  \
   do {                                                                            \
     cudaError_t e_ = (call);                                                      \
-    if (e_ != cudaSuccess) return fail(EARL_ERR_CUDA, "%s (earl_tt3.cu:%lld)", cudaGetErrorString(e_), __LINE__); \
+    if (e_ != cudaSuccess) return fail(EARL_ERR_CUDA, "%s (earl_tt3.cu:%d)", cudaGetErrorString(e_), __LINE__); \
   } while (0)
 
 }  // namespace
@@ -321,10 +325,10 @@ struct earl_tt3_handle {
     void* q = nullptr;
     if (cudaMalloc(&q, count * sizeof(T) + 16) != cudaSuccess) {
       cudaGetLastError();
-      return fail(EARL_ERR_NOMEM, "cudaMalloc of %s%lld bytes failed", "", (long long)(count * sizeof(T)));
+      return fail(EARL_ERR_NOMEM, "cudaMalloc of %zu bytes failed", count * sizeof(T));
     }
     owned.push_back(q);
-    if (zero && cudaMemset(q, 0, count * sizeof(T)) != cudaSuccess) return fail(EARL_ERR_CUDA, "cudaMemset failed%s", "");
+    if (zero && cudaMemset(q, 0, count * sizeof(T)) != cudaSuccess) return fail(EARL_ERR_CUDA, "cudaMemset failed");
     *ptr = static_cast<T*>(q);
     return 0;
   }
@@ -333,7 +337,7 @@ struct earl_tt3_handle {
 namespace {
 
 int check(const earl_tt3_handle* h) {
-  if (!h) return fail(EARL_ERR_INVALID, "null handle%s", "");
+  if (!h) return fail(EARL_ERR_INVALID, "null handle");
   CU(cudaSetDevice(h->cfg.device));
   return 0;
 }
@@ -371,20 +375,20 @@ bool aligned16(const void* q) { return ((uintptr_t)q & 15u) == 0; }
 extern "C" {
 
 int earl_tt3_create(const earl_tt3_config* cfg, size_t cfg_nbytes, earl_tt3_handle** out) {
-  if (!cfg || !out) return fail(EARL_ERR_INVALID, "null argument%s", "");
-  if (cfg_nbytes != sizeof(earl_tt3_config)) return fail(EARL_ERR_INVALID, "earl_tt3_config size mismatch%s (%lld)", "", (long long)cfg_nbytes);
-  if (cfg->num_envs < 1) return fail(EARL_ERR_INVALID, "num_envs must be >= 1%s", "");
-  if (cfg->num_goals < 1 || cfg->num_goals > EARL_TT3_MAX_GOALS) return fail(EARL_ERR_INVALID, "num_goals out of range%s", "");
-  if (cfg->flags & ~(uint32_t)EARL_FLAG_DENSE_REWARD) return fail(EARL_ERR_UNSUPPORTED, "unsupported flag for the three-object tabletop%s", "");
-  if (cfg->episode_horizon < 1) return fail(EARL_ERR_INVALID, "episode_horizon must be >= 1%s", "");
+  if (!cfg || !out) return fail(EARL_ERR_INVALID, "null argument");
+  if (cfg_nbytes != sizeof(earl_tt3_config)) return fail(EARL_ERR_INVALID, "earl_tt3_config size mismatch (%zu)", cfg_nbytes);
+  if (cfg->num_envs < 1) return fail(EARL_ERR_INVALID, "num_envs must be >= 1");
+  if (cfg->num_goals < 1 || cfg->num_goals > EARL_TT3_MAX_GOALS) return fail(EARL_ERR_INVALID, "num_goals out of range");
+  if (cfg->flags & ~(uint32_t)EARL_FLAG_DENSE_REWARD) return fail(EARL_ERR_UNSUPPORTED, "unsupported flag for the three-object tabletop");
+  if (cfg->episode_horizon < 1) return fail(EARL_ERR_INVALID, "episode_horizon must be >= 1");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || cfg->device < 0 || cfg->device >= ndev) {
     cudaGetLastError();
-    return fail(EARL_ERR_CUDA, "no usable CUDA device %s(requested %lld); there is no CPU fallback", "", (long long)cfg->device);
+    return fail(EARL_ERR_CUDA, "no usable CUDA device (requested %d); there is no CPU fallback", cfg->device);
   }
   CU(cudaSetDevice(cfg->device));
   earl_tt3_handle* h = new (std::nothrow) earl_tt3_handle();
-  if (!h) return fail(EARL_ERR_NOMEM, "out of host memory%s", "");
+  if (!h) return fail(EARL_ERR_NOMEM, "out of host memory");
   h->cfg = *cfg;
   const size_t n = (size_t)cfg->num_envs;
   T3Params& p = h->p;
@@ -406,7 +410,7 @@ int earl_tt3_create(const earl_tt3_config* cfg, size_t cfg_nbytes, earl_tt3_hand
   if (cudaMemcpy(gf, g32, sizeof(g32), cudaMemcpyHostToDevice) != cudaSuccess ||
       cudaMemcpy(gd, cfg->goal_table, sizeof(cfg->goal_table), cudaMemcpyHostToDevice) != cudaSuccess) {
     earl_tt3_destroy(h);
-    return fail(EARL_ERR_CUDA, "goal table upload failed%s", "");
+    return fail(EARL_ERR_CUDA, "goal table upload failed");
   }
   p.goal_f32 = gf;
   p.goal_f64 = gd;
@@ -464,8 +468,8 @@ int earl_tt3_set_goal(earl_tt3_handle* h, const uint8_t* mask_dev, const int32_t
 int earl_tt3_step(earl_tt3_handle* h, const float* actions_dev, float* obs_dev, float* reward_dev, uint8_t* done_dev,
                   uint8_t* success_dev, void* stream) {
   if (int rc = check(h)) return rc;
-  if (!actions_dev || !obs_dev || !reward_dev || !done_dev) return fail(EARL_ERR_INVALID, "null device buffer%s", "");
-  if (!aligned16(actions_dev) || !aligned16(obs_dev)) return fail(EARL_ERR_INVALID, "actions and obs must be 16-byte aligned%s", "");
+  if (!actions_dev || !obs_dev || !reward_dev || !done_dev) return fail(EARL_ERR_INVALID, "null device buffer");
+  if (!aligned16(actions_dev) || !aligned16(obs_dev)) return fail(EARL_ERR_INVALID, "actions and obs must be 16-byte aligned");
   if (int rc = launch_step(h, 0, h->p.n, actions_dev, obs_dev, reward_dev, done_dev, success_dev, (cudaStream_t)stream)) return rc;
   h->total_steps += 1;
   return 0;
@@ -475,10 +479,10 @@ int earl_tt3_rollout(earl_tt3_handle* h, const float* actions_dev, int32_t actio
                      float* reward_dev, uint8_t* done_dev, uint8_t* success_dev, int32_t out_ring, void* stream) {
   if (int rc = check(h)) return rc;
   if (!actions_dev || !obs_dev || !reward_dev || !done_dev || action_ring < 1 || out_ring < 1 || num_steps < 0)
-    return fail(EARL_ERR_INVALID, "bad rollout argument%s", "");
+    return fail(EARL_ERR_INVALID, "bad rollout argument");
   const size_t n = (size_t)h->p.n;
   if (!aligned16(actions_dev) || !aligned16(obs_dev) || ((n * kAct * sizeof(float)) & 15u) && action_ring > 1)
-    return fail(EARL_ERR_INVALID, "rollout buffers must keep every slot 16-byte aligned%s", "");
+    return fail(EARL_ERR_INVALID, "rollout buffers must keep every slot 16-byte aligned");
   for (int t = 0; t < num_steps; ++t) {
     const size_t a = (size_t)(t % action_ring), o = (size_t)(t % out_ring);
     if (int rc = launch_step(h, 0, (int)n, actions_dev + a * n * kAct, obs_dev + o * n * kObs, reward_dev + o * n, done_dev + o * n,
@@ -492,7 +496,7 @@ int earl_tt3_rollout(earl_tt3_handle* h, const float* actions_dev, int32_t actio
 int earl_tt3_step_host(earl_tt3_handle* h, const float* actions_host, float* obs_host, float* reward_host, uint8_t* done_host,
                        uint8_t* success_host) {
   if (int rc = check(h)) return rc;
-  if (!actions_host || !obs_host || !reward_host || !done_host) return fail(EARL_ERR_INVALID, "null host buffer%s", "");
+  if (!actions_host || !obs_host || !reward_host || !done_host) return fail(EARL_ERR_INVALID, "null host buffer");
   const size_t n = (size_t)h->p.n;
   if (!h->d_act) {
     int rc = h->alloc(&h->d_act, n * kAct, false);
@@ -532,7 +536,7 @@ int earl_tt3_step_host(earl_tt3_handle* h, const float* actions_host, float* obs
 
 int earl_tt3_get_obs(earl_tt3_handle* h, float* obs_dev, void* stream) {
   if (int rc = check(h)) return rc;
-  if (!obs_dev) return fail(EARL_ERR_INVALID, "null obs%s", "");
+  if (!obs_dev) return fail(EARL_ERR_INVALID, "null obs");
   T3Params p = h->p;
   p.obs = obs_dev;
   tt3_reset_kernel<<<grid_for(p.n), kBlock, 0, (cudaStream_t)stream>>>(p, nullptr, nullptr, nullptr, 2, h->cfg.num_goals);
@@ -544,7 +548,7 @@ int earl_tt3_get_obs(earl_tt3_handle* h, float* obs_dev, void* stream) {
 int earl_tt3_compute_reward(earl_tt3_handle* h, const float* obs_dev, int64_t num_obs, float* reward_dev, uint8_t* success_dev,
                             void* stream) {
   if (int rc = check(h)) return rc;
-  if (!obs_dev || num_obs < 0) return fail(EARL_ERR_INVALID, "bad observation buffer%s", "");
+  if (!obs_dev || num_obs < 0) return fail(EARL_ERR_INVALID, "bad observation buffer");
   if (num_obs == 0) return 0;
   tt3_reward_kernel<<<grid_for(num_obs), kBlock, 0, (cudaStream_t)stream>>>(obs_dev, (long long)num_obs, reward_dev, success_dev,
                                                                            h->p.dense, h->p.success_radius);

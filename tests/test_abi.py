@@ -105,3 +105,26 @@ def test_sqrt_free_thresholds_are_exact():
         ys += [lo, hi]
     ys = np.array(ys + list(np.random.RandomState(1).uniform(0, 0.2, 20000).astype(np.float32)), dtype=np.float32)
     assert np.array_equal(np.sqrt(ys).astype(np.float64) <= 0.2, ys <= y)
+
+
+def test_three_object_tabletop_has_no_cpu_fallback_and_validates_its_config():
+    import torch
+    L = _lib.lib()
+    cfg = _lib.Tt3Config()
+    h = ctypes.c_void_p()
+    cfg.num_envs, cfg.num_goals, cfg.episode_horizon = 4, 1, 10
+    assert L.earl_tt3_create(ctypes.byref(cfg), ctypes.sizeof(cfg) - 8, ctypes.byref(h)) == -1      # size check
+    cfg.num_goals = 17
+    assert L.earl_tt3_create(ctypes.byref(cfg), ctypes.sizeof(cfg), ctypes.byref(h)) == -1          # goal rows
+    cfg.num_goals, cfg.flags = 1, _lib.FLAG_LIFELONG
+    assert L.earl_tt3_create(ctypes.byref(cfg), ctypes.sizeof(cfg), ctypes.byref(h)) == -4          # unsupported flag
+    assert b"three-object" in L.earl_last_error()
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is visible")
+    from earl_benchmark_b200.envs.tabletop_manipulation_3obj import TabletopManipulation
+    from earl_benchmark_b200.wrappers.persistent_state_wrapper import PersistentStateWrapper
+    env = PersistentStateWrapper(TabletopManipulation(reward_type="sparse", num_envs=4), 100)
+    assert env.get_next_goal().shape == (4, 10)         # host constants work without a device
+    with pytest.raises(_lib.EarlError) as ei:
+        env.reset()
+    assert ei.value.code == -2                          # EARL_ERR_CUDA: fails loudly
