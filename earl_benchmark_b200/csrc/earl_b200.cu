@@ -68,6 +68,8 @@ struct earl_handle {
   int variant = -1;       // EARL_TT_VARIANT: -1 = auto (LSU kernel up to 3M envs, 3-stage TMA pipeline above);
                           // 0 = LSU kernel; 6/8 = LSU kernel with min 6/8 CTAs per SM; 2/3/4 = TMA pipeline stages
   bool pdl = true;        // EARL_TT_PDL=0 disables programmatic dependent launch between consecutive steps
+  int host_chunks = 0;    // EARL_TT_HOST_CHUNKS: chunks of the host-buffer pipeline (0 = one per 128k envs, at most 8)
+  bool host_tail = true;  // EARL_TT_HOST_TAIL=0: copy reward / done / success per chunk instead of once per step
   int tma_grid = 0;
   int tma_tile = 256;
   size_t tma_smem = 0;
@@ -84,7 +86,7 @@ struct earl_handle {
   uint8_t* d_succ = nullptr;
   cudaStream_t host_stream = nullptr;
   cudaStream_t in_stream = nullptr;
-  static constexpr int kMaxChunks = 8;
+  static constexpr int kMaxChunks = 16;
   cudaEvent_t chunk_ev[kMaxChunks] = {};
   double* d_stats = nullptr;
 
@@ -321,6 +323,8 @@ int earl_create(const earl_config* cfg, const void* model_blob, size_t model_nby
   // bulk-copy pipeline keeps more bytes in flight and wins.
   if (h->variant < 0) h->variant = cfg->num_envs > 3 * 1024 * 1024 ? 3 : 0;
   if (const char* v = getenv("EARL_TT_PDL")) h->pdl = atoi(v) != 0;
+  if (const char* v = getenv("EARL_TT_HOST_CHUNKS")) h->host_chunks = atoi(v);
+  if (const char* v = getenv("EARL_TT_HOST_TAIL")) h->host_tail = atoi(v) != 0;
   if (fast && !f64(h) && (h->variant == 8 || h->variant == 6)) {
     rc = h->variant == 8 ? occupancy_grid(earl::tabletop_step_kernel<false, true, 8>, h->sm_count, &h->step_grid)
                          : occupancy_grid(earl::tabletop_step_kernel<false, true, 6>, h->sm_count, &h->step_grid);
@@ -454,8 +458,11 @@ int earl_step_host(earl_handle* h, const float* actions_host, float* obs_host, f
   // Chunked software pipeline over the PCIe link: the host->device copy of chunk c+1 (in_stream) overlaps the
   // kernel and the device->host copies of chunk c (host_stream); the link is full duplex.
   constexpr int kMaxChunks = earl_handle::kMaxChunks;
-  int chunks = (int)(n / (128 * 1024));
+  int chunks = h->host_chunks > 0 ? h->host_chunks : (int)(n / (128 * 1024));
   chunks = chunks < 1 ? 1 : (chunks > kMaxChunks ? kMaxChunks : chunks);
+  // the three small outputs (6 B per env) go back in one copy each after the last chunk instead of one per chunk:
+  // 11 instead of 32 device->host copies per step, whose fixed costs are what separates this path from the link rate
+  const bool tail = h->host_tail && chunks > 1;
   const size_t per = ((n / chunks + 255) / 256) * 256;  // chunk boundaries stay tile- and 16-byte aligned
   cudaStream_t si = h->in_stream, so = h->host_stream;
   uint8_t* d_succ = success_host ? h->d_succ : nullptr;
@@ -469,9 +476,15 @@ int earl_step_host(earl_handle* h, const float* actions_host, float* obs_host, f
     if (int rc = launch_step_range(h, (int)off, (int)cnt, h->d_act, h->d_obs, h->d_rew, h->d_done, d_succ, so)) return rc;
     CU(cudaMemcpyAsync(obs_host + off * earl::kTTObs, h->d_obs + off * earl::kTTObs, cnt * earl::kTTObs * sizeof(float),
                        cudaMemcpyDeviceToHost, so));
+    if (tail) continue;
     CU(cudaMemcpyAsync(reward_host + off, h->d_rew + off, cnt * sizeof(float), cudaMemcpyDeviceToHost, so));
     CU(cudaMemcpyAsync(done_host + off, h->d_done + off, cnt, cudaMemcpyDeviceToHost, so));
     if (success_host) CU(cudaMemcpyAsync(success_host + off, h->d_succ + off, cnt, cudaMemcpyDeviceToHost, so));
+  }
+  if (tail) {
+    CU(cudaMemcpyAsync(reward_host, h->d_rew, n * sizeof(float), cudaMemcpyDeviceToHost, so));
+    CU(cudaMemcpyAsync(done_host, h->d_done, n, cudaMemcpyDeviceToHost, so));
+    if (success_host) CU(cudaMemcpyAsync(success_host, h->d_succ, n, cudaMemcpyDeviceToHost, so));
   }
   h->total_steps += 1;
   CU(cudaStreamSynchronize(so));
