@@ -68,7 +68,7 @@ struct earl_handle {
   int variant = -1;       // EARL_TT_VARIANT: -1 = auto (LSU kernel up to 3M envs, 3-stage TMA pipeline above);
                           // 0 = LSU kernel; 6/8 = LSU kernel with min 6/8 CTAs per SM; 2/3/4 = TMA pipeline stages
   bool pdl = true;        // EARL_TT_PDL=0 disables programmatic dependent launch between consecutive steps
-  int host_chunks = 0;    // EARL_TT_HOST_CHUNKS: chunks of the host-buffer pipeline (0 = one per 128k envs, at most 8)
+  int host_chunks = 0;    // EARL_TT_HOST_CHUNKS: chunks of the host-buffer pipeline (0 = one per 256k envs, at most 16)
   bool host_tail = true;  // EARL_TT_HOST_TAIL=0: copy reward / done / success per chunk instead of once per step
   int tma_grid = 0;
   int tma_tile = 256;
@@ -458,10 +458,12 @@ int earl_step_host(earl_handle* h, const float* actions_host, float* obs_host, f
   // Chunked software pipeline over the PCIe link: the host->device copy of chunk c+1 (in_stream) overlaps the
   // kernel and the device->host copies of chunk c (host_stream); the link is full duplex.
   constexpr int kMaxChunks = earl_handle::kMaxChunks;
-  int chunks = h->host_chunks > 0 ? h->host_chunks : (int)(n / (128 * 1024));
+  int chunks = h->host_chunks > 0 ? h->host_chunks : (int)(n / (256 * 1024));
   chunks = chunks < 1 ? 1 : (chunks > kMaxChunks ? kMaxChunks : chunks);
   // the three small outputs (6 B per env) go back in one copy each after the last chunk instead of one per chunk:
-  // 11 instead of 32 device->host copies per step, whose fixed costs are what separates this path from the link rate
+  // fewer, larger device->host copies per step: their fixed costs are what separates this path from the link rate
+  // (1M envs, env-steps/s: 8 chunks, all outputs per chunk 7.8e8; 8 chunks + tail 8.4e8; 4 chunks + tail 8.8e8; 2 chunks
+  // + tail 8.7e8; 16 chunks + tail 7.9e8; one chunk 8.2e8 -- profiles/r01/e2e_sweep_r01.txt)
   const bool tail = h->host_tail && chunks > 1;
   const size_t per = ((n / chunks + 255) / 256) * 256;  // chunk boundaries stay tile- and 16-byte aligned
   cudaStream_t si = h->in_stream, so = h->host_stream;

@@ -512,7 +512,7 @@ int earl_tt3_step_host(earl_tt3_handle* h, const float* actions_host, float* obs
   // chunked pipeline over the full-duplex PCIe link: the upload of chunk c+1 overlaps the kernel and the
   // downloads of chunk c
   CU(cudaDeviceSynchronize());  // order after whatever the caller enqueued on its own streams
-  int chunks = (int)(n / (128 * 1024));
+  int chunks = (int)(n / (256 * 1024));
   chunks = chunks < 1 ? 1 : (chunks > earl_tt3_handle::kMaxChunks ? earl_tt3_handle::kMaxChunks : chunks);
   const size_t per = ((n / chunks + 255) / 256) * 256;
   cudaStream_t si = h->in_stream, so = h->out_stream;
@@ -526,7 +526,7 @@ int earl_tt3_step_host(earl_tt3_handle* h, const float* actions_host, float* obs
       return rc;
     CU(cudaMemcpyAsync(obs_host + off * kObs, h->d_obs + off * kObs, cnt * kObs * sizeof(float), cudaMemcpyDeviceToHost, so));
   }
-  // the small outputs (6 B per env) go back in one copy each after the last chunk: 11 instead of 32 copies per step
+  // the small outputs (6 B per env) go back in one copy each after the last chunk: fewer, larger copies (profiles/r01/e2e_sweep_r01.txt)
   CU(cudaMemcpyAsync(reward_host, h->d_rew, n * sizeof(float), cudaMemcpyDeviceToHost, so));
   CU(cudaMemcpyAsync(done_host, h->d_done, n, cudaMemcpyDeviceToHost, so));
   if (success_host) CU(cudaMemcpyAsync(success_host, h->d_succ, n, cudaMemcpyDeviceToHost, so));
