@@ -126,12 +126,18 @@ __global__ void __launch_bounds__(kBlock) tt3_step_kernel(const __grid_constant_
   const int rows = min(kBlock, end - base);
   pdl_wait_prior_grid();  // nothing is read before the previous grid in the stream (the previous step, or the
                           // caller's action producer) has completed and flushed
-  {  // actions of the tile: contiguous 16-byte loads (base * 12 B is 16-byte aligned since base % 256 == 0)
-    const float4* src = reinterpret_cast<const float4*>(p.actions + (size_t)base * kAct);
-    const int full = rows * kAct / 4;
-    if (t < full) s_act4[t] = __ldcs(src + t);
-    const int rem = rows * kAct - full * 4;
-    if (t < rem) s_act[full * 4 + t] = p.actions[(size_t)base * kAct + full * 4 + t];
+  {  // actions of the tile: contiguous 16-byte loads when the tile starts on a 16-byte boundary (always, unless the
+     // caller's buffer or a ring slot of a batch that is not a multiple of 4 envs is only 4-byte aligned)
+    const float* asrc = p.actions + (size_t)base * kAct;
+    if ((reinterpret_cast<uintptr_t>(asrc) & 15u) == 0) {
+      const float4* src = reinterpret_cast<const float4*>(asrc);
+      const int full = rows * kAct / 4;
+      if (t < full) s_act4[t] = __ldcs(src + t);
+      const int rem = rows * kAct - full * 4;
+      if (t < rem) s_act[full * 4 + t] = asrc[full * 4 + t];
+    } else {
+      for (int k = t; k < rows * kAct; k += kBlock) s_act[k] = asrc[k];
+    }
   }
   __syncthreads();
   if (i < end) {
@@ -469,7 +475,7 @@ int earl_tt3_step(earl_tt3_handle* h, const float* actions_dev, float* obs_dev, 
                   uint8_t* success_dev, void* stream) {
   if (int rc = check(h)) return rc;
   if (!actions_dev || !obs_dev || !reward_dev || !done_dev) return fail(EARL_ERR_INVALID, "null device buffer");
-  if (!aligned16(actions_dev) || !aligned16(obs_dev)) return fail(EARL_ERR_INVALID, "actions and obs must be 16-byte aligned");
+  if (!aligned16(obs_dev)) return fail(EARL_ERR_INVALID, "obs must be 16-byte aligned");
   if (int rc = launch_step(h, 0, h->p.n, actions_dev, obs_dev, reward_dev, done_dev, success_dev, (cudaStream_t)stream)) return rc;
   h->total_steps += 1;
   return 0;
@@ -481,8 +487,7 @@ int earl_tt3_rollout(earl_tt3_handle* h, const float* actions_dev, int32_t actio
   if (!actions_dev || !obs_dev || !reward_dev || !done_dev || action_ring < 1 || out_ring < 1 || num_steps < 0)
     return fail(EARL_ERR_INVALID, "bad rollout argument");
   const size_t n = (size_t)h->p.n;
-  if (!aligned16(actions_dev) || !aligned16(obs_dev) || ((n * kAct * sizeof(float)) & 15u) && action_ring > 1)
-    return fail(EARL_ERR_INVALID, "rollout buffers must keep every slot 16-byte aligned");
+  if (!aligned16(obs_dev)) return fail(EARL_ERR_INVALID, "obs must be 16-byte aligned");
   for (int t = 0; t < num_steps; ++t) {
     const size_t a = (size_t)(t % action_ring), o = (size_t)(t % out_ring);
     if (int rc = launch_step(h, 0, (int)n, actions_dev + a * n * kAct, obs_dev + o * n * kObs, reward_dev + o * n, done_dev + o * n,

@@ -146,7 +146,7 @@ def test_compute_reward_and_is_successful_on_reference_observations():
 
 
 def test_rollout_entry_point_equals_single_steps():
-    n, steps = 4096, 40
+    n, steps = 4099, 40          # ragged: ring slots of the action buffer are only 4-byte aligned
     rs = np.random.RandomState(3)
     acts = torch.from_numpy(biased_actions(rs, 8, n)).cuda()
     a, b = make(n, 1000, reward_type="sparse"), make(n, 1000, reward_type="sparse")

@@ -23,11 +23,7 @@ for n, reward_type in ((1, "sparse"), (257, "dense"), (300003, "sparse")):
     obs = torch.empty((2, n, 20), device="cuda")
     rew = torch.empty((2, n), device="cuda")
     done = torch.empty((2, n), dtype=torch.uint8, device="cuda")
-    if n % 4 == 0 or True:
-        try:
-            env.rollout_into(acts, 7, obs, rew, done)
-        except Exception as e:  # ring slots of a ragged batch are not 16-byte aligned: the library must refuse, not fault
-            print("rollout refused:", e)
+    env.rollout_into(acts, 7, obs, rew, done)     # ring slots of a ragged batch are only 4-byte aligned: scalar action loads
     env.compute_reward(env._get_obs())
     env.is_successful()
     q, att = env.get_state()
