@@ -429,3 +429,33 @@ def test_invalid_arguments_fail_loudly():
     with pytest.raises(_lib.EarlError):  # misaligned observation buffer
         buf = torch.empty(8 * 12 + 1, device=DEV)[1:].view(8, 12)
         env.step(torch.zeros((8, 3), device=DEV), out=(buf, env._reward, env._done, env._success))
+
+
+def test_config1_full_reset_free_horizon():
+    """BASELINE.json configs[0] at its true size: sparse reward, default train horizon 200,000,
+    200,000 random-action steps in ONE device rollout.  `done` is first True at step index 199,999, total_steps ==
+    200000, num_interventions == 1, and every observation / reward of the run is bit-exact against the checker."""
+    n, steps = 8, 200000
+    train, _ = eb.EARLEnvs("tabletop_manipulation", reward_type="sparse", num_envs=n, device=DEV, seed=0,
+                           state_dtype="float64").get_envs()
+    assert train._episode_horizon == steps
+    o0 = np_(train.reset())
+    orc = TabletopOracle(n, steps, state_f32=False)
+    assert np.array_equal(orc.reset(goal_row(o0)), o0)
+    acts = np.random.RandomState(0).uniform(-1, 1, (steps, n, 3)).astype(np.float32)
+    acts[:, : n // 2, 2] = np.abs(acts[:, : n // 2, 2])          # half of the envs keep the gripper closed: they drag the mug
+    obs = torch.empty((steps, n, 12), device=DEV)
+    rew = torch.empty((steps, n), device=DEV)
+    done = torch.empty((steps, n), dtype=torch.uint8, device=DEV)
+    train.rollout_into(torch.from_numpy(acts).to(DEV), steps, obs, rew, done)
+    obs, rew, done = np_(obs), np_(rew), np_(done)
+    assert not done[:-1].any() and done[-1].all()                 # first True at index 199,999
+    assert train.total_steps == steps and (np_(train.num_interventions) == 1).all()
+    dragged = 0
+    for t in range(steps):
+        o2, r2, d2, _ = orc.step(acts[t])
+        if not (np.array_equal(obs[t], o2) and np.array_equal(rew[t].astype(np.float64), r2)):
+            raise AssertionError(f"mismatch at step {t}")
+        dragged += int((orc.attached != 0).sum())
+    assert bool(d2.all()) and dragged > steps                     # the attach / drag path was busy
+    assert np.array_equal(train.get_state()["qpos"], orc.qpos)    # fp64 state after 200,000 steps, bit for bit
