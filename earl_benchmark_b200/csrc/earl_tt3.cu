@@ -23,6 +23,8 @@
 
 #include <cuda_runtime.h>
 
+#include "tt3_env.cuh"
+
 namespace earl {
 int set_error(int code, const char* msg);  // earl_b200.cu
 }
@@ -57,46 +59,9 @@ __device__ __forceinline__ void pdl_wait_prior_grid() {
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
 
-__device__ __forceinline__ double clipd(double x, double lo, double hi) {  // np.clip: NaN propagates
-  return x < lo ? lo : (x > hi ? hi : x);
-}
-
-// np.linalg.norm of an fp32 vector as numpy's BLAS evaluates it: fp32 products, accumulated in index order
-// in fp64, rounded to fp32, fp32 sqrt
-template <int K>
-__device__ __forceinline__ float norm_f32(const float (&d)[K]) {
-  double s = 0.0;
-#pragma unroll
-  for (int k = 0; k < K; ++k) s = __dadd_rn(s, (double)__fmul_rn(d[k], d[k]));
-  return __fsqrt_rn((float)s);
-}
-
-// is_successful (3OBJ:161-165): ||obs[0:8] - obs[10:18]|| <= 0.4, fp32 norm against the fp64 constant
-__device__ __forceinline__ bool t3_success(const float (&o)[8], const float* g, double radius) {
-  float d[8];
-#pragma unroll
-  for (int k = 0; k < 8; ++k) d[k] = __fsub_rn(o[k], g[k]);
-  return (double)norm_f32(d) <= radius;
-}
-
-// dense reward (3OBJ:150-157): fp32 norms and squares, fp64 from the division by 0.01 on (numpy 1.22 promotion)
-__device__ __forceinline__ double t3_dense(const float (&o)[8], const float* g) {
-  float d6[6];
-#pragma unroll
-  for (int k = 0; k < 6; ++k) d6[k] = __fsub_rn(o[2 + k], g[2 + k]);
-  double r = (double)(-norm_f32(d6));
-#pragma unroll
-  for (int j = 1; j < 4; ++j) {
-    float d2[2] = {__fsub_rn(o[2 * j], g[2 * j]), __fsub_rn(o[2 * j + 1], g[2 * j + 1])};
-    const float nk = norm_f32(d2);
-    r += 2.0 * exp((double)(-__fmul_rn(nk, nk)) / 0.01);
-  }
-  return r;
-}
-
-__device__ __forceinline__ float marker(uint32_t att) {  // attached_object tuples, 3OBJ:31-37
-  return att == 0 ? -1.0f : 0.5f * (float)(att - 1);
-}
+using earl::tt3::EnvConst;
+using earl::tt3::EnvState;
+using earl::tt3::marker;
 
 // stage one env's observation row (20 floats = 5 float4) in the block's tile: slot 5*t + j is conflict-free
 // for 16-byte shared-memory accesses (5 is odd)
@@ -141,48 +106,19 @@ __global__ void __launch_bounds__(kBlock) tt3_step_kernel(const __grid_constant_
   }
   __syncthreads();
   if (i < end) {
-    double2 f = p.q[0][i];
-    double2 ob[3] = {p.q[1][i], p.q[2][i], p.q[3][i]};
-    uint2 m = p.meta[i];
-    uint32_t att = m.x & 3u;
+    const double2 f = p.q[0][i], oa = p.q[1][i], ob = p.q[2][i], oc = p.q[3][i];
+    const uint2 m = p.meta[i];
     const uint32_t row = (m.x >> 8) & 0xffu;
-    // 3OBJ:88-90: clip to [-1,1] in fp64, then lb + (a + 1) * 0.5 * (ub - lb)
-    double a[3];
+    EnvState st{f.x, f.y, {oa.x, ob.x, oc.x}, {oa.y, ob.y, oc.y}, m.x & 3u};
+    const EnvConst ec{p.act_lo, p.act_span, p.threshold, p.clip, p.success_radius};
+    earl::tt3::move(ec, st, s_act[kAct * t], s_act[kAct * t + 1], s_act[kAct * t + 2]);  // 3OBJ:86-144
+    const uint32_t att = st.att;
+    p.q[0][i] = make_double2(st.fx, st.fy);
 #pragma unroll
-    for (int k = 0; k < 3; ++k)
-      a[k] = __dadd_rn(p.act_lo, __dmul_rn(__dmul_rn(__dadd_rn(clipd((double)s_act[kAct * t + k], -1.0, 1.0), 1.0), 0.5), p.act_span));
-    if (a[2] > 0.0) {  // 3OBJ:98-108: the closest object within the threshold, dict order breaks ties
-      if (att == 0) {
-        double held = INFINITY;
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-          const double dx = __dsub_rn(f.x, ob[k].x), dy = __dsub_rn(f.y, ob[k].y);
-          const double dist = __dsqrt_rn(__fma_rn(dy, dy, __dmul_rn(dx, dx)));
-          if (dist < p.threshold && dist < held) {
-            att = k + 1;
-            held = dist;
-          }
-        }
-      }
-    } else {
-      att = 0;  // 3OBJ:109-110
-    }
-    const double nfx = clipd(__dadd_rn(f.x, a[0]), -p.clip, p.clip);  // 3OBJ:112-113
-    const double nfy = clipd(__dadd_rn(f.y, a[1]), -p.clip, p.clip);
-    if (att) {  // 3OBJ:114-119
-      const double ddx = __dsub_rn(nfx, f.x), ddy = __dsub_rn(nfy, f.y);
-#pragma unroll
-      for (int k = 0; k < 3; ++k)
-        if (att == (uint32_t)(k + 1)) {
-          ob[k].x = clipd(__dadd_rn(ob[k].x, ddx), -p.clip, p.clip);
-          ob[k].y = clipd(__dadd_rn(ob[k].y, ddy), -p.clip, p.clip);
-          p.q[1 + k][i] = ob[k];
-        }
-    }
-    p.q[0][i] = make_double2(nfx, nfy);
-    // 3OBJ:49-54
-    const float o[8] = {(float)nfx, (float)nfy, (float)ob[0].x, (float)ob[0].y,
-                        (float)ob[1].x, (float)ob[1].y, (float)ob[2].x, (float)ob[2].y};
+    for (int k = 0; k < 3; ++k)  // only the dragged object's plane is written back
+      if (att == (uint32_t)(k + 1)) p.q[1 + k][i] = make_double2(st.ox[k], st.oy[k]);
+    float o[8];
+    earl::tt3::observe8(st, o);  // 3OBJ:49-54
     float g[10];
     {
       const float2* gr = reinterpret_cast<const float2*>(p.goal_f32 + row * 10);
@@ -194,8 +130,8 @@ __global__ void __launch_bounds__(kBlock) tt3_step_kernel(const __grid_constant_
       }
     }
     stage_obs(s_obs, t, o, marker(att), g);
-    const bool succ = t3_success(o, g, p.success_radius);
-    const float rew = p.dense ? (float)t3_dense(o, g) : (succ ? 1.0f : 0.0f);  // 3OBJ:146-159
+    const bool succ = earl::tt3::success(o, g, p.success_radius);
+    const float rew = p.dense ? (float)earl::tt3::dense(o, g) : (succ ? 1.0f : 0.0f);  // 3OBJ:146-159
     // PSW:22-31
     const uint32_t steps = m.y == 0xffffffffu ? m.y : m.y + 1u;
     p.meta[i] = make_uint2((m.x & ~3u) | att, steps);
@@ -257,8 +193,8 @@ __global__ void __launch_bounds__(kBlock) tt3_reward_kernel(const float* obs, lo
   for (int k = 0; k < 8; ++k) o[k] = r[k];
 #pragma unroll
   for (int k = 0; k < 10; ++k) g[k] = r[10 + k];
-  const bool succ = t3_success(o, g, radius);
-  if (reward) reward[i] = dense ? (float)t3_dense(o, g) : (succ ? 1.0f : 0.0f);
+  const bool succ = earl::tt3::success(o, g, radius);
+  if (reward) reward[i] = dense ? (float)earl::tt3::dense(o, g) : (succ ? 1.0f : 0.0f);
   if (success) success[i] = succ ? 1 : 0;
 }
 
