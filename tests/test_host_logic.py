@@ -187,3 +187,35 @@ def test_sawyer_reset_draws_do_not_depend_on_the_number_of_shards():
             lo, hi = shard_range(total, r, world)
             parts.append(kt.Kitchen(num_envs=hi - lo, seed=5, env_offset=lo, total_envs=total)._draw_configs(hi - lo)[1])
         assert np.array_equal(np.concatenate(parts), whole_k)
+
+
+def test_three_object_env_host_side_contract():
+    """Constructor validation, goal-table bookkeeping and wrapper configuration of the three-object env need no device."""
+    import pytest
+    from earl_benchmark_b200.envs import tabletop_manipulation_3obj as t3
+    from earl_benchmark_b200.wrappers.lifelong_wrapper import LifelongWrapper
+    from earl_benchmark_b200.wrappers.persistent_state_wrapper import PersistentStateWrapper
+    with pytest.raises(ValueError):
+        t3.TabletopManipulation(reward_type="shaped")
+    with pytest.raises(ValueError):
+        t3.TabletopManipulation(device="cpu")
+    env = t3.TabletopManipulation(reward_type="sparse", num_envs=3)
+    assert env.action_space.shape == (3,) and env.observation_space.shape == (20,)
+    assert env.object_dict == {(0, 0): [2, 3], (0.5, 0.5): [4, 5], (1, 1): [6, 7]}     # reference :31-35
+    assert np.array_equal(env.get_next_goal(), np.broadcast_to(t3.goal_states[0], (3, 10)))
+    assert list(env._rows_for(t3.goal_states[0])) == [0, 0, 0]
+    custom = t3.goal_states[0].copy()
+    custom[2:4] = [1.0, 1.0]
+    assert list(env._rows_for(np.stack([t3.goal_states[0], custom, custom]))) == [0, 1, 1]   # appended once
+    for k in range(14):
+        c = custom.copy()
+        c[4] = 0.1 * (k + 1)
+        env._rows_for(c)
+    with pytest.raises(ValueError):                                                     # 16 rows at most
+        c = custom.copy()
+        c[4] = -1.0
+        env._rows_for(c)
+    w = PersistentStateWrapper(t3.TabletopManipulation(num_envs=2), 123)
+    assert w.env._episode_horizon == 123
+    with pytest.raises(ValueError):
+        LifelongWrapper(t3.TabletopManipulation(num_envs=2), 400)
