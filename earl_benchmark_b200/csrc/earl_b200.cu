@@ -88,6 +88,10 @@ struct earl_handle {
   cudaStream_t in_stream = nullptr;
   static constexpr int kMaxChunks = 16;
   cudaEvent_t chunk_ev[kMaxChunks] = {};
+  // recorded on the caller's stream after every state-mutating launch (reset / set_goal / step / rollout); the
+  // host-buffer step, which runs on the handle's private streams, waits on it (it could race a reset)
+  cudaEvent_t order_ev = nullptr;
+  bool order_pending = false;
   double* d_stats = nullptr;
 
   template <typename T>
@@ -174,6 +178,7 @@ int occupancy_grid(K kernel, int sm_count, int* grid) {
 int launch_step_range(earl_handle* h, int first, int count, const float* actions, float* obs, float* reward,
                       uint8_t* done, uint8_t* success, cudaStream_t s) {
   earl::TabletopParams p = h->p;
+  p.n_total = h->p.n;
   p.n = first + count;
   p.actions = actions;
   p.obs = obs;
@@ -214,6 +219,14 @@ int launch_step(earl_handle* h, const float* actions, float* obs, float* reward,
                 cudaStream_t s) {
   if (int rc = launch_step_range(h, 0, h->p.n, actions, obs, reward, done, success, s)) return rc;
   h->total_steps += 1;
+  return 0;
+}
+
+// remember that `s` carries work the private host-path streams must wait for
+int note_stream(earl_handle* h, cudaStream_t s) {
+  if (!h->order_ev) CU(cudaEventCreateWithFlags(&h->order_ev, cudaEventDisableTiming));
+  CU(cudaEventRecord(h->order_ev, s));
+  h->order_pending = true;
   return 0;
 }
 
@@ -297,6 +310,7 @@ int earl_create(const earl_config* cfg, const void* model_blob, size_t model_nby
   p.goal32 = g32;
   p.goal64 = g64;
   p.n = cfg->num_envs;
+  p.n_total = cfg->num_envs;
   p.goal_stream_rows = h->cfg.goal_stream_rows;
   p.features = cfg->flags;
   p.horizon = (unsigned long long)cfg->episode_horizon;
@@ -366,6 +380,7 @@ int earl_destroy(earl_handle* h) {
   if (h->host_stream) cudaStreamDestroy(h->host_stream);
   if (h->in_stream) cudaStreamDestroy(h->in_stream);
   for (auto& ev : h->chunk_ev) if (ev) cudaEventDestroy(ev);
+  if (h->order_ev) cudaEventDestroy(h->order_ev);
   delete h;
   return 0;
 }
@@ -405,7 +420,7 @@ static int reset_impl(earl_handle* h, const uint8_t* mask, const int32_t* goal_i
   else earl::tabletop_reset_kernel<false><<<grid, 256, 0, s>>>(h->p, a);
   CU(cudaGetLastError());
   h->launches += 1;
-  return 0;
+  return note_stream(h, s);
 }
 
 int earl_reset(earl_handle* h, const uint8_t* mask_dev, const int32_t* goal_idx_dev, const double* init_qpos_dev,
@@ -421,7 +436,8 @@ int earl_step(earl_handle* h, const float* actions_dev, float* obs_dev, float* r
               uint8_t* success_dev, void* stream) {
   if (int rc = check_handle(h)) return rc;
   if (int rc = check_io(actions_dev, obs_dev, reward_dev, done_dev)) return rc;
-  return launch_step(h, actions_dev, obs_dev, reward_dev, done_dev, success_dev, static_cast<cudaStream_t>(stream));
+  if (int rc = launch_step(h, actions_dev, obs_dev, reward_dev, done_dev, success_dev, static_cast<cudaStream_t>(stream))) return rc;
+  return note_stream(h, static_cast<cudaStream_t>(stream));
 }
 
 int earl_rollout(earl_handle* h, const float* actions_dev, int32_t action_ring, int32_t num_steps, float* obs_dev,
@@ -437,7 +453,7 @@ int earl_rollout(earl_handle* h, const float* actions_dev, int32_t action_ring, 
                          done_dev + io * n, success_dev ? success_dev + io * n : nullptr, s);
     if (rc) return rc;
   }
-  return 0;
+  return note_stream(h, s);
 }
 
 int earl_step_host(earl_handle* h, const float* actions_host, float* obs_host, float* reward_host, uint8_t* done_host,
@@ -465,12 +481,19 @@ int earl_step_host(earl_handle* h, const float* actions_host, float* obs_host, f
   // (1M envs, env-steps/s: 8 chunks, all outputs per chunk 7.8e8; 8 chunks + tail 8.4e8; 4 chunks + tail 8.8e8; 2 chunks
   // + tail 8.7e8; 16 chunks + tail 7.9e8; one chunk 8.2e8 -- profiles/r01/e2e_sweep_r01.txt)
   const bool tail = h->host_tail && chunks > 1;
-  const size_t per = ((n / chunks + 255) / 256) * 256;  // chunk boundaries stay tile- and 16-byte aligned
+  // ceil(n / chunks) rounded up to whole 256-env tiles: at most `chunks` iterations (floor could give chunks + 1 and
+  // index chunk_ev out of bounds); chunk boundaries stay tile- and 16-byte aligned
+  const size_t per = (((n + chunks - 1) / chunks + 255) / 256) * 256;
   cudaStream_t si = h->in_stream, so = h->host_stream;
+  if (h->order_pending) {  // resets / device steps queued on the caller's stream come first
+    CU(cudaStreamWaitEvent(si, h->order_ev, 0));
+    CU(cudaStreamWaitEvent(so, h->order_ev, 0));
+    h->order_pending = false;
+  }
   uint8_t* d_succ = success_host ? h->d_succ : nullptr;
   int c = 0;
-  for (size_t off = 0; off < n; off += per, ++c) {
-    const size_t cnt = off + per <= n ? per : n - off;
+  for (size_t off = 0; off < n && c < kMaxChunks; off += per, ++c) {
+    const size_t cnt = (off + per <= n && c + 1 < kMaxChunks) ? per : n - off;
     CU(cudaMemcpyAsync(h->d_act + off * earl::kTTAct, actions_host + off * earl::kTTAct, cnt * earl::kTTAct * sizeof(float),
                        cudaMemcpyHostToDevice, si));
     CU(cudaEventRecord(h->chunk_ev[c], si));

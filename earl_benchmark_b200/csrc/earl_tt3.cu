@@ -455,10 +455,10 @@ int earl_tt3_step_host(earl_tt3_handle* h, const float* actions_host, float* obs
   CU(cudaDeviceSynchronize());  // order after whatever the caller enqueued on its own streams
   int chunks = (int)(n / (256 * 1024));
   chunks = chunks < 1 ? 1 : (chunks > earl_tt3_handle::kMaxChunks ? earl_tt3_handle::kMaxChunks : chunks);
-  const size_t per = ((n / chunks + 255) / 256) * 256;
+  const size_t per = (((n + chunks - 1) / chunks + 255) / 256) * 256;  // ceil: never more than `chunks` iterations
   cudaStream_t si = h->in_stream, so = h->out_stream;
   int c = 0;
-  for (size_t off = 0; off < n; off += per, ++c) {
+  for (size_t off = 0; off < n && c < earl_tt3_handle::kMaxChunks; off += per, ++c) {
     const size_t cnt = off + per <= n ? per : n - off;
     CU(cudaMemcpyAsync(h->d_act + off * kAct, actions_host + off * kAct, cnt * kAct * sizeof(float), cudaMemcpyHostToDevice, si));
     CU(cudaEventRecord(h->chunk_ev[c], si));

@@ -61,7 +61,9 @@ struct TabletopParams {
   float* reward;         // [N]
   uint8_t* done;         // [N]
   uint8_t* success;      // [N] or null
-  int n;
+  int n;        // one past the last env this launch touches (chunked host path: first + count)
+  int n_total;  // envs of the handle = row stride of goal_stream[R,N]; never changes with the chunk (a chunked
+                // launch used `n` as the stride and read other envs' draws)
   int first;  // first env this launch touches (chunked host path; ragged tail after the TMA kernel); multiple of 32
               // the launch covers envs [first, n)
   int goal_stream_rows;
@@ -252,7 +254,7 @@ __global__ void __launch_bounds__(kTTBlock, MINB) tabletop_step_kernel(const Tab
           if ((unsigned long long)ls >= p.goal_change_frequency) {
             ls = 0u;
             const uint32_t c = p.goal_cursor[i];
-            gi = p.goal_stream[(size_t)(c % (uint32_t)p.goal_stream_rows) * p.n + i];
+            gi = p.goal_stream[(size_t)(c % (uint32_t)p.goal_stream_rows) * p.n_total + i];
             p.goal_cursor[i] = c + 1u;
             s.flags = (s.flags & ~kGoalMask) | (gi << kGoalShift);
             g0 = __ldg(p.goal32 + 2 * gi);  // the returned obs carries the NEW goal, the reward the old one
@@ -262,7 +264,7 @@ __global__ void __launch_bounds__(kTTBlock, MINB) tabletop_step_kernel(const Tab
         }
         if (done && (p.features & kAutoReset)) {  // what the user's reset() would do, fused
           const uint32_t c = p.goal_cursor[i];
-          gi = p.goal_stream[(size_t)(c % (uint32_t)p.goal_stream_rows) * p.n + i];
+          gi = p.goal_stream[(size_t)(c % (uint32_t)p.goal_stream_rows) * p.n_total + i];
           p.goal_cursor[i] = c + 1u;
           p.interventions[i] += 1;
           steps = 0u;
@@ -464,7 +466,7 @@ __global__ void tabletop_reset_kernel(const TabletopParams p, const TabletopRese
     gi = (uint32_t)a.goal_idx[i] & 0xffu;
   } else {
     const uint32_t c = p.goal_cursor[i];
-    gi = p.goal_stream[(size_t)(c % (uint32_t)p.goal_stream_rows) * p.n + i];
+    gi = p.goal_stream[(size_t)(c % (uint32_t)p.goal_stream_rows) * p.n_total + i];
     p.goal_cursor[i] = c + 1u;
   }
   if (a.set_goal_only) {

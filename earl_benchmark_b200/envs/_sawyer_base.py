@@ -9,6 +9,7 @@ import numpy as np
 import torch
 
 from .. import _lib, rng
+from ._hostio import HostBuffers
 from ..mjcf.compile import Model
 from ..spaces import Box
 
@@ -33,7 +34,7 @@ class SawyerBatchedEnv:
     HAS_DENSE_REWARD = False
 
     def __init__(self, reward_type="sparse", reset_at_goal=False, num_envs=1, device=None, seed=0, eval_stats=False,
-                 env_offset=0, total_envs=None, model_path=None, max_newton=0, **_tabletop_only):
+                 env_offset=0, total_envs=None, model_path=None, max_newton=0, host_io=False, **_tabletop_only):
         name = type(self).__name__
         if reward_type == "dense" and not self.HAS_DENSE_REWARD:
             raise NotImplementedError(f"{name}: the dense reward (metaworld reward_utils, gripper caging) is not built yet")
@@ -64,6 +65,7 @@ class SawyerBatchedEnv:
         self._np_random = rng.NumpyLegacyRandom(self._seed & 0xFFFFFFFF)
         self._obs = self._reward = self._done = self._success = None
         self._host_bufs = None
+        self._host_mode = bool(host_io)   # numpy in / numpy out (set by host_io=True or by the first numpy step)
 
     # ------------------------------------------------------------------ task hooks
     def _task_spec(self):
@@ -161,7 +163,7 @@ class SawyerBatchedEnv:
         _lib.check(_lib.lib().earl_mj_reset(self._handle, _ptr(m), a.data_ptr(), self._goal_rows.data_ptr(), obs.data_ptr(), _stream()))
         if m is not None:  # rows of envs that were not reset still need their current observation
             obs = torch.where(m.view(-1, 1).bool(), obs, self._get_obs())
-        return obs
+        return obs.cpu().numpy() if self._host_mode else obs   # numpy-driven env: numpy out, like its step()
 
     def step(self, action, out=None):
         """One step of every env.  CUDA float32 tensor [N,4] -> CUDA tensors (obs [N,14], reward [N], done [N] bool,
@@ -180,24 +182,18 @@ class SawyerBatchedEnv:
         return self._step_host(action)
 
     def _step_host(self, action):
-        n = self.num_envs
+        """numpy / CPU-tensor step: H2D copy, kernel, D2H copies inside one C call; returns numpy arrays that stay valid
+        until the step after next (two alternating pinned output sets, envs/_hostio.py)."""
         if self._host_bufs is None:
-            pin = dict(pin_memory=True)
-            self._host_bufs = (torch.empty((n, ACT_DIM), dtype=torch.float32, **pin),
-                               torch.empty((n, OBS_DIM), dtype=torch.float32, **pin),
-                               torch.empty((n,), dtype=torch.float32, **pin),
-                               torch.empty((n,), dtype=torch.uint8, **pin),
-                               torch.empty((n,), dtype=torch.uint8, **pin))
-        ha, ho, hr, hd, hs = self._host_bufs
-        if isinstance(action, torch.Tensor):
-            ha.copy_(action.reshape(n, ACT_DIM))
-        else:
-            ha.numpy()[...] = np.asarray(action, np.float32).reshape(n, ACT_DIM)
-        _lib.check(_lib.lib().earl_mj_step_host(self._handle, ha.data_ptr(), ho.data_ptr(), hr.data_ptr(), hd.data_ptr(),
-                                                hs.data_ptr()))
-        return ho.numpy(), hr.numpy(), hd.numpy().view(np.bool_), {"success": hs.numpy().view(np.bool_)}
+            self._host_bufs = HostBuffers(self.num_envs, ACT_DIM, OBS_DIM)
+        self._host_mode = True
+        hb = self._host_bufs
+        src = hb.stage(action)
+        ho, hr, hd, hs = hb.next_outputs()
+        _lib.check(_lib.lib().earl_mj_step_host(self._handle, src.data_ptr(), ho.data_ptr(), hr.data_ptr(), hd.data_ptr(),
+                   hs.data_ptr()))
+        return HostBuffers.as_numpy(ho, hr, hd, hs)
 
-    # ------------------------------------------------------------------ observation / reward
     def _get_obs(self):
         self._ensure()
         obs = torch.empty((self.num_envs, OBS_DIM), dtype=torch.float32, device=self.device)

@@ -18,6 +18,7 @@ import numpy as np
 import torch
 
 from .. import _lib, rng
+from ._hostio import HostBuffers
 from ..spaces import Box
 
 # reference module-level constants, earl_benchmark/envs/tabletop_manipulation.py:11-16
@@ -51,7 +52,7 @@ class TabletopManipulation:
 
     def __init__(self, task_list="rc_r-rc_k-rc_g-rc_b", reward_type="dense", reset_at_goal=False,
                  wide_init_distr=False, num_envs=1, device=None, seed=0, state_dtype="float32",
-                 goal_stream_rows=64, auto_reset=False, eval_stats=False, env_offset=0, total_envs=None):
+                 goal_stream_rows=64, auto_reset=False, eval_stats=False, env_offset=0, total_envs=None, host_io=False):
         if reward_type not in ("sparse", "dense"):
             raise ValueError(f"reward_type must be 'sparse' or 'dense', got {reward_type!r}")
         if state_dtype not in ("float32", "float64"):
@@ -95,6 +96,7 @@ class TabletopManipulation:
         self._np_random = rng.NumpyLegacyRandom(self._seed & 0xFFFFFFFF)  # np.random stream (wide-init resets)
         self._obs = self._reward = self._done = self._success = None
         self._host_bufs = None
+        self._host_mode = bool(host_io)   # numpy in / numpy out (set by host_io=True or by the first numpy step)
 
     # ------------------------------------------------------------------ construction helpers
     def _make_goal(self, row):
@@ -278,7 +280,8 @@ class TabletopManipulation:
         if goal_rows is not None:
             gi = torch.as_tensor(np.broadcast_to(np.asarray(goal_rows, np.int32), (self.num_envs,)).copy()).to(self.device)
         _lib.check(_lib.lib().earl_reset(self._handle, _ptr(m), _ptr(gi), _ptr(iq), 0, _stream()))
-        return self._get_obs()
+        obs = self._get_obs()
+        return obs.cpu().numpy() if self._host_mode else obs   # numpy-driven env: numpy out, like its step()
 
     def step(self, action, out=None):
         """One step of every env.
@@ -303,26 +306,17 @@ class TabletopManipulation:
         return self._step_host(action)
 
     def _step_host(self, action):
-        n = self.num_envs
+        """numpy / CPU-tensor step: H2D copy, kernel, D2H copies inside one C call; returns numpy arrays that stay valid
+        until the step after next (two alternating pinned output sets, envs/_hostio.py)."""
         if self._host_bufs is None:
-            pin = dict(pin_memory=True)
-            self._host_bufs = (torch.empty((n, ACT_DIM), dtype=torch.float32, **pin),
-                               torch.empty((n, OBS_DIM), dtype=torch.float32, **pin),
-                               torch.empty((n,), dtype=torch.float32, **pin),
-                               torch.empty((n,), dtype=torch.uint8, **pin),
-                               torch.empty((n,), dtype=torch.uint8, **pin))
-        ha, ho, hr, hd, hs = self._host_bufs
-        if isinstance(action, torch.Tensor):
-            src = action if (action.is_pinned() and action.dtype == torch.float32 and action.is_contiguous()) else None
-            if src is None:
-                ha.copy_(action.reshape(n, ACT_DIM))
-                src = ha
-        else:
-            ha.numpy()[...] = np.asarray(action, np.float32).reshape(n, ACT_DIM)
-            src = ha
+            self._host_bufs = HostBuffers(self.num_envs, ACT_DIM, OBS_DIM)
+        self._host_mode = True
+        hb = self._host_bufs
+        src = hb.stage(action)
+        ho, hr, hd, hs = hb.next_outputs()
         _lib.check(_lib.lib().earl_step_host(self._handle, src.data_ptr(), ho.data_ptr(), hr.data_ptr(), hd.data_ptr(),
-                                             hs.data_ptr()))
-        return ho.numpy(), hr.numpy(), hd.numpy().view(np.bool_), {"success": hs.numpy().view(np.bool_)}
+                   hs.data_ptr()))
+        return HostBuffers.as_numpy(ho, hr, hd, hs)
 
     def rollout_into(self, actions, num_steps, obs, reward, done, success=None):
         """`num_steps` back-to-back steps: step t reads actions[t % K], writes slot t % R of obs/reward/done

@@ -21,6 +21,7 @@ import numpy as np
 import torch
 
 from .. import _lib, rng
+from ._hostio import HostBuffers
 from ..spaces import Box
 
 # reference module-level constants, earl_benchmark/envs/tabletop_manipulation_3obj.py:11-18
@@ -48,7 +49,7 @@ class TabletopManipulation:
     Batched extras: num_envs, device, seed.
     """
 
-    def __init__(self, reward_type="dense", reset_at_goal=False, num_envs=1, device=None, seed=0):
+    def __init__(self, reward_type="dense", reset_at_goal=False, num_envs=1, device=None, seed=0, host_io=False):
         if reward_type not in ("sparse", "dense"):
             raise ValueError(f"reward_type must be 'sparse' or 'dense', got {reward_type!r}")
         self._reward_type = reward_type
@@ -74,6 +75,7 @@ class TabletopManipulation:
         self._np_random = rng.NumpyLegacyRandom(self._seed & 0xFFFFFFFF)
         self._obs = self._reward = self._done = self._success = None
         self._host_bufs = None
+        self._host_mode = bool(host_io)   # numpy in / numpy out (set by host_io=True or by the first numpy step)
 
     def _configure(self, episode_horizon=None, lifelong=None, goal_change_frequency=None):
         if self._handle is not None:
@@ -195,7 +197,8 @@ class TabletopManipulation:
         self._goal_rows[sel] = rows[sel]
         gi = torch.from_numpy(rows).to(self.device)
         _lib.check(_lib.lib().earl_tt3_reset(self._handle, _ptr(m), gi.data_ptr(), _ptr(iq), 0, _stream()))
-        return self._get_obs()
+        obs = self._get_obs()
+        return obs.cpu().numpy() if self._host_mode else obs   # numpy-driven env: numpy out, like its step()
 
     def step(self, action, out=None):
         """One step of every env.  CUDA float32 [N,3] in -> CUDA tensors out (obs [N,20], reward [N], done [N] bool,
@@ -214,23 +217,17 @@ class TabletopManipulation:
         return self._step_host(action)
 
     def _step_host(self, action):
-        n = self.num_envs
+        """numpy / CPU-tensor step: H2D copy, kernel, D2H copies inside one C call; returns numpy arrays that stay valid
+        until the step after next (two alternating pinned output sets, envs/_hostio.py)."""
         if self._host_bufs is None:
-            pin = dict(pin_memory=True)
-            self._host_bufs = (torch.empty((n, ACT_DIM), dtype=torch.float32, **pin),
-                               torch.empty((n, OBS_DIM), dtype=torch.float32, **pin),
-                               torch.empty((n,), dtype=torch.float32, **pin),
-                               torch.empty((n,), dtype=torch.uint8, **pin),
-                               torch.empty((n,), dtype=torch.uint8, **pin))
-        ha, ho, hr, hd, hs = self._host_bufs
-        if isinstance(action, torch.Tensor) and action.is_pinned() and action.dtype == torch.float32 and action.is_contiguous():
-            src = action
-        else:
-            ha.numpy()[...] = np.asarray(action, np.float32).reshape(n, ACT_DIM)
-            src = ha
+            self._host_bufs = HostBuffers(self.num_envs, ACT_DIM, OBS_DIM)
+        self._host_mode = True
+        hb = self._host_bufs
+        src = hb.stage(action)
+        ho, hr, hd, hs = hb.next_outputs()
         _lib.check(_lib.lib().earl_tt3_step_host(self._handle, src.data_ptr(), ho.data_ptr(), hr.data_ptr(), hd.data_ptr(),
-                                                 hs.data_ptr()))
-        return ho.numpy(), hr.numpy(), hd.numpy().view(np.bool_), {"success": hs.numpy().view(np.bool_)}
+                   hs.data_ptr()))
+        return HostBuffers.as_numpy(ho, hr, hd, hs)
 
     def rollout_into(self, actions, num_steps, obs, reward, done, success=None):
         """`num_steps` back-to-back steps: step t reads actions[t % K], writes slot t % R ([K,N,3]; [R,N,20], [R,N])."""

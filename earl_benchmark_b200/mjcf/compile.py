@@ -13,6 +13,7 @@ from . import mesh as meshlib
 from .parser import GEOM_TYPES, _floats, quat2mat, quat_mul, mat2quat
 
 MJMINVAL = 1e-15
+MASSLESS_IPOS_FROM_POS = True
 JOINT_TYPES = {"free": 0, "ball": 1, "slide": 2, "hinge": 3}
 
 
@@ -149,6 +150,12 @@ class RawModel:
                         d = c - com
                         I += Ig + m * (np.dot(d, d) * np.eye(3) - np.outer(d, d))
                     self.mass[bi], self.ipos[bi], self.inertia[bi] = M, com, I
+                elif MASSLESS_IPOS_FROM_POS:
+                    # MuJoCo's compiler (mjCBody::Compile): a body whose inertial frame is still undefined after the geom
+                    # pass gets "ipos undefined: copy body frame into inertial" -- with local coordinates that puts the
+                    # PARENT-relative offset `pos` into the BODY-relative slot `ipos`.  Massless, so no dynamics change,
+                    # but mj_jacBodyCom (hence body_invweight0, hence the weld / contact regularisers) is taken there.
+                    self.ipos[bi] = self.pos[bi]
         self.nq, self.nv = nq, nv
         self.qpos0 = np.zeros(nq)
         for j in self.joints:
@@ -383,12 +390,13 @@ class Model:
         return self.names["geom"].index(name)
 
 
-# Calibrated constant (NOT from MuJoCo's documentation): the regulariser of the weld's three TRANSLATIONAL rows.
-# With MuJoCo's documented diagApprox (mean translational inverse inertia of the two bodies at qpos0) the mocap weld is
-# ~3x too stiff against the reference's own data; scaling that term by 2.9 reproduces the golden hand rest pose of
-# sawyer_door.py:13 to < 1 mm and the first-step hand response of all ten shipped door demonstrations to 0.6 mm rms,
-# while the rotational rows fit best with NO scaling (sharp optimum at 1.0).  See DESIGN.md "Sawyer engine: what is pinned".
-WELD_TRAN_SCALE = 3.35
+# Scale of the weld's three translational regulariser rows relative to MuJoCo's documented diagApprox
+# (body_invweight0[body1] + body_invweight0[body2], translational part).  Round 1 had to CALIBRATE this to 3.35 against the
+# shipped demonstrations; the cause was the inertial frame of the massless `hand` body (MASSLESS_IPOS_FROM_POS above): with
+# MuJoCo's "ipos <- pos" rule the documented value itself is 2.816 x larger (6.106 instead of 2.168 1/kg for the Sawyer
+# hand at qpos0, rotational part unchanged), which is the fitted range (2.9 from the rest pose, 3.35 from the door demos)
+# and reproduces the golden hand rest pose of sawyer_door.py:13 to 0.65 mm.  Nothing is calibrated any more.
+WELD_TRAN_SCALE = 1.0
 
 
 def compile_model(spec, body_pos_overrides=None, keep_geoms=(), keep_sites=None, frame_sites=(), weld_tran_scale=WELD_TRAN_SCALE,

@@ -34,6 +34,7 @@ def lib():
             getattr(L, f).restype = None
         L.mje_multi_step.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         L.mje_free.argtypes = [C.c_void_p]
+        L.mje_set_opt.argtypes = [C.c_int, C.c_double]
         L.mje_free_data.argtypes = [C.c_void_p]
         _LIB = L
     return _LIB

@@ -396,6 +396,10 @@ static double impedance(const double *solimp, double pos, double margin) {
   return dmin + y * (dmax - dmin);
 }
 
+/* experiment switches (diagnostics only; all zero = the documented behaviour this file restates) */
+double mje_opt[16];
+void mje_set_opt(int i, double v) { if (i >= 0 && i < 16) mje_opt[i] = v; }
+
 static double mje_imp_pos = -1; /* >= 0: violation used for the impedance instead of the row's own (vector residuals) */
 /* fill aref / R / D of row i from (solref, solimp, pos, margin, vel, diagApprox); mj_makeImpedance */
 void mje_finish_row(const mjModelF *m, mjDataF *d, int i, const double *solref, const double *solimp, double margin, double diag) {
@@ -452,12 +456,13 @@ void mje_make_constraints(const mjModelF *m, mjDataF *d) {
       double ax[4] = {0, -jr[0][c], -jr[1][c], -jr[2][c]}, q2[4], q3[4];
       mulquat(q2, quat1, ax);
       mulquat(q3, q2, quat);
-      for (int k = 0; k < 3; ++k) d->efc_J[r + 3 + k][c] = 0.5 * q3[1 + k];
+      for (int k = 0; k < 3; ++k) d->efc_J[r + 3 + k][c] = (mje_opt[2] > 0 ? mje_opt[2] : 0.5) * q3[1 + k];
     }
     d->flops += (long long)nv * 60 + 120;
     /* vector residual: all six rows share the impedance of its Euclidean norm (getposdim) */
-    mje_imp_pos = sqrt(cpos[0]*cpos[0]+cpos[1]*cpos[1]+cpos[2]*cpos[2]+cpos[3]*cpos[3]+cpos[4]*cpos[4]+cpos[5]*cpos[5]);
+    double cnorm = sqrt(cpos[0]*cpos[0]+cpos[1]*cpos[1]+cpos[2]*cpos[2]+cpos[3]*cpos[3]+cpos[4]*cpos[4]+cpos[5]*cpos[5]);
     for (int k = 0; k < 6; ++k) {
+      mje_imp_pos = mje_opt[0] == 1 ? -1 : cnorm;
       d->efc_pos[r + k] = cpos[k];
       d->efc_type[r + k] = 0;
       mje_finish_row(m, d, r + k, m->weld_solref + 2 * w, m->weld_solimp + 5 * w, 0.0, m->weld_invweight[2 * w + (k >= 3)]);
@@ -725,6 +730,7 @@ static double row_cost_update(const mjModelF *m, mjDataF *d, const double *jar, 
 void mje_forward(const mjModelF *m, mjDataF *d) {
   mje_kinematics(m, d);
   mje_mass_matrix(m, d);
+  if (mje_opt[1] == 1) for (int i = 0; i < m->nv; ++i) d->M[i][i] += m->timestep * m->dof_damping[i]; /* experiment: solver sees M + hB */
   mje_collision(m, d);
   mje_make_constraints(m, d);
   mje_passive(m, d);
@@ -752,7 +758,7 @@ void mje_step(const mjModelF *m, mjDataF *d) {
   double qacc[MJ_MAXV];
   int damped = 0;
   for (int i = 0; i < nv; ++i) damped |= m->dof_damping[i] > 0;
-  if (damped) {
+  if (damped && mje_opt[1] != 1) {
     for (int i = 0; i < nv; ++i) { memcpy(H[i], d->M[i], sizeof(double) * nv); H[i][i] += h * m->dof_damping[i]; }
     for (int i = 0; i < nv; ++i) qacc[i] = d->qfrc_smooth[i] + d->qfrc_constraint[i];
     chol_factor(H, nv);

@@ -30,60 +30,79 @@ def test_handle_position_known_answers(oracle):
 
 def test_hand_rest_pose_known_answer(oracle):
     """Hand position after sim.reset() + _reset_hand() (sawyer_door.py:13): a snapshot of a still-moving arm 250
-    substeps after a 1 m weld pull, so it pins weld, limits, bias forces and integration together.  Reached to 2 mm."""
+    substeps after a 1.1 m weld pull (the hand is still tilted 29 degrees off the mocap orientation at that instant), so
+    it pins weld, limits, bias forces, implicit-damping integration and the constraint regularisers together.  Reached to
+    0.65 mm in every coordinate with NO fitted constant (round 1: 1.7 mm with the weld regulariser calibrated to 3.35 x)."""
     ob = oracle.reset()
-    assert np.abs(ob[:3] - sawyer_door.initial_states[0][:3]).max() < 2e-3
+    assert np.abs(ob[:3] - sawyer_door.initial_states[0][:3]).max() < 1e-3
     assert ob[3] == 1.0
 
 
-def _replay(oracle, which):
-    d = demos.load("sawyer_door", which)
-    obs, nobs, act = d["observations"], d["next_observations"], d["actions"]
-    term, rew = d["terminals"].ravel(), d["rewards"].ravel()
-    ends = list(np.nonzero(term)[0] + 1)
-    starts = [0] + ends[:-1]
-    out = []
-    for s, en in zip(starts, ends):
-        oracle.goal = obs[s][7:14].astype(np.float64)
-        oracle.reset(door_angle=door_angle(obs[s][4:6]))
-        r, hand, handle = [], [], []
-        for t in range(s, en):
-            ob, rr = oracle.step(act[t])
-            r.append(rr)
-            hand.append(np.abs(ob[:3] - nobs[t][:3]).max())
-            handle.append(np.abs(ob[4:7] - nobs[t][4:7]).max())
-        out.append(dict(reward=np.array(r), demo_reward=rew[s:en], hand=np.array(hand), handle=np.array(handle)))
+def test_weld_regulariser_is_derived():
+    """The weld's translational regulariser is MuJoCo's documented body_invweight0 sum with scale 1.0: the factor round 1
+    had to calibrate (2.9 from the rest pose, 3.35 from the door demonstrations) is the inertial frame of the MASSLESS
+    `hand` body, which MuJoCo's compiler puts at ipos = pos ("ipos undefined: copy body frame"), 0.12 m off the body origin:
+    mj_jacBodyCom there gives 6.106 1/kg instead of 2.168 (x 2.816), the rotational weight is unchanged (284.9)."""
+    from earl_benchmark_b200.envs import sawyer_peg
+    from earl_benchmark_b200.mjcf import compile as C
+    assert C.WELD_TRAN_SCALE == 1.0 and C.MASSLESS_IPOS_FROM_POS
+    for path in (sawyer_door.MODEL_PATH, sawyer_peg.MODEL_PATH):
+        m = Model.load(path)
+        assert abs(m.weld_invweight[0, 0] - 6.1056) < 1e-3 and abs(m.weld_invweight[0, 1] - 284.895) < 1e-2
+        assert abs(m.weld_invweight[0, 0] / 2.16812 - 2.816) < 2e-3
+
+
+def _replay(oracle, task, which):
+    import sys, os
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import demo_eval
+    return demo_eval.replay(oracle, task, which)
+
+
+def _summary(eps):
+    import demo_eval
+    return demo_eval.summarise(eps)
+
+
+def test_forward_door_demonstrations_by_episode(oracle):
+    """Five door-closing episodes (75-85 steps, the hand pushing the door shut against the friction of a door panel that
+    `obj_init_pos` sinks 23 mm into the table), replayed open loop and judged BY EPISODE: all five reach success; the
+    success step is 2-5 steps EARLY (recorded 77, 78, 74, 77, 84; replay 75, 74, 70, 73, 79), i.e. one episode inside the
+    +-3 band.  The hand stays within 5.5 cm and the handle within 4 cm of the recording over whole episodes.
+    (Round 1's calibrated weld gave 4 of 5 within one step -- by construction: the constant was fitted to these episodes.)"""
+    eps = _replay(oracle, "sawyer_door", "forward")
     oracle.goal = oracle.GOAL.copy()
-    return out
+    assert len(eps) == 5 and all(e["success"] for e in eps)
+    for e in eps:
+        assert -5 <= e["step"] - e["demo_step"] <= 0, (e["step"], e["demo_step"])
+        assert e["hand"].max() < 0.055 and e["obj"].max() < 0.04
+    s = _summary(eps)
+    assert s["within3"] >= 1
 
 
-def test_forward_demonstrations_replay_open_loop(oracle):
-    """Five door-closing episodes (75-85 steps each, hand pushing the door against table friction): the open-loop
-    replay keeps the hand within 1.5 cm and the handle within 1.2 cm of the recorded trajectory for the whole episode;
-    four of the five episodes close the door within one step of the recorded success step, the fifth is 1 cm short
-    of the goal when the recording ends."""
-    eps = _replay(oracle, "forward")
-    assert len(eps) == 5
-    exact = 0
-    for ep in eps:
-        assert ep["hand"].max() < 0.015 and ep["handle"].max() < 0.012
-        demo_step = int(np.nonzero(ep["demo_reward"])[0][0])
-        first = np.nonzero(ep["reward"])[0]
-        exact += int(len(first) > 0 and abs(int(first[0]) - demo_step) <= 1)
-    assert exact >= 4
-
-
-def test_sparse_reward_agreement_over_all_demonstrations(oracle):
-    """North-star bar: >= 99 % per-step sparse-reward agreement over the shipped demonstrations (1,095 transitions).
-    The five reverse (grasp-and-pull) episodes track the recording until the grasp and then lose the handle, so
-    their single success step each is counted as a mismatch."""
-    eps = _replay(oracle, "forward") + _replay(oracle, "reverse")
-    total = sum(len(e["reward"]) for e in eps)
-    mism = sum(int((e["reward"] != e["demo_reward"]).sum()) for e in eps)
-    assert total == 1095
-    assert 1 - mism / total >= 0.99, (mism, total)
-    for ep in eps[5:]:  # reverse episodes: free-space approach (first 45 steps) tracks the recording
-        assert ep["hand"][:45].max() < 0.03
+def test_sparse_reward_agreement_next_to_the_all_zeros_predictor(oracle, peg_oracle):
+    """North-star bar: >= 99 % per-step sparse-reward agreement over the shipped demonstrations -- reported NEXT TO what
+    predicting reward 0 everywhere scores, because one success step per episode makes that predictor hard to beat
+    (VERDICT r1 weak #1), and by episode.  State of the checker with nothing fitted:
+        door forward  5/5 episodes succeed (2-5 steps early)   agreement 0.949   all-zeros 0.987
+        door reverse  0/5 (the grasp of the 4 cm handle bar is missed: the free-space approach is up to 16 mm off)
+                                                              agreement 0.993 = all-zeros 0.993
+        peg  forward  0/10, peg reverse 2/20                   agreement 0.985 / 0.970, all-zeros 0.985 / 0.982
+    The bar is NOT met (KNOWN GAP); these assertions keep the numbers honest and fail if they move."""
+    rows = {}
+    for name, o, task in (("door", oracle, "sawyer_door"), ("peg", peg_oracle, "sawyer_peg")):
+        for which in ("forward", "reverse"):
+            rows[f"{name}_{which}"] = _summary(_replay(o, task, which))
+        o.goal = o.GOAL.copy()
+    print({k: (v["success"], v["episodes"], round(v["agreement"], 4), round(v["all_zeros"], 4)) for k, v in rows.items()})
+    assert (rows["door_forward"]["success"], rows["door_forward"]["episodes"]) == (5, 5)
+    assert rows["door_reverse"]["episodes"] == 5 and rows["peg_forward"]["episodes"] == 10 and rows["peg_reverse"]["episodes"] == 20
+    total = sum(v["episodes"] for v in rows.values())
+    succ = sum(v["success"] for v in rows.values())
+    assert total == 40 and 5 <= succ < 40
+    for k, v in rows.items():     # whoever improves the engine must update the documented table above
+        assert v["agreement"] >= v["all_zeros"] - 0.04
+    assert rows["door_reverse"]["hand_max"] < 0.40
 
 
 # ------------------------------------------------------------------------------------------------ sawyer_peg
@@ -97,37 +116,14 @@ def peg_oracle():
 def test_peg_reset_known_answers(peg_oracle):
     """initial_states of sawyer_peg.py:18-50: pegHead = peg position - (0.1, 0, 0) at z = 0.02 (exact: FK of the free
     joint + site), hand rest pose [0.00615235, 0.6001898, 0.19430117] after sim.reset() + _reset_hand().
-    KNOWN GAP: the hand rest pose (a snapshot of a moving arm with joint j1 on its limit) is reproduced to 1.2 cm only."""
+    KNOWN GAP: the hand rest pose (a snapshot of a moving arm with joint j1 resting ON its limit from substep ~100 on, a
+    regime the door scene never visits) is reproduced to 1.1 cm only (x; 1.3 mm in y, 3.3 mm in z)."""
     from earl_benchmark_b200.envs import sawyer_peg
     for row in sawyer_peg.initial_states[:4]:
         ob = peg_oracle.reset(peg_pos=row[4:7] + np.array([0.1, 0, 0]))
         assert np.abs(ob[4:7] - row[4:7]).max() < 1e-6
         assert np.abs(ob[:3] - row[:3]).max() < 0.012
         assert ob[3] == 1.0
-
-
-def test_peg_demonstrations_are_not_reproduced(peg_oracle):
-    """Documents the state of the peg checker honestly: the open-loop replay of the shipped forward demonstrations
-    tracks the recorded HAND within 7 cm, but the grasp-lift-insert sequence is not reproduced (the peg is left behind),
-    so no episode reaches the goal and the per-step sparse agreement (98.4 %) is below the 99 % north-star bar."""
-    d = demos.load("sawyer_peg", "forward")
-    obs, nobs, act = d["observations"], d["next_observations"], d["actions"]
-    term, rew = d["terminals"].ravel(), d["rewards"].ravel()
-    ends = list(np.nonzero(term)[0] + 1)
-    total = mism = 0
-    for s, en in zip([0] + ends[:-1], ends):
-        peg_oracle.goal = obs[s][7:14].astype(np.float64)
-        peg_oracle.reset(peg_pos=obs[s][4:7].astype(np.float64) + np.array([0.1, 0, 0]))
-        r, hand = [], []
-        for t in range(s, en):
-            ob, rr = peg_oracle.step(act[t])
-            r.append(rr)
-            hand.append(np.abs(ob[:3] - nobs[t][:3]).max())
-        assert max(hand) < 0.07
-        total += en - s
-        mism += int((np.array(r) != rew[s:en]).sum())
-    peg_oracle.goal = peg_oracle.GOAL.copy()
-    assert 0.98 <= 1 - mism / total < 0.99
 
 
 def test_gripper_opening_trajectory_known_answer(oracle):
@@ -145,36 +141,33 @@ def test_gripper_opening_trajectory_known_answer(oracle):
     assert ref.min() < 0.28 and np.abs(sim - ref).max() < 4e-4, np.abs(sim - ref).max()
 
 
-def test_recorded_weld_lag_vs_documented_and_calibrated_weld():
-    """KNOWN GAP, kept measurable.  The mocap position follows from the recorded actions, so hand - mocap is observable
-    in the demonstrations.  While the mocap descends at ~0.93 cm per env step the RECORDED hand settles 32-34 mm behind
-    it.  With MuJoCo's documented weld regulariser the checker settles at the critically damped value
-    2 * timeconst * v (minus one substep of observation staleness) = 28-29 mm; with the calibrated translational
-    regulariser (`WELD_TRAN_SCALE` = 3.35) it follows the recording within 2 mm."""
-    from earl_benchmark_b200.mjcf.compile import WELD_TRAN_SCALE
+def test_recorded_weld_lag_with_the_derived_regulariser(oracle):
+    """The mocap position follows from the recorded actions, so hand - mocap is observable in the demonstrations.  While
+    the mocap descends at ~0.93 cm per env step (first forward door episode) the RECORDED hand settles 32-34 mm behind it.
+    A critically damped weld alone would give 2 * timeconst * v = 28-29 mm (what round 1's checker did with the body-origin
+    regulariser); with the derived regulariser (R / A ~ 1 in z at this pose, so joint damping leaks into the lag) the
+    checker follows the recorded z-lag within 2 mm on every one of the first nine steps, and the x-lag within 3.5 mm over
+    the first five (after that the recorded hand falls up to 9 mm further behind in x: the open gap of DESIGN.md 8.4)."""
     d = demos.load("sawyer_door", "forward")
     obs, nobs, act = d["observations"], d["next_observations"], d["actions"]
     assert np.all(act[:9, 2] < -0.85)                      # steady descent
-    lags = {}
-    for name, scale in (("calibrated", 1.0), ("documented", 1.0 / WELD_TRAN_SCALE)):
-        m = Model.load(sawyer_door.MODEL_PATH)
-        m.weld_invweight[:, 0] *= scale
-        o = SawyerDoorOracle(m)
-        o.goal = obs[0][7:14].astype(np.float64)
-        o.reset(door_angle=door_angle(obs[0][4:6]))
-        mocap = o.HAND_INIT.copy()
-        lag_demo, lag_sim = [], []
-        for t in range(9):
-            a = np.clip(act[t].astype(np.float64), -1, 1)
-            mocap = np.clip(mocap + a[:3] * o.ACTION_SCALE, o.MOCAP_LOW, o.MOCAP_HIGH)
-            ob, _ = o.step(act[t])
-            lag_demo.append(nobs[t][2] - mocap[2])
-            lag_sim.append(ob[2] - mocap[2])
-        lags[name] = np.array(lag_sim)
-    lag_demo = np.array(lag_demo)
-    assert 0.0315 < lag_demo[6:].max() < 0.0355, lag_demo               # recorded: 32-34 mm
-    assert 0.0275 < lags["documented"][6:].max() < 0.0300, lags         # 2 * 0.02 s * 0.74 m/s - staleness
-    assert np.abs(lags["calibrated"][3:] - lag_demo[3:]).max() < 2e-3, (lags, lag_demo)
+    o = oracle
+    o.goal = obs[0][7:14].astype(np.float64)
+    o.reset(door_angle=door_angle(obs[0][4:6]))
+    mocap = o.HAND_INIT.copy()
+    lag_demo, lag_sim = [], []
+    for t in range(9):
+        a = np.clip(act[t].astype(np.float64), -1, 1)
+        mocap = np.clip(mocap + a[:3] * o.ACTION_SCALE, o.MOCAP_LOW, o.MOCAP_HIGH)
+        ob, _ = o.step(act[t])
+        lag_demo.append(nobs[t][:3] - mocap)
+        lag_sim.append(ob[:3] - mocap)
+    o.goal = o.GOAL.copy()
+    lag_demo, lag_sim = np.array(lag_demo), np.array(lag_sim)
+    assert 0.0315 < lag_demo[6:, 2].max() < 0.0355, lag_demo               # recorded: 32-34 mm
+    assert 0.0310 < lag_sim[6:, 2].max() < 0.0340, lag_sim
+    assert np.abs(lag_sim[:, 2] - lag_demo[:, 2]).max() < 2e-3, (lag_sim, lag_demo)
+    assert np.abs(lag_sim[:5, 0] - lag_demo[:5, 0]).max() < 4.5e-3, (lag_sim, lag_demo)
 
 
 def test_peg_dense_reward_building_blocks(peg_oracle):
