@@ -441,6 +441,168 @@ def config_dict(args, n_total):
 
 # ----------------------------------------------------------------------------------------------- GPU arm
 
+MIN_REGION_S = 0.30      # the CUDA-event pair always brackets at least this much device time (a 0.33 ms region
+                         # made the driver's --steps 20 run measure the NCCL barrier's aftermath, not the kernel)
+
+
+def pin_to_gpu_numa(local):
+    """Run this rank on the CPUs NVML reports as local to its GPU BEFORE any pinned allocation, so that first-touch puts
+    the pinned staging buffers on the GPU's own NUMA node (matters when 8 ranks share the host)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = [64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1]
+        cpus = [c for c in cpus if c in os.sched_getaffinity(0)]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return f"{len(cpus)} cpus [{min(cpus)}..{max(cpus)}]" if cpus else "nvml affinity empty"
+    except Exception as e:  # not fatal: the default placement is what round 1 measured
+        return f"unavailable ({type(e).__name__})"
+
+
+def timed_blocks(rollout, steps, barrier, dev):
+    """Time R repetitions of the K-step block with ONE CUDA-event pair on the launching stream.
+
+    barrier -> one untimed K-step priming block (the NCCL barrier kernel evicts the L2-resident state and the first
+    launches after it pay for that; at N=1 it is a no-op) -> estimate the block time -> choose R so the timed region is
+    >= MIN_REGION_S (same R on every rank) -> barrier -> priming block -> e0, R x K steps, e1 -> sync -> max over ranks.
+    Returns (ms_total, reps)."""
+    import torch
+
+    from earl_benchmark_b200.distributed import max_over_ranks
+    barrier()
+    rollout(steps)
+    a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a0.record()
+    rollout(steps)
+    a1.record()
+    torch.cuda.synchronize()
+    est_ms = max(max_over_ranks(a0.elapsed_time(a1), dev), 1e-3)
+    reps = int(min(4096, max(1, -(-MIN_REGION_S * 1e3 // est_ms))))
+    barrier()
+    rollout(steps)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        rollout(steps)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = max_over_ranks(e0.elapsed_time(e1), dev)
+    barrier()
+    return ms, reps
+
+
+def tabletop_point(eb, dev, rank, world, barrier, n, steps, gen, label, alg_bytes=ALG_BYTES_PER_ENV_STEP, **kw):
+    """One extra operating point of the tabletop step: n envs per GPU, `steps`-step blocks."""
+    import torch
+    ring_a, ring_o = (64, 16) if n <= (1 << 20) else (8, 4)
+    loader = eb.EARLEnvs("tabletop_manipulation", reward_type="sparse", num_envs=n * world, rank=rank, world_size=world,
+                         device=dev, seed=0, goal_stream_rows=kw.pop("goal_stream_rows", 2), **kw)
+    train, _ = loader.get_envs()
+    train.reset()
+    a = torch.rand((ring_a, n, 3), generator=gen, device=dev, dtype=torch.float32) * 2 - 1
+    o = torch.empty((ring_o, n, 12), device=dev, dtype=torch.float32)
+    r = torch.empty((ring_o, n), device=dev, dtype=torch.float32)
+    d = torch.empty((ring_o, n), device=dev, dtype=torch.uint8)
+    env = train.env
+    env.rollout_into(a, 20, o, r, d)
+    l0 = env.launch_count
+    ms, reps = timed_blocks(lambda k: env.rollout_into(a, k, o, r, d), steps, barrier, dev)
+    per_launch_s = ms * 1e-3 / (steps * reps)
+    out = {"point": label, "envs_per_gpu": n, "total_envs": n * world, "steps": steps, "reps": reps,
+           "value": n * world / per_launch_s, "unit": UNIT, "ms_per_step": per_launch_s * 1e3,
+           "achieved": alg_bytes * n / per_launch_s / 1e9, "algorithmic_bytes_per_env_step": alg_bytes,
+           "num_interventions_mean": float(train.num_interventions.double().mean()) if hasattr(train.num_interventions, "double") else None}
+    del a, o, r, d, train, loader, env
+    torch.cuda.empty_cache()
+    return out
+
+
+def pcie_ceiling(dev, n, barrier, reps=10):
+    """The e2e roofline: this step's own byte mix (12 B up, 54 B down per env) moved with plain pinned cudaMemcpyAsync on
+    two streams, all ranks at once -- no kernel, no library of this repo involved."""
+    import torch
+
+    from earl_benchmark_b200.distributed import max_over_ranks
+    up = torch.empty((n, 3), dtype=torch.float32).pin_memory()
+    down = [torch.empty((n, 12), dtype=torch.float32).pin_memory(), torch.empty((n,), dtype=torch.float32).pin_memory(),
+            torch.empty((n, 2), dtype=torch.uint8).pin_memory()]
+    d_up = torch.empty((n, 3), dtype=torch.float32, device=dev)
+    d_down = [torch.empty_like(t, device=dev) for t in down]
+    s_up, s_down = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+
+    def once():
+        with torch.cuda.stream(s_up):
+            d_up.copy_(up, non_blocking=True)
+        with torch.cuda.stream(s_down):
+            for h, g in zip(down, d_down):
+                h.copy_(g, non_blocking=True)
+    once()
+    torch.cuda.synchronize()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        once()
+    torch.cuda.synchronize()
+    el = max_over_ranks(time.perf_counter() - t0, dev)
+    return n * reps / el, (n * 54 * reps) / el / 1e9, (n * 12 * reps) / el / 1e9
+
+
+def eval_collective_check(eb, dev, rank, world, barrier):
+    """the system's ONE collective, on hardware.  Every rank runs a short evaluation episode on its shard of the
+    eval env, reduces (sum return, successes, N) on the device, and all-reduces the 4 doubles over NCCL; the result must
+    equal the sum of the per-rank vectors gathered separately, and count every env of the job."""
+    import torch
+    import torch.distributed as dist
+
+    from earl_benchmark_b200.distributed import all_reduce_eval_stats
+    n = 4096
+    loader = eb.EARLEnvs("tabletop_manipulation", reward_type="sparse", num_envs=n * world, rank=rank, world_size=world,
+                         device=dev, seed=0, eval_horizon=50)
+    _, ev = loader.get_envs()
+    ev.reset()
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(555 + rank)
+    for _ in range(50):
+        ev.step(torch.rand((n, 3), generator=gen, device=dev) * 2 - 1)
+    local = ev.env.eval_stats().clone()
+    gathered = [torch.zeros_like(local) for _ in range(world)]
+    if world > 1:
+        dist.all_gather(gathered, local)
+    else:
+        gathered = [local]
+    expect = torch.stack(gathered).sum(0)
+    barrier()
+    red = local.clone()
+    lat = []
+    for k in range(12):     # first calls include NCCL's lazy channel setup: report the steady latency
+        buf = local.clone()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        stats = all_reduce_eval_stats(buf)
+        lat.append(time.perf_counter() - t0)
+        red = buf
+    ok = bool(torch.equal(red, expect)) and stats["num_envs"] == n * world
+    if not ok:
+        raise SystemExit(f"eval all-reduce mismatch: {red.tolist()} vs {expect.tolist()}, num_envs {stats['num_envs']}")
+    return {"world_size": world, "backend": "nccl" if world > 1 else "none (single process)", "num_envs": stats["num_envs"],
+            "mean_return": stats["mean_return"], "success_rate": stats["success_rate"],
+            "equals_sum_of_gathered_per_rank_stats": ok, "latency_us_median": 1e6 * statistics.median(lat[2:]),
+            "latency_us_first": 1e6 * lat[0], "bytes": 32}
+
+
+def ncu_traffic(num_envs):
+    """dram bytes per launch of the dominant kernel at this batch size, from the committed `ncu --set full` captures
+    (profiles/ncu_traffic.json, keyed by envs per GPU); None when no capture exists for the configuration."""
+    try:
+        t = json.load(open(os.path.join(REPO, "profiles", "ncu_traffic.json")))["tabletop"].get(str(num_envs))
+        return (t["dram_bytes_read"] + t["dram_bytes_write"], t["source"]) if t else (None, None)
+    except Exception:
+        return None, None
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -451,6 +613,7 @@ def run_ours(args):
     rank, world, local = init_from_env()
     if world != args.gpus:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run")
+    numa = pin_to_gpu_numa(local)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     n = args.num_envs
@@ -482,19 +645,24 @@ def run_ours(args):
         env.rollout_into(actions, 256, obs, rew, done)
         torch.cuda.synchronize()
 
-    # ---- device-resident timing: exactly K steps, CUDA events on the launching stream
+    # ---- device-resident timing: `reps` repetitions of the K-step block inside one CUDA-event pair
     launches0 = env.launch_count
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_region0 = time.perf_counter()
-    e0.record()
-    env.rollout_into(actions, args.steps, obs, rew, done)
-    e1.record()
-    barrier()
+    if args.profile:
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        env.rollout_into(actions, args.steps, obs, rew, done)
+        e1.record()
+        barrier()
+        ms, reps = max_over_ranks(e0.elapsed_time(e1), dev), 1
+        launches = env.launch_count - launches0
+    else:
+        ms, reps = timed_blocks(lambda k: env.rollout_into(actions, k, obs, rew, done), args.steps, barrier, dev)
+        launches = args.steps * reps            # one kernel per step (the estimate / priming blocks are outside the region)
     t_region1 = time.perf_counter()
-    ms = max_over_ranks(e0.elapsed_time(e1), dev)
-    launches = env.launch_count - launches0
-    value = n_total * args.steps / (ms * 1e-3)
+    per_launch_s = ms * 1e-3 / (args.steps * reps)
+    value = n_total / per_launch_s
 
     # ---- end to end through the public API with host buffers
     e2e_steps = args.steps if args.e2e_steps is None else args.e2e_steps
@@ -512,33 +680,35 @@ def run_ours(args):
     e2e_value = n_total * e2e_steps / e2e_s
     h2d = n * 3 * 4
     d2h = n * (12 * 4 + 4 + 1 + 1)
+    ceiling = None
+    if not args.profile:
+        c_rate, c_down, c_up = pcie_ceiling(dev, n, barrier)
+        ceiling = {"value": c_rate * world, "unit": UNIT, "d2h_gbs_per_gpu": c_down, "h2d_gbs_per_gpu": c_up,
+                   "how": "the step's own byte mix (12 B up + 54 B down per env) as plain pinned cudaMemcpyAsync on two streams, "
+                          f"all {world} ranks concurrently, no kernel; pinned buffers allocated after binding to the GPU's NUMA "
+                          f"cpus ({numa})"}
     clocks = sampler.stop(t_region0, t_region1) if sampler else None
 
-    # ---- second operating point: 8,388,608 envs per GPU, where state, actions and outputs all stream from HBM
-    big = None
-    if not args.profile and not args.no_hbm_check and n < (1 << 23):
+    # ---- the other batch sizes, strong scaling, the done / auto-reset path, fp64 state, all-HBM points
+    sweep, big = [], None
+    if not args.profile and not args.no_hbm_check:
         del actions, obs, rew, done
-        nb, kb = 1 << 23, max(20, min(args.steps, 300))
-        lb = eb.EARLEnvs("tabletop_manipulation", reward_type="sparse", num_envs=nb * world, rank=rank, world_size=world,
-                         device=dev, seed=0, train_horizon=TRAIN_HORIZON, goal_stream_rows=2)
-        tb, _ = lb.get_envs()
-        tb.reset()
-        a_b = torch.rand((8, nb, 3), generator=gen, device=dev, dtype=torch.float32) * 2 - 1
-        o_b = torch.empty((4, nb, 12), device=dev, dtype=torch.float32)
-        r_b = torch.empty((4, nb), device=dev, dtype=torch.float32)
-        d_b = torch.empty((4, nb), device=dev, dtype=torch.uint8)
-        tb.env.rollout_into(a_b, 20, o_b, r_b, d_b)
-        barrier()
-        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        b0.record()
-        tb.env.rollout_into(a_b, kb, o_b, r_b, d_b)
-        b1.record()
-        barrier()
-        ms_b = max_over_ranks(b0.elapsed_time(b1), dev)
-        big = {"envs_per_gpu": nb, "steps": kb, "value": nb * world * kb / (ms_b * 1e-3), "unit": UNIT,
-               "achieved": ALG_BYTES_PER_ENV_STEP * nb / (ms_b * 1e-3 / kb) / 1e9,
-               "kernel": "earl::tabletop_step_tma_kernel<3,256>  (cp.async.bulk pipeline)"}
-        del a_b, o_b, r_b, d_b, tb, lb
+        torch.cuda.empty_cache()
+        k = max(20, min(args.steps, 200))
+        pts = [("weak 65,536 envs per GPU", 1 << 16, {}, ALG_BYTES_PER_ENV_STEP),
+               ("weak 262,144 envs per GPU", 1 << 18, {}, ALG_BYTES_PER_ENV_STEP),
+               ("strong 1,048,576 envs in total", (1 << 20) // world, {}, ALG_BYTES_PER_ENV_STEP),
+               ("train_horizon=64 with auto_reset (done fires every 64 steps, reset + goal draw inside the step kernel)",
+                1 << 20, dict(train_horizon=64, auto_reset=True, goal_stream_rows=64), ALG_BYTES_PER_ENV_STEP),
+               ("state_dtype=float64 (the bit-exact operating point: fp64 qpos, 32 B r + 32 B w instead of 16 + 16)",
+                1 << 20, dict(state_dtype="float64", train_horizon=TRAIN_HORIZON), ALG_BYTES_PER_ENV_STEP + 32),
+               ("all-HBM 4,194,304 envs per GPU (one-tile-per-CTA kernel)", 1 << 22, dict(train_horizon=TRAIN_HORIZON), ALG_BYTES_PER_ENV_STEP),
+               ("all-HBM 8,388,608 envs per GPU (one-tile-per-CTA kernel)", 1 << 23, dict(train_horizon=TRAIN_HORIZON), ALG_BYTES_PER_ENV_STEP)]
+        for label, npg, kw, ab in pts:
+            kw.setdefault("train_horizon", TRAIN_HORIZON)
+            sweep.append(tabletop_point(eb, dev, rank, world, barrier, npg, k, gen, label, alg_bytes=ab, **kw))
+        big = dict(sweep[-1], kernel="earl::tabletop_step_tile_kernel (one 256-env tile per CTA, PDL)")
+    collective = eval_collective_check(eb, dev, rank, world, barrier) if not args.profile else None
 
     door = peg = kit = tt3 = None
     if not args.profile and not args.no_door:
@@ -553,28 +723,42 @@ def run_ours(args):
 
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
-        if big is not None:
-            big["frac"] = big["achieved"] / peak
-        per_launch_s = ms * 1e-3 / args.steps
+        for pt in sweep:
+            pt["frac"] = pt["achieved"] / peak
         achieved = ALG_BYTES_PER_ENV_STEP * n / per_launch_s / 1e9
-        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config_dict(args, n_total),
+        traffic, traffic_src = (args.traffic_bytes, "--traffic-bytes") if args.traffic_bytes is not None else ncu_traffic(n)
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "reps": reps,
+                "warmup": args.warmup, "ms_per_step": per_launch_s * 1e3, "timed_region_s": ms * 1e-3,
+                "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64", "state_dtype": "float32",
+                "dtype_note": "arithmetic in fp64 (explicit round-to-nearest), state STORED as fp32 between steps (the 113-B layout): "
+                              "one step from fp32-representable states is bit-exact; the sweep's float64 point keeps fp64 state "
+                              "and is bit-exact over whole rollouts",
+                "data": "synthetic", "config": config_dict(args, n_total),
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d * world,
                         "d2h_bytes_per_step": d2h * world, "steps": e2e_steps,
-                        "api": "PersistentStateWrapper.step(pinned host actions) -> host obs/reward/done/success"},
+                        "api": "PersistentStateWrapper.step(pinned host actions) -> host obs/reward/done/success",
+                        "pcie_ceiling": ceiling,
+                        "frac_of_pcie_ceiling": (e2e_value / ceiling["value"]) if ceiling else None},
                 "gpu_launches": launches,
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                             "traffic": args.traffic_bytes, "peak_source": peak_src,
-                             "kernel": ("earl::tabletop_step_kernel<false,true,1>  (LSU path, PDL)" if n <= 3 * 1024 * 1024
-                                        else "earl::tabletop_step_tma_kernel<3,256>  (cp.async.bulk pipeline, PDL)"),
+                             "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                             "kernel": ("earl::tabletop_step_kernel<false,true,1>  (persistent LSU kernel, PDL)" if n <= 3 * 1024 * 1024
+                                        else "earl::tabletop_step_tile_kernel  (one 256-env tile per CTA, PDL)"),
                              "note": "per-env state (24 B) stays L2-resident at this batch size, so the algorithmic-byte "
-                                     "rate can exceed the HBM copy peak; hbm_bound_check is the all-HBM operating point",
+                                     "rate can exceed the HBM copy peak; frac_all_hbm is the operating point where state, "
+                                     "actions and outputs all stream from HBM (8,388,608 envs per GPU)",
+                             "frac_all_hbm": (big["achieved"] / peak) if big else None,
+                             "achieved_all_hbm": big["achieved"] if big else None,
                              "algorithmic_bytes_per_launch": ALG_BYTES_PER_ENV_STEP * n,
                              "avg_launch_us": per_launch_s * 1e6},
                 "clocks": clocks}
         if big is not None:
             line["hbm_bound_check"] = big
+        if sweep:
+            line["sweep"] = sweep
+        if collective is not None:
+            line["eval_collective"] = collective
         if tt3 is not None:
             tt3["frac"] = tt3["achieved"] / peak
             line["tabletop_3obj"] = tt3
@@ -589,7 +773,9 @@ def run_ours(args):
             rate, n_sample, el = cpu_port_rate(n, min(args.steps, 200), threads, budget_s=15.0)
             line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
                                     "sample": f"{n_sample} envs x {min(args.steps, 200)} steps of the same workload, "
-                                              f"step-major C oracle, OpenMP {threads} threads, {el:.2f} s"}
+                                              f"step-major C oracle, OpenMP {threads} threads, {el:.2f} s",
+                                    "note": "a C restatement of the reference arithmetic, ~1e4 x faster than the reference's own "
+                                            "Python loop (3.6e4 env-steps/s per core behind a no-op MuJoCo stand-in, DESIGN.md 3)"}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
@@ -610,13 +796,9 @@ def main():
     ap.add_argument("--no-door", action="store_true", help="skip the sawyer_door / sawyer_peg sections")
     ap.add_argument("--profile", action="store_true", help="under ncu: no sustained warm-up, 1 e2e step, no CPU leg")
     ap.add_argument("--traffic-bytes", type=float, default=None,
-                    help="dram bytes per launch from the committed ncu capture; default: profiles/r01 value for the "
-                         "default workload, else null")
+                    help="dram bytes per launch of the step kernel; default: looked up by batch size in "
+                         "profiles/ncu_traffic.json (committed `ncu --set full` captures), else null")
     args = ap.parse_args()
-    if args.traffic_bytes is None and args.num_envs == 1 << 20:
-        # profiles/r01/prof_step_lsu_1M_r01.raw.csv: dram__bytes_read.sum 37.76 MB + dram__bytes_write.sum 23.88 MB per
-        # launch (ncu --set full, cold L2; the remaining writes are still dirty in the 126 MB L2 when the kernel ends)
-        args.traffic_bytes = 37.759488e6 + 23.884032e6
     if args.impl == "reference":
         return run_reference(args)
     if args.gpus > 1 and "WORLD_SIZE" not in os.environ:

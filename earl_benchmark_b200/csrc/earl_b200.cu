@@ -65,7 +65,7 @@ struct earl_handle {
   int device = 0;
   int sm_count = 0;
   int step_grid = 0;
-  int variant = -1;       // EARL_TT_VARIANT: -1 = auto (LSU kernel up to 3M envs, 3-stage TMA pipeline above);
+  int variant = -1;       // EARL_TT_VARIANT: -1 = auto (LSU kernel up to 3M envs, one-tile-per-CTA kernel above); 5 = tile kernel;
                           // 0 = LSU kernel; 6/8 = LSU kernel with min 6/8 CTAs per SM; 2/3/4 = TMA pipeline stages
   bool pdl = true;        // EARL_TT_PDL=0 disables programmatic dependent launch between consecutive steps
   int host_chunks = 0;    // EARL_TT_HOST_CHUNKS: chunks of the host-buffer pipeline (0 = one per 256k envs, at most 16)
@@ -200,6 +200,20 @@ int launch_step_range(earl_handle* h, int first, int count, const float* actions
     if (p.first >= p.n) return 0;
   }
   const int tiles = (p.n - p.first + earl::kTTBlock - 1) / earl::kTTBlock;
+  if (h->variant == 5 && fast && !f64(h)) {  // one 256-env tile per CTA (obs rows are 48 B: every tile starts 16-byte aligned)
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)tiles);
+    cfg.blockDim = dim3((unsigned)earl::kTTBlock);
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = h->pdl ? 1 : 0;
+    CU(cudaLaunchKernelEx(&cfg, earl::tabletop_step_tile_kernel, p));
+    h->launches += 1;
+    return 0;
+  }
   const int grid = tiles < h->step_grid ? tiles : h->step_grid;
   if (f64(h)) {
     if (fast) earl::tabletop_step_kernel<true, true><<<grid, earl::kTTBlock, 0, s>>>(p);
@@ -335,7 +349,7 @@ int earl_create(const earl_config* cfg, const void* model_blob, size_t model_nby
   // measured on B200 (profiles/round1_variants.md): while the 24 B/env state fits in L2 next to the streams
   // the LSU kernel wins (more resident warps hide L2 latency); once everything streams from HBM the
   // bulk-copy pipeline keeps more bytes in flight and wins.
-  if (h->variant < 0) h->variant = cfg->num_envs > 3 * 1024 * 1024 ? 3 : 0;
+  if (h->variant < 0) h->variant = cfg->num_envs > 3 * 1024 * 1024 ? 5 : 0;
   if (const char* v = getenv("EARL_TT_PDL")) h->pdl = atoi(v) != 0;
   if (const char* v = getenv("EARL_TT_HOST_CHUNKS")) h->host_chunks = atoi(v);
   if (const char* v = getenv("EARL_TT_HOST_TAIL")) h->host_tail = atoi(v) != 0;

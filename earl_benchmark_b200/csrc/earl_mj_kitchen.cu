@@ -254,6 +254,20 @@ mjk_task_kernel(const Model* __restrict__ gm, const real* __restrict__ hull, con
     const int nsub = mode == 1 ? 10 * a.frame_skip : a.frame_skip;
     for (int s = 0; s < nsub; ++s) substep<32>(m, hull, w, lane);
     __syncwarp();
+    // A step that left a non-finite state (or whose factorisation broke down) is NOT stored: the environment stays at its
+    // last good state, the step returns that state's (noisy) observation with reward 0 and is counted in work[5]
+    // (the reference only prints MuJoCo's warning, ADEPT/simulation/module.py:123-126, and carries NaNs on).
+    bool fin = true;
+    for (int k = lane; k < kNQ; k += 32) fin = fin && isfinite(w.qpos[k]) && isfinite(w.qvel[k]);
+    const bool failed = mode == 0 && (!__all_sync(0xffffffffu, fin) || (w.bad & 1));
+    if (failed) {
+      const unsigned bad_k = w.bad | 1u;
+      __syncwarp();
+      task_load(a, w, env, lane);
+      kinematics<32>(m, w, lane);
+      if (lane == 0) w.bad = bad_k;
+      __syncwarp();
+    }
     if (own) {
       task_store(a, m, w, env, lane);
       if (lane == 0) {
@@ -269,7 +283,8 @@ mjk_task_kernel(const Model* __restrict__ gm, const real* __restrict__ hull, con
         if (orow) for (int k = 0; k < kObs; ++k) orow[k] = obs[k];
         if (mode == 0) {
           bool ok;
-          const double rew = kitchen_reward(obs, w.mocap_pos, a.sites + (size_t)env * kSites * 3, &ok);
+          double rew = kitchen_reward(obs, w.mocap_pos, a.sites + (size_t)env * kSites * 3, &ok);
+          if (failed) { rew = 0.0; ok = false; }
           reward_out[env] = rew;
           if (success_out) success_out[env] = ok;
           const unsigned st = a.steps_since_reset[env] + 1;  // PersistentStateWrapper.step (persistent_state_wrapper.py:22-31)

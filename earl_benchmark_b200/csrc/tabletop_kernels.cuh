@@ -301,6 +301,67 @@ __global__ void __launch_bounds__(kTTBlock, MINB) tabletop_step_kernel(const Tab
   }
 }
 
+// ------------------------------------------------------------------------------------------ tile kernel
+// The same FAST step (sparse reward, fp32 state, no lifelong / auto-reset / eval-stats) as ONE 256-env TILE PER CTA:
+// not persistent, so the grid is N / 256 independent blocks that the hardware scheduler spreads over the 148 SMs as
+// they finish (no tail imbalance, 8 CTAs resident per SM).  State (float4 qpos, uint2 meta) moves as fully coalesced 16 /
+// 8-byte accesses; the tile's 3 KB of row-major actions and 12 KB of row-major observations are staged through shared
+// memory so every global access is a contiguous float4 (observation slot 3*t + j: conflict-free for 16-byte accesses,
+// gcd(3, 8) = 1).  This is the design that reached 0.98 of the HBM copy peak on the three-object task (csrc/earl_tt3.cu);
+// it replaces the cp.async.bulk pipeline (0.93-0.95) and the persistent LSU kernel (0.87-0.88) above ~3M envs, where
+// nothing is L2-resident.
+__global__ void __launch_bounds__(kTTBlock) tabletop_step_tile_kernel(const __grid_constant__ TabletopParams p) {
+  __shared__ float4 s_obs[kTTBlock * 3];
+  __shared__ float4 s_act4[kTTBlock * kTTAct / 4];
+  float* s_act = reinterpret_cast<float*>(s_act4);
+  const int t = threadIdx.x;
+  const int base = p.first + blockIdx.x * kTTBlock;
+  const int i = base + t;
+  const int rows = min(kTTBlock, p.n - base);
+  const bool wide = p.features & kWide;
+  pdl_wait_prior_grid();
+  {
+    const float* asrc = p.actions + (size_t)base * kTTAct;
+    if ((reinterpret_cast<uintptr_t>(asrc) & 15u) == 0) {
+      const float4* src = reinterpret_cast<const float4*>(asrc);
+      const int full = rows * kTTAct / 4;
+      if (t < full) s_act4[t] = __ldcs(src + t);
+      const int rem = rows * kTTAct - full * 4;
+      if (t < rem) s_act[full * 4 + t] = asrc[full * 4 + t];
+    } else {
+      for (int k = t; k < rows * kTTAct; k += kTTBlock) s_act[k] = asrc[k];
+    }
+  }
+  __syncthreads();
+  if (i < p.n) {
+    TTState s;
+    uint32_t steps;
+    tt_load_state<false>(p, i, s, steps);
+    const uint32_t gi = (s.flags & kGoalMask) >> kGoalShift;
+    const float4 g0 = __ldg(p.goal32 + 2 * gi), g1 = __ldg(p.goal32 + 2 * gi + 1);
+    tt_move(s, s_act[kTTAct * t], s_act[kTTAct * t + 1], s_act[kTTAct * t + 2], p);
+    const float4 pos32 = make_float4(__double2float_rn(s.fx), __double2float_rn(s.fy), __double2float_rn(s.mx),
+                                     __double2float_rn(s.my));
+    const bool succ = tt_success(pos32, g0, wide, p.success_sq);
+    steps = steps == 0xffffffffu ? steps : steps + 1u;   // PersistentStateWrapper.step (persistent_state_wrapper.py:25-29)
+    tt_store_state<false>(p, i, s, pos32, steps);
+    __stcs(p.reward + i, succ ? 1.f : 0.f);
+    p.done[i] = (unsigned long long)steps >= p.horizon ? 1 : 0;
+    if (p.success) p.success[i] = succ ? 1 : 0;
+    const float att = (s.flags & kAttached) ? 0.f : -1.f;
+    s_obs[3 * t] = pos32;                                  // tabletop_manipulation.py:55-60
+    s_obs[3 * t + 1] = make_float4(att, att, g0.x, g0.y);
+    s_obs[3 * t + 2] = make_float4(g0.z, g0.w, g1.x, g1.y);
+  }
+  __syncthreads();
+  float4* dst = reinterpret_cast<float4*>(p.obs + (size_t)base * kTTObs);
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const int idx = t + kTTBlock * k;
+    if (idx < rows * 3) __stcs(dst + idx, s_obs[idx]);
+  }
+}
+
 // ------------------------------------------------------------------------------------------ TMA pipeline
 // Same step, restructured around the Blackwell/Hopper bulk-copy engine (cp.async.bulk, SASS UBLKCP):
 // a persistent CTA walks its tiles of kTile envs through an S-stage shared-memory ring.  One elected

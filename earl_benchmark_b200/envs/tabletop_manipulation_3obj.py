@@ -75,7 +75,7 @@ class TabletopManipulation:
         self._np_random = rng.NumpyLegacyRandom(self._seed & 0xFFFFFFFF)
         self._obs = self._reward = self._done = self._success = None
         self._host_bufs = None
-        self._host_mode = bool(host_io)   # numpy in / numpy out (set by host_io=True or by the first numpy step)
+        self._host_mode = bool(host_io)   # host_io=True: reset() returns numpy like the numpy-driven step()
 
     def _configure(self, episode_horizon=None, lifelong=None, goal_change_frequency=None):
         if self._handle is not None:
@@ -221,7 +221,6 @@ class TabletopManipulation:
         until the step after next (two alternating pinned output sets, envs/_hostio.py)."""
         if self._host_bufs is None:
             self._host_bufs = HostBuffers(self.num_envs, ACT_DIM, OBS_DIM)
-        self._host_mode = True
         hb = self._host_bufs
         src = hb.stage(action)
         ho, hr, hd, hs = hb.next_outputs()

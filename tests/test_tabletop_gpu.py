@@ -459,3 +459,97 @@ def test_config1_full_reset_free_horizon():
         dragged += int((orc.attached != 0).sum())
     assert bool(d2.all()) and dragged > steps                     # the attach / drag path was busy
     assert np.array_equal(train.get_state()["qpos"], orc.qpos)    # fp64 state after 200,000 steps, bit for bit
+
+
+# ---------------------------------------------------------------------------------------- round 2: kernel variants, host path
+
+@pytest.mark.parametrize("variant", ["0", "3", "5", "6"])
+@pytest.mark.parametrize("n", [255, 4099, 70001])
+def test_every_step_kernel_variant_vs_oracle(monkeypatch, variant, n):
+    """The persistent LSU kernel (0, 6), the cp.async.bulk pipeline (3) and the one-tile-per-CTA kernel (5, the default above
+    3M envs) are the same arithmetic: ragged batches, attach / drag / clip, horizon `done`, host path included -- bit-exact."""
+    monkeypatch.setenv("EARL_TT_VARIANT", variant)
+    steps, horizon = 24, 17
+    env = make(n, horizon, seed=n)
+    orc = TabletopOracle(n, horizon, state_f32=True)
+    orc.reset(goal_row(np_(env.reset())))
+    q = np.tile([0.0, 0.0, 2.5, 0.0], (n, 1))
+    q[::2, 0] = 2.3
+    q = q.astype(np.float32).astype(np.float64)  # representable in the fp32 state
+    env.set_state(qpos=q)
+    orc.qpos[:] = q
+    acts = actions(n, steps, seed=7 + n, grip_bias=0.3)
+    for t in range(steps):
+        if t % 4 == 3:
+            ob, rw, dn, info = env.step(acts[t])                      # host path drives the same kernel per chunk
+            ob, rw, dn, sc = ob, rw, dn, info["success"]
+        else:
+            ob, rw, dn, info = env.step(torch.from_numpy(acts[t]).to(DEV))
+            ob, rw, dn, sc = np_(ob), np_(rw), np_(dn), np_(info["success"])
+        o2, r2, d2, s2 = orc.step(acts[t])
+        assert np.array_equal(ob, o2), t
+        assert np.array_equal(rw.astype(np.float64), r2) and np.array_equal(dn, d2.astype(bool)) and np.array_equal(sc, s2.astype(bool)), t
+    assert (orc.attached != 0).any()
+
+
+@pytest.mark.parametrize("mode", ["lifelong", "auto_reset"])
+def test_chunked_host_path_reads_its_own_goal_stream(monkeypatch, mode):
+    """a chunked host step used the chunk's end as the row stride of goal_stream[R, N], so every chunk but
+    the last read other envs' draws once a goal was drawn inside the step (lifelong swap, auto-reset).  Host path with 4
+    chunks == device path, with goals actually changing."""
+    monkeypatch.setenv("EARL_TT_HOST_CHUNKS", "4")
+    n, steps = 2051, 40
+    if mode == "lifelong":
+        kw = dict(setup_as_lifelong_learning=True, goal_change_frequency=7, train_horizon=10**6)
+    else:
+        kw = dict(auto_reset=True, train_horizon=9)
+    mk = lambda: eb.EARLEnvs("tabletop_manipulation", reward_type="sparse", num_envs=n, device=DEV, seed=3, **kw).get_envs()  # noqa: E731
+    a, b = mk(), mk()
+    a, b = (a, b) if mode == "lifelong" else (a[0], b[0])
+    oa, ob_ = np_(a.reset()), np_(b.reset())
+    assert np.array_equal(oa, ob_)
+    acts = actions(n, steps, seed=21, grip_bias=0.2)
+    goals = set()
+    for t in range(steps):
+        o, r, d, _ = a.step(torch.from_numpy(acts[t]).to(DEV))
+        ho, hr, hd, _ = b.step(acts[t])
+        assert np.array_equal(ho, np_(o)) and np.array_equal(hr, np_(r)) and np.array_equal(hd, np_(d)), t
+        goals |= set(map(tuple, np.unique(ho[:, 8:10], axis=0)))
+    assert len(goals) == 4                                              # all four goals were drawn along the way
+
+
+def test_host_path_outputs_do_not_alias_across_consecutive_steps():
+    """`next_obs, r, d, _ = env.step(a); ...; obs = next_obs` must not see `obs` change under its feet:
+    the arrays a numpy step returns stay valid during the next step (two alternating pinned sets)."""
+    n = 1000
+    env = make(n, 50)
+    env.reset()
+    acts = actions(n, 6, seed=4)
+    obs, _, _, _ = env.step(acts[0])
+    keep = obs.copy()
+    nxt, _, _, _ = env.step(acts[1])
+    assert not np.shares_memory(obs, nxt)
+    assert np.array_equal(obs, keep) and not np.array_equal(obs, nxt)
+    host = make(n, 50, host_io=True)
+    assert isinstance(host.reset(), np.ndarray)                          # numpy-driven env: numpy out of reset() as well
+
+
+def test_host_step_is_ordered_after_a_reset_on_the_callers_stream():
+    """the host step runs on the handle's private non-blocking streams; a reset queued on torch's current
+    stream right before it must be seen.  A long-running kernel is queued first so that an unordered step would win the race."""
+    n = 1 << 18
+    env, ref = make(n, 10**6), make(n, 10**6)
+    acts = actions(n, 3, seed=9, grip_bias=0.5)
+    for e in (env, ref):
+        e.reset()
+        for t in range(2):
+            e.step(torch.from_numpy(acts[t]).to(DEV))
+    big = torch.empty(1 << 28, device=DEV)
+    for _ in range(4):
+        big.normal_()                                                   # ~ms of work on the current stream ...
+    env.reset()                                                          # ... then the reset, not yet executed when step() is called
+    ho, hr, hd, _ = env.step(acts[2])
+    ref.reset()
+    torch.cuda.synchronize()
+    o, r, d, _ = ref.step(torch.from_numpy(acts[2]).to(DEV))
+    assert np.array_equal(ho, np_(o)) and np.array_equal(hd, np_(d))
