@@ -124,6 +124,7 @@ SIGNATURES = [
     ("earl_mj_eval_stats", C.c_int, [_VP, _VP, _VP]),
     ("earl_mj_work_counters", C.c_int, [_VP, _VP]),
     ("earl_mj_launch_count", _I64, [_VP]),
+    ("earl_mj_redo_count", _I64, [_VP]),
     # include/earl_mj_kitchen_b200.h: engine-level entry points of the kitchen capacity set
     ("earl_mjk_engine_create", C.c_int, [_VP, _SZ, C.c_int32, C.POINTER(_VP)]),
     ("earl_mjk_engine_destroy", C.c_int, [_VP]),

@@ -20,3 +20,5 @@
 #define earl_mj_eval_stats earl_mjl_eval_stats
 #define earl_mj_work_counters earl_mjl_work_counters
 #define earl_mj_launch_count earl_mjl_launch_count
+#define earl_mj_redo_pass earl_mjl_redo_pass
+#define earl_mj_redo_count earl_mjl_redo_count

@@ -20,3 +20,5 @@
 #define earl_mj_eval_stats earl_mjs_eval_stats
 #define earl_mj_work_counters earl_mjs_work_counters
 #define earl_mj_launch_count earl_mjs_launch_count
+#define earl_mj_redo_pass earl_mjs_redo_pass
+#define earl_mj_redo_count earl_mjs_redo_count

@@ -82,7 +82,13 @@ constexpr int MAXHIT = 64;  // candidate pairs that survive the broad phase in o
 constexpr int MAXPAIR = 4096; // candidate geom pairs
 constexpr int MAXMG = 64;    // geoms on moving bodies (their world poses are recomputed every substep)
 #else
-#if defined(MJ_CAPSET_LARGE)
+#if defined(MJ_CAPSET_XL)
+// "extra large": only used by the redo pass that re-steps the few environments whose substep overflowed the primary set
+// (peg wedged in the block, gripper jammed between handle and door: > 24 contacts or > 96 rows)
+constexpr int MAXEFC = 224; // constraint rows
+constexpr int MAXCON = 56;  // contacts
+constexpr int MAXHIT = 72;  // candidate pairs that survive the broad phase in one substep
+#elif defined(MJ_CAPSET_LARGE)
 constexpr int MAXEFC = 96;  // constraint rows
 constexpr int MAXCON = 24;  // contacts
 constexpr int MAXHIT = 32;  // candidate pairs that survive the broad phase in one substep

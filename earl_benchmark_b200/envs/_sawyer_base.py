@@ -240,9 +240,11 @@ class SawyerBatchedEnv:
         self._ensure()
         out = np.zeros(7, np.uint64)
         _lib.check(_lib.lib().earl_mj_work_counters(self._handle, out.ctypes.data))
-        return dict(zip(("env_steps", "substeps", "newton_iterations", "constraint_rows", "contacts", "bad_states",
-                         "overflow_states"),
-                        (int(x) for x in out)))
+        d = dict(zip(("env_steps", "substeps", "newton_iterations", "constraint_rows", "contacts", "bad_states",
+                      "overflow_states"),
+                     (int(x) for x in out)))
+        d["redone_states"] = int(_lib.lib().earl_mj_redo_count(self._handle))   # re-stepped by the extra-large capacity set
+        return d
 
     @property
     def launch_count(self):

@@ -112,6 +112,11 @@ EARL_API int earl_mj_eval_stats(earl_mj_handle* h, double* out4_dev, void* strea
  * -- dropped work) }. */
 EARL_API int earl_mj_work_counters(earl_mj_handle* h, uint64_t* out7_host);
 EARL_API int64_t earl_mj_launch_count(const earl_mj_handle* h);
+/* env-steps whose substep exceeded the handle's fixed capacities and were therefore re-stepped, from their untouched
+ * pre-step record, by the extra-large capacity set (56 contacts / 224 rows) launched after every step kernel; they are
+ * NOT counted in overflow_states (that counter now only sees steps that overflow the extra-large set as well).
+ * EARL_MJ_REDO=0 at creation restores round 1's drop-and-count behaviour.  -1 on error. */
+EARL_API int64_t earl_mj_redo_count(earl_mj_handle* h);
 
 #ifdef __cplusplus
 }

@@ -100,3 +100,43 @@ def test_task_runs_and_contacts_move_the_slide_cabinet(model):
         assert r < 0 and s is False
         out.append((e.qpos.copy(), ob.copy(), r))
     assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1]) and out[0][2] == out[1][2]
+
+
+def test_kitchen_known_answers_from_reference_held_constants():
+    """What the reference itself holds about the kitchen, pushed through the compiled model: no
+    trajectory ships, so these are state-level pins of the MJCF compile + forward kinematics + the (pinned) task logic.
+      * `midpoint_pos` (-0.440, 0.1, 2.226), where reset_model parks the mocap (kitchen_multitask_v0.py:46,145-148): the
+        end-effector site at INIT_QPOS sits within 2.5 cm of it in x / y (the authors' own hand-picked pair of constants);
+      * the goal state (ENV/kitchen.py:28-52) scores exactly 8.0 (eight components done, no distance, no reaching term) and is
+        successful; each of the six initial configurations (:57-85) is unsuccessful... unless within 0.3, leaves exactly
+        two components to do, scores 6 - 10 ||obj - goal|| - 0.5 ||mocap - site(first unfinished)|| with the site taken from the
+        compiled model's kinematics, and that site is the one the reference's table names for that component;
+      * site layout the assets fix: the four knob sites form the 0.123 x 0.114 grid of oven_chain.xml."""
+    from earl_benchmark_b200.envs import kitchen
+    from oracle import kitchen_logic as KL
+    from oracle.engine import Engine
+    m = Model.load(kitchen.MODEL_PATH)
+    e = Engine(m)
+
+    def sites_at(q):
+        e.reset()
+        e.qpos[:] = q
+        e.forward()
+        return {s: e.site_xpos(s) for s in m.names["site"]}
+
+    s0 = sites_at(KL.INIT_QPOS)
+    assert np.abs(s0["end_effector"][:2] - KL.MIDPOINT[:2]).max() < 0.025
+    k = [s0[f"knob{i}_site"] for i in (1, 2, 3, 4)]
+    assert np.allclose(k[0] - k[1], [0.123, 0, 0], atol=1e-9) and np.allclose(k[2] - k[0], [0, 0, 0.114], atol=1e-9)
+    logic = KL.KitchenLogic()
+    goal_obs = np.concatenate([KL.GOAL, KL.GOAL])
+    assert logic.reward(goal_obs, KL.MIDPOINT, sites_at(KL.GOAL)) == 8.0 and logic.success(goal_obs)
+    for row in KL.ALL_PAIRS:
+        q = np.concatenate([KL.INIT_QPOS[:9], row[9:]])
+        obs = np.concatenate([q, KL.GOAL])
+        todo = [key for key, idx in KL.COMPONENTS if np.linalg.norm(obs[np.array(idx)] - obs[np.array(idx) + 23]) >= len(idx) * 0.01]
+        assert len(todo) == 2
+        st = sites_at(q)
+        expect = 6 - 10 * np.linalg.norm(obs[9:23] - KL.GOAL[9:23]) - 0.5 * np.linalg.norm(KL.MIDPOINT - st[KL.TASK_SITE[todo[0]]])
+        assert abs(logic.reward(obs, KL.MIDPOINT, st) - expect) < 1e-12
+        assert logic.success(obs) == (np.linalg.norm(obs[9:23] - KL.GOAL[9:23]) <= 0.3)

@@ -130,3 +130,33 @@ def test_dense_reward_matches_checker(oracle):
             rmax, rmin = max(rmax, r_ref), min(rmin, r_ref)
     print("peg dense reward: max |device - checker| %.2e over rewards in [%.3f, %.3f]" % (worst, rmin, rmax))
     assert worst < 2e-3 and rmax > rmin + 0.01
+
+
+def test_capacity_overflow_is_redone_by_the_extra_large_set_not_dropped(monkeypatch):
+    """a substep with more contacts / rows than the handle's fixed capacities used to DROP the excess
+    (counted, but that env had left the parity claim).  Now such an env is not stored by the step kernel; the extra-large
+    set (56 contacts / 224 rows) re-steps it from its untouched pre-step record in a second, tiny launch.  Random-action
+    rollout of the peg task on the SMALL set (16 contacts / 64 rows: ~1 % of the env steps overflow) against the same
+    rollout on the LARGE set: identical trajectories, overflow_states == 0 on both, and the redo pass did real work."""
+    n, steps = 4096, 160
+    acts = np.random.RandomState(5).uniform(-1, 1, (steps, n, 4)).astype(np.float32)
+    acts[:, :, 2] -= 0.35                                  # bias the hands down onto the peg / table: more contacts
+
+    def run(capset, redo="1"):
+        monkeypatch.setenv("EARL_MJ_CAPSET", capset)
+        monkeypatch.setenv("EARL_MJ_REDO", redo)
+        env = sawyer_peg.SawyerPegV2(reward_type="sparse", num_envs=n, device="cuda:0", seed=1)
+        env.reset()
+        for t in range(steps):
+            o, r, d, _ = env.step(torch.from_numpy(acts[t]).cuda())
+        return o.cpu().numpy().copy(), env.get_state(), env.work_counters()
+
+    o_s, st_s, wc_s = run("small")
+    o_l, st_l, wc_l = run("large")
+    _, _, wc_drop = run("small", redo="0")
+    assert wc_drop["overflow_states"] > 50 and wc_drop["redone_states"] == 0          # round 1's behaviour: dropped work
+    assert wc_s["overflow_states"] == 0 and wc_l["overflow_states"] == 0 and wc_s["bad_states"] == 0
+    assert wc_s["redone_states"] > 50 and wc_s["redone_states"] >= wc_l["redone_states"]
+    # same physics whichever set did the work: the capacities only size the workspace
+    dq = np.abs(st_s["qpos"] - st_l["qpos"]).max(axis=1)
+    assert np.median(dq) == 0.0 and (dq < 1e-4).mean() > 0.99, (np.median(dq), (dq < 1e-4).mean(), dq.max())

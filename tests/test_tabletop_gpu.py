@@ -461,6 +461,56 @@ def test_config1_full_reset_free_horizon():
     assert np.array_equal(train.get_state()["qpos"], orc.qpos)    # fp64 state after 200,000 steps, bit for bit
 
 
+def test_f32_state_against_the_fp64_reference_over_the_benchmarked_horizon():
+    """every bench number runs with the state STORED as fp32 (the 113-B layout) while the reference keeps
+    fp64 qpos.  One step from an fp32-representable state is bit-exact, but over the benchmarked 200,000-step reset-free
+    horizon an attach decision (||fist - mug|| < 0.4) or a success test can flip on a 1-ulp state difference and the two
+    trajectories then part for good.  Measured here on 2,048 envs x 200,000 random-action steps (gripper closing half of the
+    time, so the mug is grabbed, dragged and dropped all along): the fraction of envs whose attached-flag or sparse-reward
+    SEQUENCE ever differs from the fp64 checker's, the first step at which that happens, and the state error of the envs
+    that never diverged.  Decision flips are rare but real -- which is why `state_dtype='float64'` exists and is the mode the
+    bit-exact claims are made for (test_config1_full_reset_free_horizon)."""
+    n, steps, chunk = 2048, 200000, 2000
+    train, _ = eb.EARLEnvs("tabletop_manipulation", reward_type="sparse", num_envs=n, device=DEV, seed=0).get_envs()   # float32 state
+    o0 = np_(train.reset())
+    orc = TabletopOracle(n, steps, state_f32=False)
+    orc.reset(goal_row(o0))
+    rs = np.random.RandomState(123)
+    obs = torch.empty((chunk, n, 12), device=DEV)
+    rew = torch.empty((chunk, n), device=DEV)
+    done = torch.empty((chunk, n), dtype=torch.uint8, device=DEV)
+    diverged_at = np.full(n, -1, np.int64)
+    attached_steps = 0
+    for c in range(steps // chunk):
+        # actions of a noisy mug-seeking policy driven by the CHECKER's state, so that the fist keeps hovering around the
+        # 0.4 attach radius instead of random-walking away from the mug (1.5 % attached under uniform actions)
+        acts = np.empty((chunk, n, 3), np.float32)
+        ref_att, ref_rew = np.empty((chunk, n), np.float32), np.empty((chunk, n))
+        for t in range(chunk):
+            to_mug = orc.qpos[:, 2:4] - orc.qpos[:, 0:2]
+            to_mug /= np.maximum(np.linalg.norm(to_mug, axis=1, keepdims=True), 1e-9)
+            a = rs.uniform(-1, 1, (n, 3))
+            a[:, :2] += 0.35 * to_mug
+            acts[t] = a.astype(np.float32)
+            o2, r2, _, _ = orc.step(acts[t])
+            ref_att[t], ref_rew[t] = o2[:, 4], r2
+        train.rollout_into(torch.from_numpy(acts).to(DEV), chunk, obs, rew, done)
+        bad = (np_(obs[:, :, 4]) != ref_att) | (np_(rew).astype(np.float64) != ref_rew)       # attached flag, sparse reward
+        first_bad = np.where(bad.any(0), bad.argmax(0) + c * chunk, -1)
+        new = (first_bad >= 0) & (diverged_at < 0)
+        diverged_at[new] = first_bad[new]
+        attached_steps += int((ref_att == 0).sum())
+    same = diverged_at < 0
+    err = np.abs(train.get_state()["qpos"][same] - orc.qpos[same]).max() if same.any() else 0.0
+    frac = 1.0 - same.mean()
+    first = int(diverged_at[~same].min()) if (~same).any() else -1
+    print(f"fp32 state vs fp64 reference, {n} envs x {steps} steps: {100 * frac:.2f} % of the envs diverge in their attach / reward "
+          f"sequence (first at step {first}); max |dqpos| of the others {err:.2e}; attached env-steps {attached_steps}")
+    assert attached_steps > 0.05 * n * steps                      # the decisions were exercised all along
+    assert err < 1e-4                                             # north_star's one-step bar holds over the whole horizon for those
+    assert frac < 0.5, frac                                       # reported, not hidden: see the printed line / DESIGN.md 3
+
+
 # ---------------------------------------------------------------------------------------- round 2: kernel variants, host path
 
 @pytest.mark.parametrize("variant", ["0", "3", "5", "6"])
