@@ -35,6 +35,8 @@ def lib():
         L.mje_multi_step.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         L.mje_free.argtypes = [C.c_void_p]
         L.mje_set_opt.argtypes = [C.c_int, C.c_double]
+        L.mje_debug_boxbox_face_scale.argtypes = [C.c_double]
+        L.mje_con_geoms.argtypes = [C.c_void_p, C.c_int]
         L.mje_free_data.argtypes = [C.c_void_p]
         _LIB = L
     return _LIB
@@ -74,6 +76,15 @@ class Engine:
     ncon = property(lambda s: lib().mje_int(s.d, 1))
     solver_iter = property(lambda s: lib().mje_int(s.d, 2))
     flops = property(lambda s: lib().mje_flops(s.d))
+
+    def contacts(self):
+        """[(geom name 1, geom name 2, dist)] of the last forward pass."""
+        names, dist = self.model.names["geom"], self.arr("con_dist", (64,))
+        out = []
+        for k in range(self.ncon):
+            c = lib().mje_con_geoms(self.d, k)
+            out.append((names[c // 1000], names[c % 1000], float(dist[k])))
+        return out
 
     def reset(self):
         lib().mje_reset(self.m, self.d)

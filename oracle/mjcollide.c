@@ -75,6 +75,10 @@ static int clip_poly(double (*poly)[3], int n, const double *pn, double pd, doub
   return m;
 }
 
+/* MuJoCo 2.1.0 reports HALF of the vertex-below-face depth as the distance of a box-box face contact: pinned by the peg
+ * landing at the start of every shipped peg episode (16 nm over 26 env steps; 0.87 mm with the full depth). */
+double g_boxbox_face_scale = 0.5;
+void mje_debug_boxbox_face_scale(double v) { g_boxbox_face_scale = v; }
 static int box_box(const double *p1, const double *R1, const double *s1, const double *p2, const double *R2, const double *s2,
                    double margin, RawCon *out) {
   double A[3][3], B[3][3], pp[3], pA[3], pB[3], Rm[3][3], Q[3][3];
@@ -181,7 +185,7 @@ static int box_box(const double *p1, const double *R1, const double *s1, const d
     if (dup) continue;
     for (int k = 0; k < 3; ++k) out[nc].pos[k] = poly[v][k] + 0.5 * depth * n[k];
     memcpy(out[nc].normal, nrm, sizeof nrm);
-    out[nc].dist = -depth;
+    out[nc].dist = -(g_boxbox_face_scale) * depth;
     ++nc;
   }
   return nc;
@@ -614,7 +618,15 @@ void mje_collision(const mjModelF *m, mjDataF *d) {
 void mje_body_jac(const mjModelF *m, const mjDataF *d, int b, const double *pt, double jp[3][MJ_MAXV], double jr[3][MJ_MAXV]);
 void mje_finish_row(const mjModelF *m, mjDataF *d, int i, const double *solref, const double *solimp, double margin, double diag);
 
+extern int mje_row_is_contact;
+int mje_contact_rows_impl(const mjModelF *m, mjDataF *d, int row);
 int mje_contact_rows(const mjModelF *m, mjDataF *d, int row) {
+  mje_row_is_contact = 1;
+  int r = mje_contact_rows_impl(m, d, row);
+  mje_row_is_contact = 0;
+  return r;
+}
+int mje_contact_rows_impl(const mjModelF *m, mjDataF *d, int row) {
   static double jp1[3][MJ_MAXV], jr1[3][MJ_MAXV], jp2[3][MJ_MAXV], jr2[3][MJ_MAXV];
   int nv = m->nv;
   for (int c = 0; c < d->ncon; ++c) {

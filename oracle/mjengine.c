@@ -400,11 +400,13 @@ static double impedance(const double *solimp, double pos, double margin) {
 double mje_opt[16];
 void mje_set_opt(int i, double v) { if (i >= 0 && i < 16) mje_opt[i] = v; }
 
+int mje_row_is_contact = 0;
 static double mje_imp_pos = -1; /* >= 0: violation used for the impedance instead of the row's own (vector residuals) */
 /* fill aref / R / D of row i from (solref, solimp, pos, margin, vel, diagApprox); mj_makeImpedance */
 void mje_finish_row(const mjModelF *m, mjDataF *d, int i, const double *solref, const double *solimp, double margin, double diag) {
   double vel = 0;
   for (int k = 0; k < m->nv; ++k) vel += d->efc_J[i][k] * d->qvel[k];
+  if (mje_row_is_contact && mje_opt[7] > 0) d->efc_pos[i] *= mje_opt[7]; /* experiment: contact distance scale */
   double imp = mje_imp_pos >= 0 ? impedance(solimp, mje_imp_pos, margin) : impedance(solimp, d->efc_pos[i], margin);
   double dmax = solimp[1] < MJMINIMP ? MJMINIMP : (solimp[1] > MJMAXIMP ? MJMAXIMP : solimp[1]);
   double k, b;
@@ -423,6 +425,12 @@ void mje_finish_row(const mjModelF *m, mjDataF *d, int i, const double *solref, 
   d->efc_R[i] = R;
   d->efc_D[i] = 1 / R;
   d->efc_aref[i] = -b * vel - k * imp * (d->efc_pos[i] - margin);
+  if (mje_row_is_contact) { /* experiment knobs for contact rows: [4] stiffness scale, [5] damping scale, [6] R scale */
+    const double ks = mje_opt[4] > 0 ? mje_opt[4] : 1.0, bs = mje_opt[5] > 0 ? mje_opt[5] : 1.0, rs = mje_opt[6] > 0 ? mje_opt[6] : 1.0;
+    d->efc_aref[i] = -bs * b * vel - ks * k * imp * (d->efc_pos[i] - margin);
+    d->efc_R[i] = R * rs;
+    d->efc_D[i] = 1 / d->efc_R[i];
+  }
 }
 
 void mje_collision(const mjModelF *m, mjDataF *d);
@@ -457,6 +465,7 @@ void mje_make_constraints(const mjModelF *m, mjDataF *d) {
       mulquat(q2, quat1, ax);
       mulquat(q3, q2, quat);
       for (int k = 0; k < 3; ++k) d->efc_J[r + 3 + k][c] = (mje_opt[2] > 0 ? mje_opt[2] : 0.5) * q3[1 + k];
+      if (mje_opt[3] == 1) for (int k = 0; k < 3; ++k) d->efc_J[r + 3 + k][c] = -(mje_opt[2] > 0 ? mje_opt[2] : 1.0) * jr[k][c]; /* experiment: uncorrected world-frame angular velocity difference */
     }
     d->flops += (long long)nv * 60 + 120;
     /* vector residual: all six rows share the impedance of its Euclidean norm (getposdim) */
@@ -819,4 +828,5 @@ int mje_int(const mjDataF *d, int what) {
   return -1;
 }
 long long mje_flops(const mjDataF *d) { return d->flops; }
+int mje_con_geoms(const mjDataF *d, int k) { return k < d->ncon ? d->con_geom1[k] * 1000 + d->con_geom2[k] : -1; }
 void mje_multi_step(const mjModelF *m, mjDataF *d, int n) { for (int i = 0; i < n; ++i) mje_step(m, d); }

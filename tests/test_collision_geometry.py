@@ -55,8 +55,9 @@ def test_box_box_kernel_vs_checker_and_first_principles():
         for c in range(n64):
             pos, nrm, dist = o64[c, :3], o64[c, 3:6], o64[c, 6]
             assert abs(np.linalg.norm(nrm) - 1) < 1e-9 and nrm @ (p2 - p1) > -1e-9 and dist < margin
-            # the contact point sits halfway between the two surfaces: within |dist|/2 (+ margin) of both boxes
-            tol = 0.5 * abs(dist) + margin + 1e-7
+            # the contact point sits halfway between the two surfaces: within half the penetration (+ margin) of both boxes;
+            # a face contact reports dist = -depth / 2 (MuJoCo 2.1.0, pinned by the peg landing), an edge contact -depth
+            tol = abs(dist) + margin + 1e-7
             assert _inside(pos, p1, R1, s1, tol) and _inside(pos, p2, R2, s2, tol)
         if n32 == n64:
             d32, d64 = np.sort(o32[:n32, 6]), np.sort(o64[:n64, 6])
