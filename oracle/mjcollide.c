@@ -607,6 +607,14 @@ void mje_collision(const mjModelF *m, mjDataF *d) {
         d->con_friction[k][3] = d->con_friction[k][4] = f[2];
         double mix = m->geom_solmix[ga] / (m->geom_solmix[ga] + m->geom_solmix[gb]);
         for (int q = 0; q < 2; ++q) d->con_solref[k][q] = mix * m->geom_solref[2 * ga + q] + (1 - mix) * m->geom_solref[2 * gb + q];
+        { /* experiment: other mixing rules for the time constant */
+          extern double mje_opt[16];
+          double t1 = m->geom_solref[2 * ga], t2 = m->geom_solref[2 * gb];
+          if (mje_opt[8] == 1) d->con_solref[k][0] = 1.0 / (mix / t1 + (1 - mix) / t2);
+          else if (mje_opt[8] == 2) d->con_solref[k][0] = t1 < t2 ? t1 : t2;
+          else if (mje_opt[8] == 3) d->con_solref[k][0] = sqrt(t1 * t2);
+          else if (mje_opt[8] == 4) d->con_solref[k][0] = t1 > t2 ? t1 : t2;
+        }
         for (int q = 0; q < 5; ++q) d->con_solimp[k][q] = mix * m->geom_solimp[5 * ga + q] + (1 - mix) * m->geom_solimp[5 * gb + q];
         d->con_margin[k] = margin - gap; /* includemargin */
       }

@@ -160,3 +160,57 @@ def test_capacity_overflow_is_redone_by_the_extra_large_set_not_dropped(monkeypa
     # same physics whichever set did the work: the capacities only size the workspace
     dq = np.abs(st_s["qpos"] - st_l["qpos"]).max(axis=1)
     assert np.median(dq) == 0.0 and (dq < 1e-4).mean() > 0.99, (np.median(dq), (dq < 1e-4).mean(), dq.max())
+
+
+def test_peg_demonstrations_replayed_on_the_device_by_episode():
+    """All 30 shipped peg episodes (10 forward: reach, grasp, lift, insert; 20 reverse: pull the peg out of the hole and put
+    it down) replayed open loop ON THE DEVICE, one environment per episode in one batch, judged by episode against the
+    RECORDING (the reference's own MuJoCo run) and reported next to the all-zeros predictor:
+      * free space: hand and gripper within 2e-5 m of the recording for the first 8 steps of every episode (fp32 engine; the
+        fp64 checker is within 1e-7 m), the peg landing included (object within 2e-5 m);
+      * forward episodes: all reach success, at the recorded step +-3;
+      * per-step sparse-reward agreement over the 1,815 transitions >= 0.99 (north-star bar) and above the all-zeros predictor."""
+    from earl_benchmark_b200 import demos
+    eps = []
+    for which in ("forward", "reverse"):
+        d = demos.load("sawyer_peg", which)
+        for s, en in demos.episodes(d):
+            eps.append(dict(which=which, obs0=d["observations"][s], act=d["actions"][s:en], rew=d["rewards"].ravel()[s:en],
+                            nobs=d["next_observations"][s:en]))
+    n, T = len(eps), max(len(e["act"]) for e in eps)
+    assert n == 30
+    env = sawyer_peg.SawyerPegV2(reward_type="sparse", num_envs=n, device="cuda:0")
+    env.reset_goal(eps[0]["obs0"][7:14])
+    for i, e in enumerate(eps):                           # per-episode goal (the reverse episodes have 11 distinct ones)
+        env._goal_rows[i] = env._goal_row(e["obs0"][7:14])
+    env.reset(peg_pos=np.stack([demos.peg_position_from_obs(e["obs0"]) for e in eps]).astype(np.float64))
+    actions = np.zeros((T, n, 4), np.float32)
+    for i, e in enumerate(eps):
+        actions[:len(e["act"]), i] = e["act"]
+    dev = np.zeros((T, n, 14), np.float32)
+    for t in range(T):
+        dev[t] = env.step(torch.from_numpy(actions[t]).cuda())[0].cpu().numpy()
+    wc = env.work_counters()
+    assert wc["bad_states"] == 0 and wc["overflow_states"] == 0
+    total = mism = zeros = 0
+    succ = {"forward": 0, "reverse": 0}
+    within3 = {"forward": 0, "reverse": 0}
+    for i, e in enumerate(eps):
+        L = len(e["act"])
+        goal = e["obs0"][11:14]
+        r = (np.linalg.norm(dev[:L, i, 4:7] - goal, axis=1) <= 0.05).astype(np.float32)
+        total += L
+        mism += int((r != e["rew"]).sum())
+        zeros += int((e["rew"] != 0).sum())
+        first, demo_first = np.nonzero(r)[0], int(np.nonzero(e["rew"])[0][0])
+        ok = len(first) > 0
+        succ[e["which"]] += ok
+        within3[e["which"]] += ok and abs(int(first[0]) - demo_first) <= 3
+        if e["which"] == "forward":
+            assert np.abs(dev[:8, i, :7] - e["nobs"][:8, :7]).max() < 2e-5, i
+    print(f"peg demos on the device: success {succ}, within +-3 {within3}, per-step agreement {1 - mism / total:.4f}, "
+          f"all-zeros predictor {1 - zeros / total:.4f}")
+    assert total == 1815
+    assert succ["forward"] == 10 and within3["forward"] == 10
+    assert succ["reverse"] >= 10
+    assert 1 - mism / total >= 0.99 > 1 - zeros / total
