@@ -37,6 +37,7 @@ def lib():
         L.mje_set_opt.argtypes = [C.c_int, C.c_double]
         L.mje_debug_boxbox_face_scale.argtypes = [C.c_double]
         L.mje_con_geoms.argtypes = [C.c_void_p, C.c_int]
+        L.mje_debug_fix_normal.argtypes = [C.c_int]
         L.mje_free_data.argtypes = [C.c_void_p]
         _LIB = L
     return _LIB

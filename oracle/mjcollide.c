@@ -526,6 +526,45 @@ static int capsule_capsule(const mjModelF *m, const mjDataF *d, int g1, int g2, 
 static int g_round_poses = 0;
 void mje_debug_round_poses(int on) { g_round_poses = on; }
 
+
+/* MuJoCo engine_collision_convex.c: mjc_fixNormal.  After portal refinement the contact normal of a pair that involves a
+ * capsule or a cylinder (spheres / ellipsoids do not occur in these scenes) is replaced by the primitive's own surface
+ * normal at the contact position: radial from the axis for a cylinder (unless the point lies within 5 % of a flat cap),
+ * from the nearest point of the segment for a capsule; if both geoms have one, the two are averaged. */
+int g_fix_normal = 1;
+void mje_debug_fix_normal(int on) { g_fix_normal = on; }
+static void fix_normal(const mjModelF *m, const mjDataF *d, int ga, int gb, const double *pos, double *normal) {
+  int g[2] = {ga, gb}, done[2] = {0, 0};
+  double nrm[2][3] = {{0, 0, 0}, {0, 0, 0}};
+  for (int i = 0; i < 2; ++i) {
+    const double *R = d->geom_xmat[g[i]], *c = d->geom_xpos[g[i]], *sz = m->geom_size + 3 * g[i];
+    double rel[3], loc[3];
+    sub3(rel, pos, c);
+    for (int k = 0; k < 3; ++k) loc[k] = R[k] * rel[0] + R[3 + k] * rel[1] + R[6 + k] * rel[2];
+    int t = m->geom_type[g[i]];
+    if (t == GEOM_CYLINDER) {
+      if (fabs(loc[2]) > 0.95 * sz[1]) continue;
+      loc[2] = 0;
+    } else if (t == GEOM_CAPSULE) {
+      if (loc[2] > sz[1]) loc[2] -= sz[1];
+      else if (loc[2] < -sz[1]) loc[2] += sz[1];
+      else loc[2] = 0;
+    } else continue;
+    double l = sqrt(dot3(loc, loc));
+    if (l < 1e-12) continue;
+    for (int k = 0; k < 3; ++k) nrm[i][k] = (R[3 * k] * loc[0] + R[3 * k + 1] * loc[1] + R[3 * k + 2] * loc[2]) / l;
+    done[i] = 1;
+  }
+  double out[3];
+  if (done[0] && done[1]) for (int k = 0; k < 3; ++k) out[k] = nrm[0][k] - nrm[1][k];
+  else if (done[0]) memcpy(out, nrm[0], sizeof out);
+  else if (done[1]) for (int k = 0; k < 3; ++k) out[k] = -nrm[1][k];
+  else return;
+  double l = sqrt(dot3(out, out));
+  if (l < 1e-12) return;
+  for (int k = 0; k < 3; ++k) normal[k] = out[k] / l;
+}
+
 void mje_collision(const mjModelF *m, mjDataF *d) {
   d->ncon = 0;
   g_flops = 0;
@@ -586,6 +625,7 @@ void mje_collision(const mjModelF *m, mjDataF *d) {
           memcpy(rc[0].normal, dir, sizeof dir);
           rc[0].dist = margin - depth;
           n = 1;
+          if (g_fix_normal) fix_normal(m, d, ga, gb, rc[0].pos, rc[0].normal);
         }
       }
       for (int c = 0; c < n && d->ncon < MJ_MAXCON; ++c) {

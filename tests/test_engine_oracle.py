@@ -109,14 +109,16 @@ def test_demonstrations_by_episode_next_to_the_all_zeros_predictor(oracle, peg_o
         set           episodes reaching success   success step within +-3   per-step agreement   all-zeros predictor
         peg forward          10 / 10                     10                      0.9941               0.9854
         peg reverse          12 / 20                     12                      0.9929               0.9823
-        door forward          5 /  5                      0  (5-8 steps EARLY)   0.9165               0.9873
-        door reverse          0 /  5                      0                      0.9929               0.9929
+        door forward          5 /  5                      0  (4-8 steps EARLY)   0.9139               0.9873
+        door reverse          4 /  5                      0  (5-12 steps EARLY)  0.9643               0.9929
 
     PEG: the 99 % bar is met (0.9934 over the 1,815 peg transitions) and the replay beats the null predictor; 22 of 30
     episodes reproduce grasp, lift and insertion / extraction with the success step of the recording.
-    DOOR: free space and first contact are exact (the door angle after the first contact step agrees to 1e-5 rad), then the
-    door moves 10-25 % faster than recorded against the friction of its panel sunk 23 mm into the table, and the grasp of the
-    handle bar in the reverse episodes is lost -- KNOWN GAP, DESIGN.md 8.4.  The assertions keep these numbers honest."""
+    DOOR: free space and first contact are exact (the door angle after the first contact step agrees to 1e-5 rad) and, with
+    MuJoCo's mjc_fixNormal on the cylinder contacts, the gripper grasps the handle and pulls the door open in 4 of the 5
+    reverse episodes (0 of 5 before) -- but the door moves 5-12 % faster than recorded against the friction of its panel sunk
+    23 mm into the table, so every door episode ends 4-12 steps EARLY: KNOWN GAP, DESIGN.md 8.4.  The assertions keep these
+    numbers honest."""
     import demo_eval
     rows = {}
     for name, o, task in (("door", oracle, "sawyer_door"), ("peg", peg_oracle, "sawyer_peg")):
@@ -132,7 +134,7 @@ def test_demonstrations_by_episode_next_to_the_all_zeros_predictor(oracle, peg_o
     assert peg_total >= 0.99, peg_total                                   # north-star bar, peg task
     assert pf["hand_max"] < 0.02 and pr["hand_max"] < 0.007               # the hand stays within 2 cm / 7 mm for whole episodes
     assert df["success"] == 5 and df["hand_max"] < 0.06                   # door closes in every forward episode, early
-    assert dr["success"] == 0                                             # KNOWN GAP: update the table above when this moves
+    assert dr["success"] == 4 and dr["hand_max"] < 0.32                    # KNOWN GAP: update the table above when this moves
 
 
 # ------------------------------------------------------------------------------------------------ sawyer_peg
