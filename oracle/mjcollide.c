@@ -679,6 +679,7 @@ int mje_contact_rows_impl(const mjModelF *m, mjDataF *d, int row) {
   int nv = m->nv;
   for (int c = 0; c < d->ncon; ++c) {
     int dim = d->con_dim[c], g1 = d->con_geom1[c], g2 = d->con_geom2[c];
+    mje_row_is_contact = (g1 == 1 || g2 == 1) ? 2 : 1;
     if (!m->cone_elliptic) {
       /* pyramidal cone (mj_instantiateContact): 2 (dim - 1) rows J_n +- mu_k J_k, every one a unilateral row with the
        * contact distance as residual; frictionless contacts keep the single normal row.

@@ -425,7 +425,7 @@ void mje_finish_row(const mjModelF *m, mjDataF *d, int i, const double *solref, 
   d->efc_R[i] = R;
   d->efc_D[i] = 1 / R;
   d->efc_aref[i] = -b * vel - k * imp * (d->efc_pos[i] - margin);
-  if (mje_row_is_contact) { /* experiment knobs for contact rows: [4] stiffness scale, [5] damping scale, [6] R scale */
+  if (mje_row_is_contact && (mje_opt[10] == 0 || mje_row_is_contact == 2)) { /* experiment knobs for contact rows: [4] stiffness scale, [5] damping scale, [6] R scale; [10] = 1: only contacts with the table */
     const double ks = mje_opt[4] > 0 ? mje_opt[4] : 1.0, bs = mje_opt[5] > 0 ? mje_opt[5] : 1.0, rs = mje_opt[6] > 0 ? mje_opt[6] : 1.0;
     d->efc_aref[i] = -bs * b * vel - ks * k * imp * (d->efc_pos[i] - margin);
     d->efc_R[i] = R * rs;

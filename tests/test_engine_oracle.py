@@ -137,6 +137,31 @@ def test_demonstrations_by_episode_next_to_the_all_zeros_predictor(oracle, peg_o
     assert dr["success"] == 4 and dr["hand_max"] < 0.32                    # KNOWN GAP: update the table above when this moves
 
 
+def test_the_open_door_gap_is_one_scalar_of_one_contact_pair(oracle):
+    """DIAGNOSTIC, not a fix: the only thing between the checker and the ten recorded door episodes is the strength of the
+    friction between the door panel and the table it is sunk into.  Scaling the regulariser R of THAT contact pair alone by
+    0.86 (friction coefficient x 1.16; damping unchanged: a two-parameter fit gives B x 0.996, R x 0.82-0.86) makes all ten
+    episodes reach success, nine of them within +-3 steps of the recording (all five grasp-and-pull episodes at +-1), with hand
+    and handle within 2.5 cm / 2.2 cm (forward) of the recording over whole episodes.  The factor is NOT adopted: nothing in
+    MuJoCo's documented formulas produces it (DESIGN.md 8.4 lists what was excluded), and a fitted constant is what round 1 was
+    rightly criticised for."""
+    import demo_eval
+    from oracle.engine import lib
+    L = lib()
+    try:
+        L.mje_set_opt(10, 1.0)     # experiment knobs apply to contacts with the table only
+        L.mje_set_opt(6, 0.86)     # R scale
+        rows = {w: demo_eval.summarise(_replay(oracle, "sawyer_door", w)) for w in ("forward", "reverse")}
+    finally:
+        L.mje_set_opt(10, 0.0)
+        L.mje_set_opt(6, 0.0)
+        oracle.goal = oracle.GOAL.copy()
+    assert rows["forward"]["success"] == 5 and rows["reverse"]["success"] == 5
+    assert rows["forward"]["within3"] >= 4 and rows["reverse"]["within3"] == 5
+    assert rows["forward"]["hand_max"] < 0.03 and rows["forward"]["obj_max"] < 0.025
+    assert rows["reverse"]["agreement"] > 0.995 > rows["reverse"]["all_zeros"]
+
+
 # ------------------------------------------------------------------------------------------------ sawyer_peg
 @pytest.fixture(scope="module")
 def peg_oracle():
