@@ -160,6 +160,18 @@ class TabletopManipulation:
         if self._handle is not None:
             return
         L = _lib.lib()
+        # the pre-drawn goal stream is a ring of `goal_stream_rows` draws per env: a lifelong run takes
+        # horizon / goal_change_frequency of them (125 with the reference's defaults), so size it from the configuration
+        # instead of letting the cursor wrap silently into a periodic goal sequence
+        if self._lifelong and self._goal_change_frequency > 0 and self._episode_horizon < _NEVER:
+            need = -(-self._episode_horizon // self._goal_change_frequency) + 2
+            if need > self._goal_stream_rows:
+                if need * self._total_envs <= (1 << 28):
+                    self._goal_stream_rows = int(need)
+                else:
+                    import warnings
+                    warnings.warn(f"goal stream of {self._goal_stream_rows} draws per env wraps before the horizon "
+                                  f"({need} needed); pass goal_stream_rows explicitly", RuntimeWarning)
         cfg = _lib.EarlConfig(_lib.ENV_TABLETOP, self.num_envs, self.device.index or 0, self._flags(),
                               self._episode_horizon, self._goal_change_frequency, self._goal_stream_rows, 0)
         blob = self._model_blob()
@@ -268,10 +280,15 @@ class TabletopManipulation:
         self._ensure()
         m = self._mask(mask)
         if init_qpos is None and self._wide_init_distr and not self._reset_at_goal:
-            cnt = self.num_envs if m is None else int(m.sum().item())
             q = np.zeros((self.num_envs, 4))
-            sel = np.ones(self.num_envs, bool) if m is None else m.cpu().numpy().astype(bool)
-            q[sel] = self._wide_init_states(cnt)
+            if m is None:
+                # a full reset of a sharded job draws for ALL envs of the global batch, in env order, and keeps its slice
+                # (like the goal stream and the Sawyer / kitchen resets), so results do not depend on the number of GPUs
+                # (every rank used to draw the same states from its own copy of the stream)
+                q[:] = self._wide_init_states(self._total_envs)[self._env_offset:self._env_offset + self.num_envs]
+            else:
+                sel = m.cpu().numpy().astype(bool)
+                q[sel] = self._wide_init_states(int(sel.sum()))
             init_qpos = q
         iq = None
         if init_qpos is not None:

@@ -603,3 +603,25 @@ def test_host_step_is_ordered_after_a_reset_on_the_callers_stream():
     torch.cuda.synchronize()
     o, r, d, _ = ref.step(torch.from_numpy(acts[2]).to(DEV))
     assert np.array_equal(ho, np_(o)) and np.array_equal(hd, np_(d))
+
+
+def test_wide_init_resets_do_not_depend_on_the_sharding():
+    """with `wide_init_distr` every rank used to draw its initial states from its own copy of the legacy
+    numpy stream, so all shards started identically and differed from the single-GPU run.  Two shards of a 600-env job ==
+    the unsharded job."""
+    n = 600
+    whole = TabletopManipulation(num_envs=n, device=DEV, wide_init_distr=True, reward_type="sparse", seed=5)
+    a = TabletopManipulation(num_envs=n // 2, device=DEV, wide_init_distr=True, reward_type="sparse", seed=5, env_offset=0, total_envs=n)
+    b = TabletopManipulation(num_envs=n // 2, device=DEV, wide_init_distr=True, reward_type="sparse", seed=5, env_offset=n // 2, total_envs=n)
+    ow, oa, ob = np_(whole.reset()), np_(a.reset()), np_(b.reset())
+    assert np.array_equal(ow, np.concatenate([oa, ob]))
+    assert not np.array_equal(oa[:, :4], ob[:, :4])
+
+
+def test_lifelong_goal_stream_covers_the_horizon():
+    """the default lifelong tabletop run takes 50000 / 400 = 125 goal draws per env; a 64-row ring would wrap
+    silently into a periodic sequence.  The ring is sized from the configuration."""
+    env = eb.EARLEnvs("tabletop_manipulation", reward_type="sparse", setup_as_lifelong_learning=True, num_envs=8, device=DEV).get_envs()
+    env.reset()
+    base = env.env.env if hasattr(env.env, "env") else env.env
+    assert base._goal_stream.shape[0] >= 127
