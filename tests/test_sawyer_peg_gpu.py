@@ -168,7 +168,9 @@ def test_peg_demonstrations_replayed_on_the_device_by_episode():
     RECORDING (the reference's own MuJoCo run) and reported next to the all-zeros predictor:
       * free space: hand and gripper within 2e-5 m of the recording for the first 8 steps of every episode (fp32 engine; the
         fp64 checker is within 1e-7 m), the peg landing included (object within 2e-5 m);
-      * forward episodes: all reach success, at the recorded step +-3;
+      * forward episodes: all reach success, at the recorded step +-3; reverse: 12 inside the recording, 18 within +3 steps
+        (the recordings end ON their success step, the replay is 1-3 mm short of the 50 mm radius there and arrives one step
+        later: judged by holding the last action for three more steps);
       * per-step sparse-reward agreement over the 1,815 transitions >= 0.99 (north-star bar) and above the all-zeros predictor."""
     from earl_benchmark_b200 import demos
     eps = []
@@ -184,9 +186,11 @@ def test_peg_demonstrations_replayed_on_the_device_by_episode():
     for i, e in enumerate(eps):                           # per-episode goal (the reverse episodes have 11 distinct ones)
         env._goal_rows[i] = env._goal_row(e["obs0"][7:14])
     env.reset(peg_pos=np.stack([demos.peg_position_from_obs(e["obs0"]) for e in eps]).astype(np.float64))
-    actions = np.zeros((T, n, 4), np.float32)
+    T += 3                                                 # the recordings end ON their success step: "+3" is judged by
+    actions = np.zeros((T, n, 4), np.float32)              # holding each episode's last action for three more steps
     for i, e in enumerate(eps):
         actions[:len(e["act"]), i] = e["act"]
+        actions[len(e["act"]):, i] = e["act"][-1]
     dev = np.zeros((T, n, 14), np.float32)
     for t in range(T):
         dev[t] = env.step(torch.from_numpy(actions[t]).cuda())[0].cpu().numpy()
@@ -202,15 +206,16 @@ def test_peg_demonstrations_replayed_on_the_device_by_episode():
         total += L
         mism += int((r != e["rew"]).sum())
         zeros += int((e["rew"] != 0).sum())
-        first, demo_first = np.nonzero(r)[0], int(np.nonzero(e["rew"])[0][0])
-        ok = len(first) > 0
-        succ[e["which"]] += ok
-        within3[e["which"]] += ok and abs(int(first[0]) - demo_first) <= 3
+        r3 = (np.linalg.norm(dev[:L + 3, i, 4:7] - goal, axis=1) <= 0.05)
+        first, demo_first = np.nonzero(r3)[0], int(np.nonzero(e["rew"])[0][0])
+        succ[e["which"]] += len(np.nonzero(r)[0]) > 0
+        within3[e["which"]] += len(first) > 0 and abs(int(first[0]) - demo_first) <= 3
         if e["which"] == "forward":
             assert np.abs(dev[:8, i, :7] - e["nobs"][:8, :7]).max() < 2e-5, i
     print(f"peg demos on the device: success {succ}, within +-3 {within3}, per-step agreement {1 - mism / total:.4f}, "
           f"all-zeros predictor {1 - zeros / total:.4f}")
     assert total == 1815
     assert succ["forward"] == 10 and within3["forward"] == 10
-    assert succ["reverse"] >= 10
+    assert succ["reverse"] >= 10 and within3["reverse"] >= 16          # checker: 12 and 18 (the other 6 end 1-3 mm short of the
+    assert within3["forward"] + within3["reverse"] >= 26               # 50 mm radius on the last recorded step and get there next step)
     assert 1 - mism / total >= 0.99 > 1 - zeros / total
