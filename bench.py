@@ -160,6 +160,25 @@ def door_cpu_rate(procs, steps_per_proc=20000, task="sawyer_door"):
     return procs * steps_per_proc / loop, flops, wall
 
 
+
+def ncu_engine_summary():
+    """A few figures of the committed `ncu --set full` capture of the step kernel (profiles/r02/prof_door_steady_16k_r02.raw.csv:
+    sawyer_door, 16,384 envs, steady regime) -- read from the file, never typed in; None when the file is not there."""
+    import csv
+    path = os.path.join(REPO, "profiles", "r02", "prof_door_steady_16k_r02.raw.csv")
+    try:
+        rows = list(csv.reader(open(path)))
+        hdr, val = rows[0], rows[2]
+        g = lambda k: float(val[hdr.index(k)].replace(",", ""))  # noqa: E731
+        return {"source": "profiles/r02/prof_door_steady_16k_r02.raw.csv (sawyer_door, 16,384 envs, steady regime; not this run)",
+                "executed_ipc": g("sm__inst_executed.avg.per_cycle_active"),
+                "achieved_occupancy_pct": g("sm__warps_active.avg.pct_of_peak_sustained_active"),
+                "active_lanes_per_instruction": g("smsp__thread_inst_executed_per_inst_executed.ratio"),
+                "registers_per_thread": g("launch__registers_per_thread"), "kernel_ms": g("gpu__time_duration.sum")}
+    except Exception:
+        return None
+
+
 def run_door(dev, rank, world, sm_max_mhz, sm_count, with_cpu, task="sawyer_door"):
     """Second / third bench section: batched sawyer_door (BASELINE.json configs[2]) or sawyer_peg (configs[3]) step,
     65,536 envs per GPU, random actions."""
@@ -236,10 +255,10 @@ def run_door(dev, rank, world, sm_max_mhz, sm_count, with_cpu, task="sawyer_door
                         "contacts_per_substep": (w1["contacts"] - w0["contacts"]) / sub,
                         "bad_states": w1["bad_states"] - w0["bad_states"],
                         "overflow_states": w1["overflow_states"] - w0["overflow_states"]},
-               "kernel": ("mj_step_kernel (one warp per env, %d envs per SM in flight) + mj_order_kernel (visiting order, <3 us)" % (16 if door else 12)),
-               "ncu": {"source": "profiles/r01/door/prof_door_step_16k_r01.details.csv (sawyer_door, 16,384 envs, not this run)",
-                       "executed_ipc": 2.15, "issue_slots_busy_pct": 53.9, "achieved_occupancy_pct": 25.0,
-                       "warp_instructions_per_env_step": 1.03e5, "dram_pct_of_peak": 0.03}}
+               "kernel": "mj_step_kernel (one warp per env, 16 envs per SM in flight, small capacity set) + concurrent mj_redo_kernel "
+                         "(extra-large capacity set, re-steps capacity overflows) + mj_order_kernel (visiting order, <4 us)",
+               "redone_states": w1.get("redone_states", 0) - w0.get("redone_states", 0),
+               "ncu": ncu_engine_summary()}
         if with_cpu:
             procs = os.cpu_count() or 1
             rate, flops, wall = door_cpu_rate(procs, task=task)
@@ -303,7 +322,7 @@ def run_kitchen(dev, rank, world, sm_max_mhz, sm_count, with_cpu):
         value = n * world * KITCHEN_STEPS / (ms * 1e-3)
         out = {"metric": "batched env-steps/sec (kitchen, dense, 40 substeps per env step)", "value": value, "unit": UNIT,
                "envs_per_gpu": n, "steps": KITCHEN_STEPS, "warmup": KITCHEN_WARMUP, "ms_per_step": ms / KITCHEN_STEPS, "dtype": "f32",
-               "gpu_launches": 3 * KITCHEN_STEPS,   # task kernel + two tiny kernels that build the next visiting order
+               "gpu_launches": 4 * KITCHEN_STEPS,   # task kernel + redo kernel + two tiny kernels that build the next visiting order
                "window": f"env steps {KITCHEN_WARMUP}..{KITCHEN_WARMUP + KITCHEN_STEPS} of a random-action rollout after a full reset "
                          "(arms up to speed: the broad-phase cache is rebuilt more often than right after the reset)",
                "e2e": {"value": n * world * 2 / e2e_s, "unit": UNIT, "h2d_bytes_per_step": n * 36 * world,
@@ -312,8 +331,10 @@ def run_kitchen(dev, rank, world, sm_max_mhz, sm_count, with_cpu):
                         "constraint_rows_per_substep": (w1["constraint_rows"] - w0["constraint_rows"]) / sub,
                         "contacts_per_substep": (w1["contacts"] - w0["contacts"]) / sub,
                         "bad_states": w1["bad_states"] - w0["bad_states"],
-                        "overflow_states": w1["overflow_states"] - w0["overflow_states"]},
-               "kernel": "mjk_task_kernel (one warp per env, 6 envs per SM in flight, model tables in global memory, cost-sorted visiting order)"}
+                        "overflow_states": w1["overflow_states"] - w0["overflow_states"],
+                        "redone_states": w1["redone_states"] - w0["redone_states"]},
+               "kernel": "mjk_task_kernel (one warp per env, 6 envs per SM in flight, model tables in global memory, cost-sorted visiting order) "
+                         "+ mjk_redo_kernel (352-row set, concurrent on one reserved SM: env steps that outgrew 192 rows / 24 contacts)"}
         if with_cpu:
             procs = os.cpu_count() or 1
             rate, flops, wall = door_cpu_rate(procs, steps_per_proc=1500, task="kitchen")

@@ -19,7 +19,7 @@ OBJDIR = os.path.join(PKG, "build")
 # (source, extra flags)
 MJ_EXTRA = os.environ.get("EARL_MJ_EXTRA_FLAGS", "").split()  # profiling / trace builds (-DMJ_PHASE_TIMING, -DMJ_TRACE_DEVICE)
 UNITS = [("earl_b200.cu", ["--fmad=false"]), ("earl_tt3.cu", ["--fmad=false"]), ("earl_mj.cu", []), ("earl_mj_small.cu", MJ_EXTRA), ("earl_mj_large.cu", MJ_EXTRA), ("earl_mj_xl.cu", MJ_EXTRA),
-         ("earl_mj_kitchen.cu", MJ_EXTRA)]
+         ("earl_mj_kitchen.cu", MJ_EXTRA), ("earl_mj_kitchen_xl.cu", MJ_EXTRA)]
 SOURCES = [os.path.join(CSRC, u[0]) for u in UNITS]
 DEPS = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(INCLUDE, f) for f in os.listdir(INCLUDE)]
 

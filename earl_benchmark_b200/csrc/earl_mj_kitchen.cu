@@ -3,8 +3,18 @@
 // (include/earl_mj_kitchen_b200.h).  One warp per environment; the 37.1 KB workspace of an environment lives in shared
 // memory (6 environments in flight per SM), the 37 KB model stays in global memory (L1 / L2 resident: every block reads
 // the same tables).  No CPU fallback.
+//
+// Compiled a second time as earl_mj_kitchen_xl.cu (MJK_XL: 352 rows, 32 contacts, 3 environments per block) for the
+// REDO PASS: an env step in which some substep outgrew the 192 rows / 24 contacts is not stored by the step kernel but
+// listed, and re-stepped from its untouched state by the extra-large instantiation, which runs CONCURRENTLY on one SM
+// the step kernel leaves free (programmatic dependent launch; it polls the list and the step kernel's exit counter).
 #define MJ_CAPSET_KITCHEN 1
-#define mj mjk  // engine namespace of this translation unit: no symbol is shared with the door / peg capacity sets
+#ifdef MJK_XL
+#define MJ_CAPSET_KITCHEN_XL 1
+#define mj mjkx  // engine namespace of this translation unit: no symbol is shared with any other capacity set
+#else
+#define mj mjk
+#endif
 #include "../../include/earl_mj_kitchen_b200.h"
 
 #include <cstdarg>
@@ -26,7 +36,7 @@ int set_error(int code, const char* msg);  // earl_b200.cu
 
 namespace {
 
-using namespace earl::mjk;
+using namespace earl::mj;
 
 int failf(int code, const char* fmt, ...) {
   char buf[512];
@@ -44,13 +54,18 @@ int failf(int code, const char* fmt, ...) {
   } while (0)
 
 #ifndef MJK_WPB
+#ifdef MJK_XL
+#define MJK_WPB 3
+#else
 #define MJK_WPB 6
+#endif
 #endif
 constexpr int kWPB = MJK_WPB;  // warps (= environments in flight) per block
 constexpr size_t kWorkStride = (sizeof(Work) + 15) & ~size_t(15);
 constexpr size_t kSmemBytes = kWPB * kWorkStride;
 static_assert(kSmemBytes <= 227 * 1024, "workspaces exceed the 227 KB of shared memory per block");
 
+#ifndef MJK_XL
 // All warps of a block walk the same number of environments and substeps (the engine's phase barriers are block-wide);
 // a warp without an environment of its own shadows the last one and stores nothing.
 __global__ void __launch_bounds__(kWPB * 32, 1)
@@ -85,6 +100,7 @@ mjk_substeps_kernel(const Model* __restrict__ gm, const real* __restrict__ hull,
     __syncthreads();
   }
 }
+#endif  // !MJK_XL
 
 
 // ------------------------------------------------------------------------------------------------ task layer
@@ -107,10 +123,15 @@ struct TaskArgs {
   unsigned* steps_since_goal_change;
   long long* num_interventions;
   double* lifelong_return;
-  unsigned long long* work;         // 7 counters
+  unsigned long long* work;         // 12 counters
   int* cost;                        // [N] estimated cost of the last env step (visiting order of the next one)
   float4 mocap_quat;
+  // redo pass (null redo_list: disabled, overflowing steps are stored as they are and only counted)
+  long long* redo_list;             // [N] entries (step tag << 32 | env): the tag tells a fresh entry from an older step's
+  unsigned* sched;                  // [kRedoCount] listed, [kRedoNext] claimed, [kMainDone] step-kernel blocks finished, [kNextChunk]
+  unsigned redo_tag, main_blocks;
 };
+enum { kRedoCount = 0, kRedoNext = 1, kMainDone = 2, kNextChunk = 3, kSchedWords = 4 };
 
 // numpy's PCG64 (pcg64.h: pcg_setseq_128_step_r + pcg_output_xsl_rr_128_64) and Generator.uniform(-1, 1)
 struct Pcg { unsigned __int128 state, inc; };
@@ -208,121 +229,251 @@ __device__ __forceinline__ void task_store(const TaskArgs& a, const Model& m, co
   __syncwarp();
 }
 
-// mode 0: one env step of every environment.  mode 1: reset of the environments in env_ids.
-__global__ void __launch_bounds__(kWPB * 32, 1)
-mjk_task_kernel(const Model* __restrict__ gm, const real* __restrict__ hull, const TaskArgs a, int mode, const int* env_ids, int count,
-                const float* actions, const double* object_qpos, double* obs_out, double* reward_out, unsigned char* done_out,
-                unsigned char* success_out) {
-  extern __shared__ __align__(16) unsigned char smem[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  Work& w = *reinterpret_cast<Work*>(smem + warp * kWorkStride);
-  const Model& m = *gm;
-  unsigned long long c_it = 0, c_rows = 0, c_con = 0, c_bad = 0, c_over = 0, c_env = 0;
-  for (int base = blockIdx.x * kWPB; base < count; base += gridDim.x * kWPB) {
-    const bool own = base + warp < count;
-    const int slot = own ? base + warp : count - 1;
-    const int env = env_ids ? env_ids[slot] : slot;
-    Pcg g;
-    double last_qp[kRobot];
-    if (mode == 1) {  // Kitchen.reset_model: robot.reset (sim.reset, qpos write, forward, 5 cached observations at ratio 1)
-      for (int k = lane; k < kNQ; k += 32) {
-        const double q = k < kRobot ? a.init_qpos[k] : object_qpos[(size_t)slot * kObj + (k - kRobot)];
-        w.qpos[k] = (real)q; w.qvel[k] = 0; w.warm[k] = 0;
-      }
-      if (lane == 0) {
-        for (int k = 0; k < 3; ++k) w.mocap_pos[k] = a.midpoint[k];
-        w.mocap_quat[0] = a.mocap_quat.x; w.mocap_quat[1] = a.mocap_quat.y; w.mocap_quat[2] = a.mocap_quat.z; w.mocap_quat[3] = a.mocap_quat.w;
-        w.bad = 0; w.acc_iter = w.acc_rows = w.acc_con = w.acc_mpr = w.acc_sup = 0; w.broad_valid = 0; w.acc_rebuild = 0;
-      }
-      __syncwarp();
-    } else {
-      task_load(a, w, env, lane);
+struct TaskCounters { unsigned long long it = 0, rows = 0, con = 0, bad = 0, over = 0, env = 0, ov_hit = 0, ov_con = 0, ov_row = 0, redone = 0; };
+struct TaskIo {
+  const float* actions; const double* object_qpos; double* obs_out; double* reward_out; unsigned char* done_out; unsigned char* success_out;
+};
+
+// One environment of the task kernels, all lanes of its warp.  mode 0: env step, mode 1: reset (slot = row of object_qpos /
+// obs_out), mode 2: env step of the redo pass.  `own` false: the warp only keeps its block's phase barriers company.
+// Returns false when the step overflowed the capacities and was handed to the redo pass (nothing stored).
+__device__ __forceinline__ bool task_env(const Model& m, const real* hull, const TaskArgs& a, const TaskIo& io, Work& w, int mode, int env,
+                                         int slot, bool own, int lane, TaskCounters& c) {
+  Pcg g;
+  double last_qp[kRobot];
+  const bool stepping = mode != 1;
+  if (!stepping) {  // Kitchen.reset_model: robot.reset (sim.reset, qpos write, forward, 5 cached observations at ratio 1)
+    for (int k = lane; k < kNQ; k += 32) {
+      const double q = k < kRobot ? a.init_qpos[k] : io.object_qpos[(size_t)slot * kObj + (k - kRobot)];
+      w.qpos[k] = (real)q; w.qvel[k] = 0; w.warm[k] = 0;
     }
     if (lane == 0) {
-      const unsigned long long* r = a.rng + (size_t)env * 4;
-      g.state = ((unsigned __int128)r[0] << 64) | r[1];
-      g.inc = ((unsigned __int128)r[2] << 64) | r[3];
-      if (mode == 1) {
-        for (int k = 0; k < 5; ++k) kitchen_observe(a, w, g, 1.0, last_qp, nullptr);  // _observation_cache_refresh: default ratio 1
-        kitchen_control(a, nullptr, last_qp, w.mocap_pos, w.ctrl);
-      } else {
-        for (int k = 0; k < kRobot; ++k) last_qp[k] = a.last_qp[(size_t)env * kRobot + k];
-        kitchen_control(a, actions + (size_t)env * kAct, last_qp, w.mocap_pos, w.ctrl);
-      }
+      for (int k = 0; k < 3; ++k) w.mocap_pos[k] = a.midpoint[k];
+      w.mocap_quat[0] = a.mocap_quat.x; w.mocap_quat[1] = a.mocap_quat.y; w.mocap_quat[2] = a.mocap_quat.z; w.mocap_quat[3] = a.mocap_quat.w;
+      w.bad = 0; w.acc_iter = w.acc_rows = w.acc_con = w.acc_mpr = w.acc_sup = 0; w.broad_valid = 0; w.acc_rebuild = 0;
     }
     __syncwarp();
-    const int nsub = mode == 1 ? 10 * a.frame_skip : a.frame_skip;
-    for (int s = 0; s < nsub; ++s) substep<32>(m, hull, w, lane);
-    __syncwarp();
-    // A step that left a non-finite state (or whose factorisation broke down) is NOT stored: the environment stays at its
-    // last good state, the step returns that state's (noisy) observation with reward 0 and is counted in work[5]
-    // (the reference only prints MuJoCo's warning, ADEPT/simulation/module.py:123-126, and carries NaNs on).
-    bool fin = true;
-    for (int k = lane; k < kNQ; k += 32) fin = fin && isfinite(w.qpos[k]) && isfinite(w.qvel[k]);
-    const bool failed = mode == 0 && (!__all_sync(0xffffffffu, fin) || (w.bad & 1));
-    if (failed) {
-      const unsigned bad_k = w.bad | 1u;
-      __syncwarp();
-      task_load(a, w, env, lane);
-      kinematics<32>(m, w, lane);
-      if (lane == 0) w.bad = bad_k;
-      __syncwarp();
-    }
-    if (own) {
-      task_store(a, m, w, env, lane);
-      if (lane == 0) {
-        double obs[kObs];
-        kitchen_observe(a, w, g, a.noise_ratio, last_qp, obs);
-        for (int k = 0; k < kRobot; ++k) a.last_qp[(size_t)env * kRobot + k] = last_qp[k];
-        unsigned long long* r = a.rng + (size_t)env * 4;
-        r[0] = (unsigned long long)(g.state >> 64); r[1] = (unsigned long long)g.state;
-        double* orow = obs_out ? obs_out + (size_t)(mode == 0 ? env : slot) * kObs : nullptr;
-        // estimated warp instructions above the contact-free baseline: loose broad-phase passes (~9k each), extra Newton
-        // iterations (~6k), contacts (~1.5k per contact and substep), portal-refinement support calls (~0.3k)
-        a.cost[env] = 9000 * w.acc_rebuild + 6000 * (w.acc_iter - a.frame_skip) + 1500 * w.acc_con + 300 * w.acc_sup;
-        if (orow) for (int k = 0; k < kObs; ++k) orow[k] = obs[k];
-        if (mode == 0) {
-          bool ok;
-          double rew = kitchen_reward(obs, w.mocap_pos, a.sites + (size_t)env * kSites * 3, &ok);
-          if (failed) { rew = 0.0; ok = false; }
-          reward_out[env] = rew;
-          if (success_out) success_out[env] = ok;
-          const unsigned st = a.steps_since_reset[env] + 1;  // PersistentStateWrapper.step (persistent_state_wrapper.py:22-31)
-          a.steps_since_reset[env] = st;
-          done_out[env] = (long long)st >= a.horizon;
-          if (a.flags & EARL_FLAG_LIFELONG) {              // LifelongWrapper.step (lifelong_wrapper.py:30-44)
-            a.lifelong_return[env] += rew;
-            const unsigned sg = a.steps_since_goal_change[env] + 1;
-            if (a.goal_change_frequency > 0 && (long long)sg >= a.goal_change_frequency) {
-              // reset_goal() (a single goal: nothing changes) and env._get_obs(): a second noisy observation, returned
-              // instead of the first and cached for the next control; the reward stays the one already computed
-              a.steps_since_goal_change[env] = 0;
-              kitchen_observe(a, w, g, a.noise_ratio, last_qp, obs);
-              for (int k = 0; k < kRobot; ++k) a.last_qp[(size_t)env * kRobot + k] = last_qp[k];
-              r[0] = (unsigned long long)(g.state >> 64); r[1] = (unsigned long long)g.state;
-              if (orow) for (int k = 0; k < kObs; ++k) orow[k] = obs[k];
-            } else {
-              a.steps_since_goal_change[env] = sg;
-            }
-          }
-        } else {
-          a.steps_since_reset[env] = 0;                     // PersistentStateWrapper.reset (:17-20)
-          a.steps_since_goal_change[env] = 0;               // LifelongWrapper.reset (:25-28)
-          a.num_interventions[env] += 1;
-        }
-        c_it += w.acc_iter; c_rows += w.acc_rows; c_con += w.acc_con; c_bad += (w.bad & 1) ? 1 : 0; c_over += (w.bad & 14) ? 1 : 0; c_env += 1;
-      }
-    }
-    __syncthreads();
+  } else {
+    task_load(a, w, env, lane);
   }
-  if (lane == 0 && c_env) {
-    atomicAdd(&a.work[0], mode == 0 ? c_env : 0ULL);
-    atomicAdd(&a.work[1], c_env * (unsigned long long)(mode == 1 ? 10 * a.frame_skip : a.frame_skip));
-    atomicAdd(&a.work[2], c_it); atomicAdd(&a.work[3], c_rows); atomicAdd(&a.work[4], c_con);
-    atomicAdd(&a.work[5], c_bad); atomicAdd(&a.work[6], c_over);
+  if (lane == 0) {
+    const unsigned long long* r = a.rng + (size_t)env * 4;
+    g.state = ((unsigned __int128)r[0] << 64) | r[1];
+    g.inc = ((unsigned __int128)r[2] << 64) | r[3];
+    if (!stepping) {
+      for (int k = 0; k < 5; ++k) kitchen_observe(a, w, g, 1.0, last_qp, nullptr);  // _observation_cache_refresh: default ratio 1
+      kitchen_control(a, nullptr, last_qp, w.mocap_pos, w.ctrl);
+    } else {
+      for (int k = 0; k < kRobot; ++k) last_qp[k] = a.last_qp[(size_t)env * kRobot + k];
+      kitchen_control(a, io.actions + (size_t)env * kAct, last_qp, w.mocap_pos, w.ctrl);
+    }
+  }
+  __syncwarp();
+  const int nsub = stepping ? a.frame_skip : 10 * a.frame_skip;
+  for (int s = 0; s < nsub; ++s) substep<32>(m, hull, w, lane);
+  __syncwarp();
+  if (mode == 0 && a.redo_list && (w.bad & 14)) {  // capacity overflow: nothing is stored, the redo pass takes the env over
+    if (own && lane == 0) {
+      const unsigned at = atomicAdd(&a.sched[kRedoCount], 1u);
+      *reinterpret_cast<volatile long long*>(a.redo_list + at) = ((long long)a.redo_tag << 32) | (long long)(unsigned)env;
+      __threadfence();
+    }
+    return false;
+  }
+  // A step that left a non-finite state (or whose factorisation broke down) is NOT stored: the environment stays at its
+  // last good state, the step returns that state's (noisy) observation with reward 0 and is counted in work[5]
+  // (the reference only prints MuJoCo's warning, ADEPT/simulation/module.py:123-126, and carries NaNs on).
+  bool fin = true;
+  for (int k = lane; k < kNQ; k += 32) fin = fin && isfinite(w.qpos[k]) && isfinite(w.qvel[k]);
+  const bool failed = stepping && (!__all_sync(0xffffffffu, fin) || (w.bad & 1));
+  if (failed) {
+    const unsigned bad_k = w.bad | 1u;
+    __syncwarp();
+    task_load(a, w, env, lane);
+    kinematics<32>(m, w, lane);
+    if (lane == 0) w.bad = bad_k;
+    __syncwarp();
+  }
+  if (!own) return true;
+  task_store(a, m, w, env, lane);
+  if (lane == 0) {
+    double obs[kObs];
+    kitchen_observe(a, w, g, a.noise_ratio, last_qp, obs);
+    for (int k = 0; k < kRobot; ++k) a.last_qp[(size_t)env * kRobot + k] = last_qp[k];
+    unsigned long long* r = a.rng + (size_t)env * 4;
+    r[0] = (unsigned long long)(g.state >> 64); r[1] = (unsigned long long)g.state;
+    double* orow = io.obs_out ? io.obs_out + (size_t)(stepping ? env : slot) * kObs : nullptr;
+    // estimated warp instructions above the contact-free baseline: loose broad-phase passes (~9k each), extra Newton
+    // iterations (~6k), contacts (~1.5k per contact and substep), portal-refinement support calls (~0.3k)
+    a.cost[env] = 9000 * w.acc_rebuild + 6000 * (w.acc_iter - a.frame_skip) + 1500 * w.acc_con + 300 * w.acc_sup;
+    if (orow) for (int k = 0; k < kObs; ++k) orow[k] = obs[k];
+    if (stepping) {
+      bool ok;
+      double rew = kitchen_reward(obs, w.mocap_pos, a.sites + (size_t)env * kSites * 3, &ok);
+      if (failed) { rew = 0.0; ok = false; }
+      io.reward_out[env] = rew;
+      if (io.success_out) io.success_out[env] = ok;
+      const unsigned st = a.steps_since_reset[env] + 1;  // PersistentStateWrapper.step (persistent_state_wrapper.py:22-31)
+      a.steps_since_reset[env] = st;
+      io.done_out[env] = (long long)st >= a.horizon;
+      if (a.flags & EARL_FLAG_LIFELONG) {              // LifelongWrapper.step (lifelong_wrapper.py:30-44)
+        a.lifelong_return[env] += rew;
+        const unsigned sg = a.steps_since_goal_change[env] + 1;
+        if (a.goal_change_frequency > 0 && (long long)sg >= a.goal_change_frequency) {
+          // reset_goal() (a single goal: nothing changes) and env._get_obs(): a second noisy observation, returned
+          // instead of the first and cached for the next control; the reward stays the one already computed
+          a.steps_since_goal_change[env] = 0;
+          kitchen_observe(a, w, g, a.noise_ratio, last_qp, obs);
+          for (int k = 0; k < kRobot; ++k) a.last_qp[(size_t)env * kRobot + k] = last_qp[k];
+          r[0] = (unsigned long long)(g.state >> 64); r[1] = (unsigned long long)g.state;
+          if (orow) for (int k = 0; k < kObs; ++k) orow[k] = obs[k];
+        } else {
+          a.steps_since_goal_change[env] = sg;
+        }
+      }
+    } else {
+      a.steps_since_reset[env] = 0;                     // PersistentStateWrapper.reset (:17-20)
+      a.steps_since_goal_change[env] = 0;               // LifelongWrapper.reset (:25-28)
+      a.num_interventions[env] += 1;
+    }
+    c.it += w.acc_iter; c.rows += w.acc_rows; c.con += w.acc_con; c.bad += (w.bad & 1) ? 1 : 0; c.over += (w.bad & 14) ? 1 : 0; c.env += 1;
+    c.ov_hit += (w.bad & 2) ? 1 : 0; c.ov_con += (w.bad & 4) ? 1 : 0; c.ov_row += (w.bad & 8) ? 1 : 0;
+    c.redone += mode == 2 ? 1 : 0;
+  }
+  return true;
+}
+
+__device__ __forceinline__ void task_flush(const TaskArgs& a, const TaskCounters& c, int mode, int lane) {
+  if (lane == 0 && c.env) {
+    atomicAdd(&a.work[0], mode != 1 ? c.env : 0ULL);
+    atomicAdd(&a.work[1], c.env * (unsigned long long)(mode == 1 ? 10 * a.frame_skip : a.frame_skip));
+    atomicAdd(&a.work[2], c.it); atomicAdd(&a.work[3], c.rows); atomicAdd(&a.work[4], c.con);
+    atomicAdd(&a.work[5], c.bad); atomicAdd(&a.work[6], c.over); atomicAdd(&a.work[7], c.redone);
+    atomicAdd(&a.work[8], c.ov_hit); atomicAdd(&a.work[9], c.ov_con); atomicAdd(&a.work[10], c.ov_row);
   }
 }
 
+#ifndef MJK_XL
+// mode 0: one env step of every environment.  mode 1: reset of the environments in env_ids.
+__global__ void __launch_bounds__(kWPB * 32, 1)
+mjk_task_kernel(const Model* __restrict__ gm, const real* __restrict__ hull, const TaskArgs a, int mode, const int* env_ids, int count,
+                const TaskIo io) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  Work& w = *reinterpret_cast<Work*>(smem + warp * kWorkStride);
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // lets the concurrent redo kernel start (no-op otherwise)
+  TaskCounters c;
+  // Step: chunks of kWPB consecutive entries of the cost-sorted order are handed out dynamically (a block that draws expensive
+  // chunks takes fewer of them).  Reset: static stride.
+  __shared__ int s_chunk;
+  const bool dynamic = mode == 0;
+  for (int it = 0;; ++it) {
+    if (dynamic) {
+      if (threadIdx.x == 0) s_chunk = (int)atomicAdd(&a.sched[kNextChunk], 1u);
+      __syncthreads();
+    }
+    const int base = (dynamic ? s_chunk : blockIdx.x + it * (int)gridDim.x) * kWPB;
+    if (base >= count) break;
+    const bool own = base + warp < count;
+    const int slot = own ? base + warp : count - 1;
+    const int env = env_ids ? env_ids[slot] : slot;
+    task_env(*gm, hull, a, io, w, mode, env, slot, own, lane, c);
+    __syncthreads();
+  }
+  task_flush(a, c, mode, lane);
+  if (mode == 0 && a.redo_list) {
+    __syncthreads();
+    if (threadIdx.x == 0) { __threadfence(); atomicAdd(&a.sched[kMainDone], 1u); }  // the redo kernel polls this
+  }
+}
+#else
+// Redo pass: the env steps the step kernel listed, re-stepped from their untouched states with the extra-large capacities.
+// Runs while the step kernel does: thread 0 claims up to kWPB listed entries, or waits for one / for the step kernel's end.
+__global__ void __launch_bounds__(kWPB * 32, 1)
+mjk_redo_kernel(const Model* __restrict__ gm, const real* __restrict__ hull, const TaskArgs a, const TaskIo io) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  __shared__ int s_base, s_take;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  Work& w = *reinterpret_cast<Work*>(smem + warp * kWorkStride);
+  TaskCounters c;
+  volatile unsigned* sched = a.sched;
+  for (;;) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int base = 0, take = 0;
+      for (;;) {
+        const unsigned cnt = sched[kRedoCount], nx = sched[kRedoNext];
+        if (nx < cnt) {
+          const unsigned t = cnt - nx < (unsigned)kWPB ? cnt - nx : (unsigned)kWPB;
+          if (atomicCAS(&a.sched[kRedoNext], nx, nx + t) == nx) { base = (int)nx; take = (int)t; break; }
+          continue;
+        }
+        if (sched[kMainDone] >= a.main_blocks) {
+          __threadfence();
+          if (sched[kRedoNext] >= sched[kRedoCount]) break;  // step kernel over, list consumed
+          continue;
+        }
+        __nanosleep(1000);
+      }
+      s_base = base;
+      s_take = take;
+    }
+    __syncthreads();
+    const int base = s_base, take = s_take;
+    if (take == 0) break;
+    const bool own = warp < take;
+    long long entry;  // the slot was counted before it was written: wait for this step's tag
+    do {
+      entry = *reinterpret_cast<volatile long long*>(a.redo_list + base + (own ? warp : 0));
+    } while ((unsigned)(entry >> 32) != a.redo_tag);
+    const int env = (int)(unsigned)(entry & 0xffffffffll);
+    task_env(*gm, hull, a, io, w, 2, env, env, own, lane, c);
+  }
+  task_flush(a, c, 2, lane);
+}
+#endif
+
+
+#ifdef MJK_XL
+}  // namespace
+
+// Launches the redo kernel behind the step kernel (the previous launch in `stream`) as its programmatic dependent: it may
+// start while the step kernel still runs, on the SMs that one leaves free, and never calls griddepcontrol.wait -- it polls
+// the step kernel's list and exit counter.  TaskArgs / TaskIo / Model have the same layout in both instantiations (only
+// the workspace capacities differ); the sizes are checked.
+extern "C" int earl_mjkx_redo_pass(const void* d_model, size_t model_bytes, const void* d_hull, const void* task_args, size_t args_bytes,
+                                   const void* task_io, size_t io_bytes, int blocks, void* stream) {
+  if (!d_model || !task_args || !task_io || model_bytes != sizeof(Model) || args_bytes != sizeof(TaskArgs) || io_bytes != sizeof(TaskIo))
+    return failf(EARL_ERR_INVALID, "kitchen redo pass: argument layout mismatch (%zu / %zu / %zu vs %zu / %zu / %zu)", model_bytes, args_bytes,
+                 io_bytes, sizeof(Model), sizeof(TaskArgs), sizeof(TaskIo));
+  static bool configured[64] = {};
+  int dev = 0;
+  CU(cudaGetDevice(&dev));
+  if (dev >= 0 && dev < 64 && !configured[dev]) {
+    CU(cudaFuncSetAttribute(mjk_redo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+    configured[dev] = true;
+  }
+  TaskArgs a;
+  TaskIo io;
+  memcpy(&a, task_args, sizeof(a));
+  memcpy(&io, task_io, sizeof(io));
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(blocks > 0 ? blocks : 1));
+  cfg.blockDim = dim3((unsigned)(kWPB * 32));
+  cfg.dynamicSmemBytes = kSmemBytes;
+  cfg.stream = static_cast<cudaStream_t>(stream);
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  CU(cudaLaunchKernelEx(&cfg, mjk_redo_kernel, static_cast<const Model*>(d_model), static_cast<const real*>(d_hull), a, io));
+  return 0;
+}
+#else  // !MJK_XL: the rest of the file is the primary instantiation's host side
+
+extern "C" int earl_mjkx_redo_pass(const void* d_model, size_t model_bytes, const void* d_hull, const void* task_args, size_t args_bytes,
+                                   const void* task_io, size_t io_bytes, int blocks, void* stream);  // earl_mj_kitchen_xl.cu
 
 // Visiting order of the next env step: environments bucketed by the estimated cost of the step they just took, most
 // expensive bucket first, so the warps of a block (which meet at block-wide phase barriers) carry similar work.
@@ -435,6 +586,7 @@ struct earl_mjk_handle {
   int* d_rank = nullptr;
   unsigned* d_counts = nullptr;
   int bucket_width = 60000;  // flat between 40k and 160k (measured); EARL_MJK_BUCKET_WIDTH overrides
+  int redo_sms = 1;          // SMs the step kernel leaves to the concurrent redo kernel (EARL_MJ_REDO_SMS)
   std::vector<void*> owned;
   template <typename T>
   int alloc(T** ptr, size_t count) {
@@ -453,10 +605,22 @@ namespace {
 int launch_task(earl_mjk_handle* h, int mode, const int* env_ids, int count, const float* actions, const double* object_qpos,
                 double* obs, double* reward, unsigned char* done, unsigned char* success, void* stream) {
   const int blocks = (count + kWPB - 1) / kWPB;
-  const int grid = blocks < h->eng->sm_count ? blocks : h->eng->sm_count;
-  mjk_task_kernel<<<grid, kWPB * 32, kSmemBytes, static_cast<cudaStream_t>(stream)>>>(h->eng->d_model, h->eng->d_hull, h->a, mode, env_ids,
-                                                                                   count, actions, object_qpos, obs, reward, done, success);
+  int grid = blocks < h->eng->sm_count ? blocks : h->eng->sm_count;
+  TaskArgs a = h->a;
+  const TaskIo io{actions, object_qpos, obs, reward, done, success};
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (mode != 0) a.redo_list = nullptr;
+  if (a.redo_list) {
+    if (grid == h->eng->sm_count && grid > 8 * h->redo_sms) grid -= h->redo_sms;  // SMs left to the concurrent redo kernel
+    a.main_blocks = (unsigned)grid;
+    a.redo_tag = (unsigned)(h->total_steps & 0x7fffffff);
+  }
+  if (mode == 0) CU(cudaMemsetAsync(a.sched, 0, kSchedWords * sizeof(unsigned), s));
+  mjk_task_kernel<<<grid, kWPB * 32, kSmemBytes, s>>>(h->eng->d_model, h->eng->d_hull, a, mode, env_ids, count, io);
   CU(cudaGetLastError());
+  if (a.redo_list)
+    if (int rc = earl_mjkx_redo_pass(h->eng->d_model, sizeof(Model), h->eng->d_hull, &a, sizeof(a), &io, sizeof(io), h->redo_sms > 0 ? h->redo_sms : 1, stream))
+      return rc;
   return 0;
 }
 }  // namespace
@@ -490,8 +654,9 @@ int earl_mjk_create(const earl_mjk_config* cfg, const void* model_blob, size_t m
   if ((rc = h->alloc(&a.qpos, n * kNQ)) || (rc = h->alloc(&a.qvel, n * kNQ)) || (rc = h->alloc(&a.warm, n * kNQ)) ||
       (rc = h->alloc(&a.mocap, n * 3)) || (rc = h->alloc(&a.last_qp, n * kRobot)) || (rc = h->alloc(&a.sites, n * kSites * 3)) ||
       (rc = h->alloc(&a.rng, n * 4)) || (rc = h->alloc(&a.steps_since_reset, n)) || (rc = h->alloc(&a.steps_since_goal_change, n)) || (rc = h->alloc(&a.num_interventions, n)) ||
-      (rc = h->alloc(&a.lifelong_return, n)) || (rc = h->alloc(&a.work, 8)) || (rc = h->alloc(&a.cost, n)) || (rc = h->alloc(&h->d_order, n)) ||
-      (rc = h->alloc(&h->d_bucket, n)) || (rc = h->alloc(&h->d_rank, n)) || (rc = h->alloc(&h->d_counts, kBuckets))) {
+      (rc = h->alloc(&a.lifelong_return, n)) || (rc = h->alloc(&a.work, 12)) || (rc = h->alloc(&a.cost, n)) || (rc = h->alloc(&h->d_order, n)) ||
+      (rc = h->alloc(&h->d_bucket, n)) || (rc = h->alloc(&h->d_rank, n)) || (rc = h->alloc(&h->d_counts, kBuckets)) ||
+      (rc = h->alloc(&a.sched, kSchedWords))) {
     earl_mjk_destroy(h);
     return rc;
   }
@@ -500,6 +665,9 @@ int earl_mjk_create(const earl_mjk_config* cfg, const void* model_blob, size_t m
   CU(cudaGetLastError());
   CU(cudaDeviceSynchronize());  // the first step may be enqueued on any stream
   if (const char* e = getenv("EARL_MJK_BUCKET_WIDTH")) h->bucket_width = atoi(e) > 0 ? atoi(e) : h->bucket_width;
+  if (!(getenv("EARL_MJ_REDO") && atoi(getenv("EARL_MJ_REDO")) == 0))
+    if ((rc = h->alloc(&a.redo_list, n))) { earl_mjk_destroy(h); return rc; }
+  if (const char* e = getenv("EARL_MJ_REDO_SMS")) { const int r = atoi(e); if (r >= 1 && r < eng->sm_count / 8) h->redo_sms = r; }
   *out = h;
   return 0;
 }
@@ -604,7 +772,23 @@ int earl_mjk_work_counters(earl_mjk_handle* h, uint64_t* out7_host) {
   CU(cudaSetDevice(h->eng->device));
   CU(cudaDeviceSynchronize());
   CU(cudaMemcpy(out7_host, h->a.work, 7 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+  if (getenv("EARL_MJ_OVERFLOW_DETAIL")) {
+    uint64_t d[12];
+    CU(cudaMemcpy(d, h->a.work, sizeof(d), cudaMemcpyDeviceToHost));
+    fprintf(stderr, "[mjk overflow] env-steps with dropped candidate pairs %llu, dropped contacts %llu, dropped rows %llu\n",
+            (unsigned long long)d[8], (unsigned long long)d[9], (unsigned long long)d[10]);
+  }
   return 0;
 }
 
+int64_t earl_mjk_redo_count(earl_mjk_handle* h) {
+  if (!h) return -1;
+  unsigned long long v = 0;
+  if (cudaSetDevice(h->eng->device) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess ||
+      cudaMemcpy(&v, h->a.work + 7, sizeof(v), cudaMemcpyDeviceToHost) != cudaSuccess)
+    return -1;
+  return (int64_t)v;
+}
+
 }  // extern "C"
+#endif  // MJK_XL

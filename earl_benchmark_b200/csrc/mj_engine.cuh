@@ -76,8 +76,15 @@ constexpr float BROAD_SLACK = MJ_BROAD_SLACK;  // inflation of the cached broad 
 // Two capacity sets are compiled from these sources (earl_mj_small.cu / earl_mj_large.cu): the workspace of one
 // environment lives in shared memory, so rows x dofs and contacts decide how many environments one SM keeps in flight.
 #if defined(MJ_CAPSET_KITCHEN)
+#if defined(MJ_CAPSET_KITCHEN_XL)
+// kitchen redo pass (earl_mj_kitchen_xl.cu): the few env steps with a substep beyond 192 rows (a dozen six-dimensional
+// finger contacts at once: 10 rows each) or 24 contacts are re-stepped with these capacities
+constexpr int MAXEFC = 352; // constraint rows
+constexpr int MAXCON = 32;  // contacts
+#else
 constexpr int MAXEFC = 192; // constraint rows (6 weld + 5 equality + 23 friction loss + limits + 4 / 10 per pyramidal contact)
 constexpr int MAXCON = 24;  // contacts
+#endif
 constexpr int MAXHIT = 64;  // candidate pairs that survive the broad phase in one substep
 constexpr int MAXPAIR = 4096; // candidate geom pairs
 constexpr int MAXMG = 64;    // geoms on moving bodies (their world poses are recomputed every substep)

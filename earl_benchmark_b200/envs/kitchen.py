@@ -317,8 +317,10 @@ class Kitchen:
         self._ensure()
         out = np.zeros(7, np.uint64)
         _lib.check(_lib.lib().earl_mjk_work_counters(self._handle, out.ctypes.data))
-        return dict(zip(("env_steps", "substeps", "newton_iterations", "constraint_rows", "contacts", "bad_states", "overflow_states"),
-                        (int(x) for x in out)))
+        d = dict(zip(("env_steps", "substeps", "newton_iterations", "constraint_rows", "contacts", "bad_states", "overflow_states"),
+                     (int(x) for x in out)))
+        d["redone_states"] = int(_lib.lib().earl_mjk_redo_count(self._handle))
+        return d
 
     def get_state(self):
         """dict(qpos, qvel, qacc_warmstart [N,23], mocap_pos [N,3], last_noisy_qp [N,9], site_xpos [N,8,3]) as host arrays."""

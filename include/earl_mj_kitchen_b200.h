@@ -88,6 +88,9 @@ EARL_API int earl_mjk_counters(earl_mjk_handle* h, int64_t* total_steps_host, in
                                uint32_t* steps_since_reset_dev, double* lifelong_return_dev, void* stream);
 /* { env_steps, substeps, newton_iterations, constraint_rows, contacts, bad_states, overflow_states } since creation */
 EARL_API int earl_mjk_work_counters(earl_mjk_handle* h, uint64_t* out7_host);
+/* env steps re-stepped by the extra-large capacity set since creation (a substep of theirs outgrew 192 rows / 24 contacts;
+ * overflow_states counts what even that set could not hold, or every overflow when EARL_MJ_REDO=0); -1 on error */
+EARL_API int64_t earl_mjk_redo_count(earl_mjk_handle* h);
 
 #ifdef __cplusplus
 }

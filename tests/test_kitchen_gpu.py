@@ -165,3 +165,37 @@ def test_same_results_for_any_batch_composition():
     full, part = run([0, 1, 2, 3, 4, 5, 6]), run([5, 2])
     for (o1, r1), (o2, r2) in zip(full, part):
         assert torch.equal(o1[[5, 2]], o2) and torch.equal(r1[[5, 2]], r2)
+
+
+def test_row_overflow_is_redone_by_the_extra_large_set_not_dropped(monkeypatch):
+    """bench.py's kitchen stream: a dozen env steps in ~10^5 have a substep beyond the 192 rows of the primary set (a handful
+    of six-dimensional finger contacts, 10 rows each).  With the redo pass they are re-stepped by the 352-row set
+    (overflow_states stays 0); every environment that never overflowed is bit-identical to the run without it."""
+    n, warm, steps = 14208, 30, 8   # bench.py's kitchen section: the arms have to get up to speed first
+
+    def run(redo):
+        monkeypatch.setenv("EARL_MJ_REDO", "1" if redo else "0")
+        env = kitchen.Kitchen(num_envs=n, device="cuda:0", seed=0)
+        env.seed(0)
+        env.reset()
+        gen = torch.Generator(device="cuda:0")
+        gen.manual_seed(99)
+        actions = torch.rand((8 + steps, n, 9), generator=gen, device="cuda:0", dtype=torch.float32) * 2 - 1
+        rew = []
+        for t in range(warm + steps):
+            ob, r, d, info = env.step(actions[t % 8 if t < warm else 8 + t - warm])
+            rew.append(r.clone())
+        torch.cuda.synchronize()
+        return env.get_state(), torch.stack(rew).cpu().numpy(), env.work_counters()
+
+    st0, r0, w0 = run(False)
+    st1, r1, w1 = run(True)
+    assert w0["redone_states"] == 0 and w1["env_steps"] == w0["env_steps"] == n * (warm + steps)
+    if w0["overflow_states"] == 0:
+        pytest.skip("this action stream no longer outgrows the primary capacity set")
+    assert w1["overflow_states"] == 0, w1
+    assert 1 <= w1["redone_states"] <= 2 * w0["overflow_states"], (w0, w1)
+    assert w1["bad_states"] == 0
+    differ = np.flatnonzero((st0["qpos"] != st1["qpos"]).any(1) | (r0 != r1).any(0))
+    assert 1 <= len(differ) <= w1["redone_states"], (len(differ), w1)
+    assert np.isfinite(st1["qpos"]).all() and np.isfinite(r1).all()
