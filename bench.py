@@ -280,8 +280,8 @@ KITCHEN_ENVS, KITCHEN_STEPS, KITCHEN_WARMUP = 14208, 8, 30
 
 
 def run_kitchen(dev, rank, world, sm_max_mhz, sm_count, with_cpu):
-    """Fourth bench section: batched kitchen step (BASELINE.json configs[4]): 14,208 envs per GPU (= 148 SMs x 6 resident
-    environments x 16 waves), random actions after a full reset (400 settle substeps per env)."""
+    """Fourth bench section: batched kitchen step (BASELINE.json configs[4]): 14,208 envs per GPU (= 148 SMs x 8 resident
+    environments x 12 waves), random actions after a full reset (400 settle substeps per env)."""
     import torch
     import torch.distributed as dist
 
@@ -333,8 +333,8 @@ def run_kitchen(dev, rank, world, sm_max_mhz, sm_count, with_cpu):
                         "bad_states": w1["bad_states"] - w0["bad_states"],
                         "overflow_states": w1["overflow_states"] - w0["overflow_states"],
                         "redone_states": w1["redone_states"] - w0["redone_states"]},
-               "kernel": "mjk_task_kernel (one warp per env, 6 envs per SM in flight, model tables in global memory, cost-sorted visiting order) "
-                         "+ mjk_redo_kernel (352-row set, concurrent on one reserved SM: env steps that outgrew 192 rows / 24 contacts)"}
+               "kernel": "mjk_task_kernel (one warp per env, 8 envs per SM in flight, 112-row workspaces, model tables in global memory, cost-sorted visiting order, dynamic chunks) "
+                         "+ mjk_redo_kernel (352-row set, concurrent on four reserved SMs: the ~0.1 % of env steps that outgrew 112 rows / 24 contacts)"}
         if with_cpu:
             procs = os.cpu_count() or 1
             rate, flops, wall = door_cpu_rate(procs, steps_per_proc=1500, task="kitchen")

@@ -1,13 +1,14 @@
-// earl_mj_kitchen.cu -- the kitchen capacity set of the articulated-body engine (24 dofs, 128 geoms, 192 rows, 24
+// earl_mj_kitchen.cu -- the kitchen capacity set of the articulated-body engine (24 dofs, 128 geoms, 112 rows, 24
 // contacts; joint-equality / friction-loss / pyramidal rows, capsule geoms) and its ENGINE-LEVEL entry points
-// (include/earl_mj_kitchen_b200.h).  One warp per environment; the 37.1 KB workspace of an environment lives in shared
-// memory (6 environments in flight per SM), the 37 KB model stays in global memory (L1 / L2 resident: every block reads
+// (include/earl_mj_kitchen_b200.h).  One warp per environment; the 27.1 KB workspace of an environment lives in shared
+// memory (8 environments in flight per SM), the 37 KB model stays in global memory (L1 / L2 resident: every block reads
 // the same tables).  No CPU fallback.
 //
 // Compiled a second time as earl_mj_kitchen_xl.cu (MJK_XL: 352 rows, 32 contacts, 3 environments per block) for the
-// REDO PASS: an env step in which some substep outgrew the 192 rows / 24 contacts is not stored by the step kernel but
-// listed, and re-stepped from its untouched state by the extra-large instantiation, which runs CONCURRENTLY on one SM
-// the step kernel leaves free (programmatic dependent launch; it polls the list and the step kernel's exit counter).
+// REDO PASS: an env step in which some substep outgrew the 112 rows / 24 contacts (~0.1 % of them) is not stored by the
+// step kernel but listed, and re-stepped from its untouched state by the extra-large instantiation, which runs
+// CONCURRENTLY on four SMs the step kernel leaves free (programmatic dependent launch; it polls the list and the step
+// kernel's exit counter).
 #define MJ_CAPSET_KITCHEN 1
 #ifdef MJK_XL
 #define MJ_CAPSET_KITCHEN_XL 1
@@ -57,28 +58,37 @@ int failf(int code, const char* fmt, ...) {
 #ifdef MJK_XL
 #define MJK_WPB 3
 #else
-#define MJK_WPB 6
+#define MJK_WPB 8
 #endif
+#endif
+#ifndef MJK_BPS
+#define MJK_BPS 1
 #endif
 constexpr int kWPB = MJK_WPB;  // warps (= environments in flight) per block
+constexpr int kBPS = MJK_BPS;  // resident blocks per SM (each block is one phase-barrier domain)
 constexpr size_t kWorkStride = (sizeof(Work) + 15) & ~size_t(15);
 constexpr size_t kSmemBytes = kWPB * kWorkStride;
-static_assert(kSmemBytes <= 227 * 1024, "workspaces exceed the 227 KB of shared memory per block");
+static_assert(kBPS * (kSmemBytes + 1024) <= 228 * 1024, "workspaces exceed the shared memory of an SM");
 
-#ifndef MJK_XL
 // All warps of a block walk the same number of environments and substeps (the engine's phase barriers are block-wide);
-// a warp without an environment of its own shadows the last one and stores nothing.
+// a warp without an environment of its own shadows the last one and stores nothing.  Primary set: environments whose
+// substeps outgrow the capacities keep their input state and are flagged in info[:, 3]; the extra-large instantiation
+// (only_flagged 1) then walks the flagged ones.  only_flagged 2: primary set, everything stored (EARL_MJ_REDO=0).
 __global__ void __launch_bounds__(kWPB * 32, 1)
 mjk_substeps_kernel(const Model* __restrict__ gm, const real* __restrict__ hull, int n, int nsub, float* qpos, float* qvel, float* warm,
-                    const double* mocap_pos, float4 mocap_quat, const float* ctrl, int* info) {
+                    const double* mocap_pos, float4 mocap_quat, const float* ctrl, int* info, int only_flagged) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   Work& w = *reinterpret_cast<Work*>(smem + warp * kWorkStride);
   const Model& m = *gm;
   const int nq = m.nq, nv = m.nv;
   for (int base = blockIdx.x * kWPB; base < n; base += gridDim.x * kWPB) {
-    const bool own = base + warp < n;
+    bool own = base + warp < n;
     const int env = own ? base + warp : n - 1;
+    if (only_flagged == 1) {
+      own = own && (info[4 * env + 3] & 14);
+      if (!__syncthreads_or(own)) continue;
+    }
     for (int k = lane; k < nq; k += 32) w.qpos[k] = qpos[(size_t)env * nq + k];
     for (int k = lane; k < nv; k += 32) { w.qvel[k] = qvel[(size_t)env * nv + k]; w.warm[k] = warm[(size_t)env * nv + k]; }
     if (lane == 0) {
@@ -91,16 +101,17 @@ mjk_substeps_kernel(const Model* __restrict__ gm, const real* __restrict__ hull,
     for (int s = 0; s < nsub; ++s) substep<32>(m, hull, w, lane);
     __syncwarp();
     if (own) {
-      for (int k = lane; k < nq; k += 32) qpos[(size_t)env * nq + k] = w.qpos[k];
-      for (int k = lane; k < nv; k += 32) { qvel[(size_t)env * nv + k] = w.qvel[k]; warm[(size_t)env * nv + k] = w.warm[k]; }
+      if (only_flagged != 0 || !(w.bad & 14)) {
+        for (int k = lane; k < nq; k += 32) qpos[(size_t)env * nq + k] = w.qpos[k];
+        for (int k = lane; k < nv; k += 32) { qvel[(size_t)env * nv + k] = w.qvel[k]; warm[(size_t)env * nv + k] = w.warm[k]; }
+      }
       if (lane == 0) {
-        info[4 * env] = w.nefc; info[4 * env + 1] = w.ncon; info[4 * env + 2] = w.acc_iter; info[4 * env + 3] = w.bad;
+        info[4 * env] = w.nefc; info[4 * env + 1] = w.ncon; info[4 * env + 2] = w.acc_iter; info[4 * env + 3] = w.bad | (only_flagged == 1 ? 16 : 0);
       }
     }
     __syncthreads();
   }
 }
-#endif  // !MJK_XL
 
 
 // ------------------------------------------------------------------------------------------------ task layer
@@ -355,7 +366,7 @@ __device__ __forceinline__ void task_flush(const TaskArgs& a, const TaskCounters
 
 #ifndef MJK_XL
 // mode 0: one env step of every environment.  mode 1: reset of the environments in env_ids.
-__global__ void __launch_bounds__(kWPB * 32, 1)
+__global__ void __launch_bounds__(kWPB * 32, kBPS)
 mjk_task_kernel(const Model* __restrict__ gm, const real* __restrict__ hull, const TaskArgs a, int mode, const int* env_ids, int count,
                 const TaskIo io) {
   extern __shared__ __align__(16) unsigned char smem[];
@@ -470,7 +481,33 @@ extern "C" int earl_mjkx_redo_pass(const void* d_model, size_t model_bytes, cons
   CU(cudaLaunchKernelEx(&cfg, mjk_redo_kernel, static_cast<const Model*>(d_model), static_cast<const real*>(d_hull), a, io));
   return 0;
 }
+
+// Second pass of earl_mjk_engine_substeps: the environments the primary set flagged (info[:, 3] & 14), from their untouched
+// input states, with the extra-large capacities; info[:, 3] gets bit 4 (and again bits 1-3 if even this set overflowed).
+extern "C" int earl_mjkx_substeps_flagged(const void* d_model, size_t model_bytes, const void* d_hull, int n, int nsub, float* qpos, float* qvel,
+                                          float* warm, const double* mocap_pos, const float* mocap_quat4, const float* ctrl, int* info,
+                                          int sm_count, void* stream) {
+  if (!d_model || model_bytes != sizeof(Model)) return failf(EARL_ERR_INVALID, "kitchen substeps: model layout mismatch");
+  static bool configured[64] = {};
+  int dev = 0;
+  CU(cudaGetDevice(&dev));
+  if (dev >= 0 && dev < 64 && !configured[dev]) {
+    CU(cudaFuncSetAttribute(mjk_substeps_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+    configured[dev] = true;
+  }
+  const int blocks = (n + kWPB - 1) / kWPB;
+  const int grid = blocks < 4 * sm_count ? blocks : 4 * sm_count;
+  mjk_substeps_kernel<<<grid, kWPB * 32, kSmemBytes, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const Model*>(d_model), static_cast<const real*>(d_hull), n, nsub, qpos, qvel, warm, mocap_pos,
+      make_float4(mocap_quat4[0], mocap_quat4[1], mocap_quat4[2], mocap_quat4[3]), ctrl, info, 1);
+  CU(cudaGetLastError());
+  return 0;
+}
 #else  // !MJK_XL: the rest of the file is the primary instantiation's host side
+
+extern "C" int earl_mjkx_substeps_flagged(const void* d_model, size_t model_bytes, const void* d_hull, int n, int nsub, float* qpos, float* qvel,
+                                          float* warm, const double* mocap_pos, const float* mocap_quat4, const float* ctrl, int* info,
+                                          int sm_count, void* stream);  // earl_mj_kitchen_xl.cu
 
 extern "C" int earl_mjkx_redo_pass(const void* d_model, size_t model_bytes, const void* d_hull, const void* task_args, size_t args_bytes,
                                    const void* task_io, size_t io_bytes, int blocks, void* stream);  // earl_mj_kitchen_xl.cu
@@ -566,9 +603,13 @@ int earl_mjk_engine_substeps(earl_mjk_engine* e, int32_t num_envs, int32_t nsub,
   const int blocks = (num_envs + kWPB - 1) / kWPB;
   const int grid = blocks < e->sm_count ? blocks : e->sm_count;
   const float4 mq = make_float4(mocap_quat_host[0], mocap_quat_host[1], mocap_quat_host[2], mocap_quat_host[3]);
+  const bool redo = !(getenv("EARL_MJ_REDO") && atoi(getenv("EARL_MJ_REDO")) == 0);
   mjk_substeps_kernel<<<grid, kWPB * 32, kSmemBytes, static_cast<cudaStream_t>(stream)>>>(
-      e->d_model, e->d_hull, num_envs, nsub, qpos_dev, qvel_dev, warm_dev, mocap_pos_dev, mq, ctrl_dev, info_dev);
+      e->d_model, e->d_hull, num_envs, nsub, qpos_dev, qvel_dev, warm_dev, mocap_pos_dev, mq, ctrl_dev, info_dev, redo ? 0 : 2);
   CU(cudaGetLastError());
+  if (redo)
+    return earl_mjkx_substeps_flagged(e->d_model, sizeof(Model), e->d_hull, num_envs, nsub, qpos_dev, qvel_dev, warm_dev, mocap_pos_dev,
+                                      mocap_quat_host, ctrl_dev, info_dev, e->sm_count, stream);
   return 0;
 }
 
@@ -586,7 +627,7 @@ struct earl_mjk_handle {
   int* d_rank = nullptr;
   unsigned* d_counts = nullptr;
   int bucket_width = 60000;  // flat between 40k and 160k (measured); EARL_MJK_BUCKET_WIDTH overrides
-  int redo_sms = 1;          // SMs the step kernel leaves to the concurrent redo kernel (EARL_MJ_REDO_SMS)
+  int redo_sms = 4;          // SMs the step kernel leaves to the concurrent redo kernel (EARL_MJ_REDO_SMS; measured 2: 1.49e5, 4: 1.54e5, 6: 1.53e5)
   std::vector<void*> owned;
   template <typename T>
   int alloc(T** ptr, size_t count) {
@@ -605,13 +646,14 @@ namespace {
 int launch_task(earl_mjk_handle* h, int mode, const int* env_ids, int count, const float* actions, const double* object_qpos,
                 double* obs, double* reward, unsigned char* done, unsigned char* success, void* stream) {
   const int blocks = (count + kWPB - 1) / kWPB;
-  int grid = blocks < h->eng->sm_count ? blocks : h->eng->sm_count;
+  const int slots = h->eng->sm_count * kBPS;
+  int grid = blocks < slots ? blocks : slots;
   TaskArgs a = h->a;
   const TaskIo io{actions, object_qpos, obs, reward, done, success};
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (mode != 0) a.redo_list = nullptr;
   if (a.redo_list) {
-    if (grid == h->eng->sm_count && grid > 8 * h->redo_sms) grid -= h->redo_sms;  // SMs left to the concurrent redo kernel
+    if (grid == slots && grid > 8 * h->redo_sms * kBPS) grid -= h->redo_sms * kBPS;  // SMs left to the concurrent redo kernel
     a.main_blocks = (unsigned)grid;
     a.redo_tag = (unsigned)(h->total_steps & 0x7fffffff);
   }

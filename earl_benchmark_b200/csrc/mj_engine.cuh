@@ -77,12 +77,22 @@ constexpr float BROAD_SLACK = MJ_BROAD_SLACK;  // inflation of the cached broad 
 // environment lives in shared memory, so rows x dofs and contacts decide how many environments one SM keeps in flight.
 #if defined(MJ_CAPSET_KITCHEN)
 #if defined(MJ_CAPSET_KITCHEN_XL)
-// kitchen redo pass (earl_mj_kitchen_xl.cu): the few env steps with a substep beyond 192 rows (a dozen six-dimensional
-// finger contacts at once: 10 rows each) or 24 contacts are re-stepped with these capacities
+// kitchen redo pass (earl_mj_kitchen_xl.cu): the few env steps with a substep beyond the primary set's rows (half a dozen
+// six-dimensional finger contacts at once: 10 rows each) or 24 contacts are re-stepped with these capacities
 constexpr int MAXEFC = 352; // constraint rows
 constexpr int MAXCON = 32;  // contacts
 #else
-constexpr int MAXEFC = 192; // constraint rows (6 weld + 5 equality + 23 friction loss + limits + 4 / 10 per pyramidal contact)
+// Device: 112 rows (27.1 KB workspace, 8 environments in flight per SM); the ~0.1 % of env steps with a substep beyond
+// that are re-stepped by the extra-large set.  Measured at 14,208 envs: 192 rows / 6 per SM 1.33e5 env-steps/s, 128 / 7
+// 1.47e5, 112 / 8 1.54e5, 96 / 8 1.52e5.  The host build of this source (tests) has no redo pass and keeps 192 rows.
+#ifndef MJK_MAXEFC
+#ifdef __CUDACC__
+#define MJK_MAXEFC 112
+#else
+#define MJK_MAXEFC 192
+#endif
+#endif
+constexpr int MAXEFC = MJK_MAXEFC; // constraint rows (6 weld + 5 equality + 23 friction loss + limits + 4 / 10 per pyramidal contact)
 constexpr int MAXCON = 24;  // contacts
 #endif
 constexpr int MAXHIT = 64;  // candidate pairs that survive the broad phase in one substep

@@ -30,7 +30,8 @@ EARL_API int earl_mjk_engine_nv(const earl_mjk_engine* e);
  * In / out: qpos, qvel, qacc_warmstart f32 [N, nv].  In: mocap_pos f64 [N,3], mocap_quat f32 [4] (one for all: the task
  * never moves it), ctrl f32 [N,2] (the engine clamps to ctrlrange).  Out: info i32 [N,4] = { rows of the last substep,
  * contacts of the last substep, Newton iterations summed over the substeps, flags (bit 0 non-positive pivot, bits 1-3
- * capacity overflow: candidate pairs / contacts / rows) }. */
+ * capacity overflow: candidate pairs / contacts / rows, bit 4: the primary 112-row set overflowed and the environment was
+ * re-run from its input state by the 352-row set -- bits 1-3 then refer to that run) }. */
 EARL_API int earl_mjk_engine_substeps(earl_mjk_engine* e, int32_t num_envs, int32_t nsub, float* qpos_dev, float* qvel_dev,
                                       float* warm_dev, const double* mocap_pos_dev, const float* mocap_quat_host,
                                       const float* ctrl_dev, int32_t* info_dev, void* stream);
@@ -88,7 +89,7 @@ EARL_API int earl_mjk_counters(earl_mjk_handle* h, int64_t* total_steps_host, in
                                uint32_t* steps_since_reset_dev, double* lifelong_return_dev, void* stream);
 /* { env_steps, substeps, newton_iterations, constraint_rows, contacts, bad_states, overflow_states } since creation */
 EARL_API int earl_mjk_work_counters(earl_mjk_handle* h, uint64_t* out7_host);
-/* env steps re-stepped by the extra-large capacity set since creation (a substep of theirs outgrew 192 rows / 24 contacts;
+/* env steps re-stepped by the extra-large capacity set since creation (a substep of theirs outgrew the 112 rows / 24 contacts of the primary set;
  * overflow_states counts what even that set could not hold, or every overflow when EARL_MJ_REDO=0); -1 on error */
 EARL_API int64_t earl_mjk_redo_count(earl_mjk_handle* h);
 
