@@ -110,8 +110,14 @@ constexpr int MAXEFC = 96;  // constraint rows
 constexpr int MAXCON = 24;  // contacts
 constexpr int MAXHIT = 32;  // candidate pairs that survive the broad phase in one substep
 #else
-constexpr int MAXEFC = 64;
-constexpr int MAXCON = 16;
+#ifndef MJ_SMALL_MAXEFC
+#define MJ_SMALL_MAXEFC 64
+#endif
+#ifndef MJ_SMALL_MAXCON
+#define MJ_SMALL_MAXCON 16
+#endif
+constexpr int MAXEFC = MJ_SMALL_MAXEFC;
+constexpr int MAXCON = MJ_SMALL_MAXCON;
 constexpr int MAXHIT = 24;
 #endif
 constexpr int MAXPAIR = 192; // candidate geom pairs

