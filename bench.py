@@ -102,7 +102,7 @@ class ClockSampler:
 
 # ----------------------------------------------------------------------------------------------- CPU arm
 
-def cpu_port_rate(num_envs, steps, threads, budget_s=20.0):
+def cpu_port_rate(num_envs, steps, threads, budget_s=20.0, min_wall_s=0.0):
     """env-steps/s of the CPU oracle (step-major: all envs advance one step at a time, like a vector env).
     The sample is bounded to about `budget_s` seconds: fewer envs per step if needed, never fewer steps."""
     import numpy as np
@@ -133,8 +133,10 @@ def cpu_port_rate(num_envs, steps, threads, budget_s=20.0):
     if per_env_step * num_envs * steps > budget_s:
         n_sample = max(1 << 14, int(budget_s / (per_env_step * steps)))
         n_sample = min(num_envs, n_sample)
-    el = run(n_sample, steps)
-    return n_sample * steps / el, n_sample, el
+    # a sample worth timing: at least `min_wall_s` seconds on all threads (tens of core-seconds), by more steps of the same batch
+    k = max(steps, int(min_wall_s / max(per_env_step * n_sample, 1e-9)) + 1)
+    el = run(n_sample, k)
+    return n_sample * k / el, n_sample, el, k
 
 
 # ----------------------------------------------------------------------------------------------- Sawyer door (config 3)
@@ -428,6 +430,18 @@ def run_tt3(dev, rank, world, with_e2e):
     return out
 
 
+def ref_python_loop():
+    """The UNMODIFIED reference's own Python step loop (SURVEY 8(d) CPU baseline (i)), measured where /root/reference exists
+    (oracle/ref_python_rate.py, build container) and committed: the GPU box cannot run it."""
+    p = os.path.join(REPO, "profiles", "r02", "ref_python_loop_rate.json")
+    try:
+        d = json.load(open(p))
+        return {"unit": UNIT, "measured_in": "build container (8 host cpus), committed as profiles/r02/ref_python_loop_rate.json",
+                "runs": [{"procs": r["procs"], "value": r["env_steps_per_s"]} for r in d["runs"]]}
+    except Exception:
+        return None
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -435,15 +449,16 @@ def run_reference(args):
     threads = os.cpu_count() or 1
     n_total = args.num_envs * args.gpus
     cpu_port_rate(1 << 14, max(1, args.warmup), threads, budget_s=2.0)
-    rate, n_sample, el = cpu_port_rate(n_total, args.steps, threads, budget_s=90.0)
-    sample = (f"{n_sample} of {n_total} envs x {args.steps} steps, step-major, OpenMP {threads} threads, "
+    rate, n_sample, el, k = cpu_port_rate(n_total, args.steps, threads, budget_s=90.0, min_wall_s=1.5)
+    sample = (f"{n_sample} of {n_total} envs x {k} steps, step-major, OpenMP {threads} threads, "
               f"{el:.2f} s; C port of reference tabletop step + PersistentStateWrapper (the reference itself is Python "
               "over mujoco-py and cannot run here)")
     line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * n_total / rate, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": config_dict(args, n_total),
-            "cpu_baseline": {"value": rate, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": rate, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
+                             "reference_python_loop": ref_python_loop()},
             "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -791,12 +806,14 @@ def run_ours(args):
             line["kitchen"] = kit
         if world == 1 and not args.no_cpu_baseline and not args.profile:
             threads = os.cpu_count() or 1
-            rate, n_sample, el = cpu_port_rate(n, min(args.steps, 200), threads, budget_s=15.0)
+            rate, n_sample, el, k = cpu_port_rate(n, min(args.steps, 200), threads, budget_s=15.0, min_wall_s=1.5)
             line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
-                                    "sample": f"{n_sample} envs x {min(args.steps, 200)} steps of the same workload, "
-                                              f"step-major C oracle, OpenMP {threads} threads, {el:.2f} s",
-                                    "note": "a C restatement of the reference arithmetic, ~1e4 x faster than the reference's own "
-                                            "Python loop (3.6e4 env-steps/s per core behind a no-op MuJoCo stand-in, DESIGN.md 3)"}
+                                    "sample": f"{n_sample} envs x {k} steps of the same workload, "
+                                              f"step-major C oracle, OpenMP {threads} threads, {el:.2f} s ({el * threads:.0f} core-seconds)",
+                                    "note": "a C restatement of the reference arithmetic, ~2e4 x faster per core than the reference's "
+                                            "own Python loop (reference_python_loop: measured in the build container, where "
+                                            "/root/reference exists, by oracle/ref_python_rate.py)",
+                                    "reference_python_loop": ref_python_loop()}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
