@@ -336,7 +336,7 @@ def run_kitchen(dev, rank, world, sm_max_mhz, sm_count, with_cpu):
                         "overflow_states": w1["overflow_states"] - w0["overflow_states"],
                         "redone_states": w1["redone_states"] - w0["redone_states"]},
                "kernel": "mjk_task_kernel (one warp per env, 8 envs per SM in flight, 112-row workspaces, model tables in global memory, cost-sorted visiting order, dynamic chunks) "
-                         "+ mjk_redo_kernel (352-row set, concurrent on four reserved SMs: the ~0.1 % of env steps that outgrew 112 rows / 24 contacts)"}
+                         "+ mjk_redo_kernel (544-row set, concurrent on four reserved SMs plus every SM the step kernel vacates: the ~0.1 % of env steps that outgrew 112 rows / 24 contacts)"}
         if with_cpu:
             procs = os.cpu_count() or 1
             rate, flops, wall = door_cpu_rate(procs, steps_per_proc=1500, task="kitchen")

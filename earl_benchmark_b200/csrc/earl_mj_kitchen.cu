@@ -4,7 +4,7 @@
 // memory (8 environments in flight per SM), the 37 KB model stays in global memory (L1 / L2 resident: every block reads
 // the same tables).  No CPU fallback.
 //
-// Compiled a second time as earl_mj_kitchen_xl.cu (MJK_XL: 352 rows, 32 contacts, 3 environments per block) for the
+// Compiled a second time as earl_mj_kitchen_xl.cu (MJK_XL: 544 rows, 48 contacts, 2 environments per block) for the
 // REDO PASS: an env step in which some substep outgrew the 112 rows / 24 contacts (~0.1 % of them) is not stored by the
 // step kernel but listed, and re-stepped from its untouched state by the extra-large instantiation, which runs
 // CONCURRENTLY on four SMs the step kernel leaves free (programmatic dependent launch; it polls the list and the step
@@ -56,7 +56,7 @@ int failf(int code, const char* fmt, ...) {
 
 #ifndef MJK_WPB
 #ifdef MJK_XL
-#define MJK_WPB 3
+#define MJK_WPB 2
 #else
 #define MJK_WPB 8
 #endif
@@ -660,8 +660,10 @@ int launch_task(earl_mjk_handle* h, int mode, const int* env_ids, int count, con
   if (mode == 0) CU(cudaMemsetAsync(a.sched, 0, kSchedWords * sizeof(unsigned), s));
   mjk_task_kernel<<<grid, kWPB * 32, kSmemBytes, s>>>(h->eng->d_model, h->eng->d_hull, a, mode, env_ids, count, io);
   CU(cudaGetLastError());
+  // one redo block per SM: those that find no free SM start as step-kernel blocks retire, so a regime with many overflows
+  // (arms deep in the cabinets: 5 % of the env steps) ends with the whole GPU working on the list
   if (a.redo_list)
-    if (int rc = earl_mjkx_redo_pass(h->eng->d_model, sizeof(Model), h->eng->d_hull, &a, sizeof(a), &io, sizeof(io), h->redo_sms > 0 ? h->redo_sms : 1, stream))
+    if (int rc = earl_mjkx_redo_pass(h->eng->d_model, sizeof(Model), h->eng->d_hull, &a, sizeof(a), &io, sizeof(io), h->eng->sm_count, stream))
       return rc;
   return 0;
 }

@@ -79,8 +79,8 @@ constexpr float BROAD_SLACK = MJ_BROAD_SLACK;  // inflation of the cached broad 
 #if defined(MJ_CAPSET_KITCHEN_XL)
 // kitchen redo pass (earl_mj_kitchen_xl.cu): the few env steps with a substep beyond the primary set's rows (half a dozen
 // six-dimensional finger contacts at once: 10 rows each) or 24 contacts are re-stepped with these capacities
-constexpr int MAXEFC = 352; // constraint rows
-constexpr int MAXCON = 32;  // contacts
+constexpr int MAXCON = 48;  // contacts (an arm jammed into a cabinet: 33-40 seen in 0.04 % of the env steps of a long random rollout)
+constexpr int MAXEFC = 544; // constraint rows: cannot overflow before the contacts do (6 weld + 5 equality + 23 friction loss + <= 23 limits + 48 x 10)
 #else
 // Device: 112 rows (27.1 KB workspace, 8 environments in flight per SM); the ~0.1 % of env steps with a substep beyond
 // that are re-stepped by the extra-large set.  Measured at 14,208 envs: 192 rows / 6 per SM 1.33e5 env-steps/s, 128 / 7

@@ -31,7 +31,7 @@ EARL_API int earl_mjk_engine_nv(const earl_mjk_engine* e);
  * never moves it), ctrl f32 [N,2] (the engine clamps to ctrlrange).  Out: info i32 [N,4] = { rows of the last substep,
  * contacts of the last substep, Newton iterations summed over the substeps, flags (bit 0 non-positive pivot, bits 1-3
  * capacity overflow: candidate pairs / contacts / rows, bit 4: the primary 112-row set overflowed and the environment was
- * re-run from its input state by the 352-row set -- bits 1-3 then refer to that run) }. */
+ * re-run from its input state by the 544-row set -- bits 1-3 then refer to that run) }. */
 EARL_API int earl_mjk_engine_substeps(earl_mjk_engine* e, int32_t num_envs, int32_t nsub, float* qpos_dev, float* qvel_dev,
                                       float* warm_dev, const double* mocap_pos_dev, const float* mocap_quat_host,
                                       const float* ctrl_dev, int32_t* info_dev, void* stream);
