@@ -50,7 +50,7 @@ def test_substep_parity_and_batch_independence():
     q1, v1, w1 = q.clone(), v.clone(), w.clone()
     info = eng.substeps(q1, v1, w1, mp, c, nsub=4).cpu().numpy()
     # no failure, nothing dropped; the states with many six-dimensional finger contacts outgrow the 112 rows of the primary
-    # set and went through the 352-row set (bit 4) -- the comparison below covers them like any other state
+    # set and went through the 544-row set (bit 4) -- the comparison below covers them like any other state
     assert np.all((info[:, 3] & 15) == 0) and np.any(info[:, 3] & 16) and not np.all(info[:, 3] & 16)
     dq, dv, con = [], [], 0
     for i, (qq, vv, ww, mm, cc) in enumerate(states):
