@@ -173,7 +173,7 @@ def test_same_results_for_any_batch_composition():
 
 
 def test_row_overflow_is_redone_by_the_extra_large_set_not_dropped(monkeypatch):
-    """bench.py's kitchen stream: a dozen env steps in ~10^5 have a substep beyond the 192 rows of the primary set (a handful
+    """bench.py's kitchen stream: ~130 env steps in ~10^5 have a substep beyond the 112 rows of the primary set (a handful
     of six-dimensional finger contacts, 10 rows each).  With the redo pass they are re-stepped by the 544-row set
     (overflow_states stays 0); every environment that never overflowed is bit-identical to the run without it."""
     n, warm, steps = 14208, 30, 8   # bench.py's kitchen section: the arms have to get up to speed first
