@@ -15,6 +15,12 @@
 #define mj mjkx  // engine namespace of this translation unit: no symbol is shared with any other capacity set
 #else
 #define mj mjk
+// the 8 warps of a block keep in phase in two groups of 4 (two named barriers): less waiting for the slowest warp, and the
+// kitchen's phases still fit the instruction caches twice (measured 1.54e5 -> 1.60e5 env-steps/s; the door / peg sets lose
+// 19 % with the same split: their 16 warps per SM want one phase resident)
+#ifndef MJ_BARRIER_DOMAINS
+#define MJ_BARRIER_DOMAINS 2
+#endif
 #endif
 #include "../../include/earl_mj_kitchen_b200.h"
 
@@ -69,6 +75,9 @@ constexpr int kBPS = MJK_BPS;  // resident blocks per SM (each block is one phas
 constexpr size_t kWorkStride = (sizeof(Work) + 15) & ~size_t(15);
 constexpr size_t kSmemBytes = kWPB * kWorkStride;
 static_assert(kBPS * (kSmemBytes + 1024) <= 228 * 1024, "workspaces exceed the shared memory of an SM");
+#if defined(MJ_BARRIER_DOMAINS)
+static_assert(kWPB % MJ_BARRIER_DOMAINS == 0, "barrier domains must divide the warps of a block");
+#endif
 
 // All warps of a block walk the same number of environments and substeps (the engine's phase barriers are block-wide);
 // a warp without an environment of its own shadows the last one and stores nothing.  Primary set: environments whose

@@ -276,7 +276,17 @@ MJ_HD void wsync() {
 template <int NL>
 MJ_HD void bsync() {
 #if defined(__CUDA_ARCH__) && !defined(MJ_NO_PHASE_BARRIERS)
+#if defined(MJ_BARRIER_DOMAINS) && MJ_BARRIER_DOMAINS > 1
+  // the block's warps in MJ_BARRIER_DOMAINS groups, each with its own named barrier (fewer warps to wait for, more phases
+  // resident in the instruction caches at once): used by the kitchen set (earl_mj_kitchen.cu)
+  if (NL > 1) {
+    const unsigned per = (blockDim.x >> 5) / MJ_BARRIER_DOMAINS;
+    const unsigned dom = (threadIdx.x >> 5) / per;
+    if (dom < MJ_BARRIER_DOMAINS) asm volatile("bar.sync %0, %1;" ::"r"(1u + dom), "r"(per * 32u) : "memory");
+  }
+#else
   if (NL > 1) __syncthreads();
+#endif
 #endif
 }
 template <int NL>
