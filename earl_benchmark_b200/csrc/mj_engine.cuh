@@ -251,6 +251,7 @@ struct Work {
   int solver_iter;
   int bad;  // bit 0: numerical failure (non-positive pivot); capacity overflows: bit 1 candidate pairs, bit 2 contacts, bit 3 rows
   int acc_iter, acc_rows, acc_con, acc_mpr, acc_sup;  // summed over the substeps of one env step (acc_sup: support-function calls)
+  int peak_efc, peak_con, peak_hit;                   // largest row / contact / candidate-pair count of a substep of this env step
 #ifdef MJ_PHASE_TIMING
   long long phase[8], phase_t0;     // SM cycles per engine phase (profiling builds only)
 #endif

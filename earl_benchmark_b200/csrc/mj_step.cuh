@@ -60,7 +60,12 @@ MJ_FN void substep(const Model& m, const real* hull, Work& w, int lane) {
   solve<NL>(m, w, lane);
   if (MJ_BSYNC_MASK & 8) bsync<NL>();
   MJ_PHASE_END(w, 6);
-  if (lane == 0) { w.acc_iter += w.solver_iter; w.acc_rows += w.nefc; w.acc_con += w.ncon; }
+  if (lane == 0) {
+    w.acc_iter += w.solver_iter; w.acc_rows += w.nefc; w.acc_con += w.ncon;
+    if (w.nefc > w.peak_efc) w.peak_efc = w.nefc;
+    if (w.ncon > w.peak_con) w.peak_con = w.ncon;
+    if (w.nhit > w.peak_hit) w.peak_hit = w.nhit;
+  }
   // mj_Euler: implicit in joint damping
   const real h = m.timestep;
   for (int i = lane; i < nv; i += NL) {
