@@ -104,7 +104,7 @@ mjk_substeps_kernel(const Model* __restrict__ gm, const real* __restrict__ hull,
       for (int k = 0; k < 3; ++k) w.mocap_pos[k] = mocap_pos[(size_t)env * 3 + k];
       w.mocap_quat[0] = mocap_quat.x; w.mocap_quat[1] = mocap_quat.y; w.mocap_quat[2] = mocap_quat.z; w.mocap_quat[3] = mocap_quat.w;
       for (int k = 0; k < m.nu; ++k) w.ctrl[k] = ctrl[(size_t)env * m.nu + k];
-      w.bad = 0; w.acc_iter = w.acc_rows = w.acc_con = w.acc_mpr = w.acc_sup = 0; w.broad_valid = 0; w.acc_rebuild = 0;
+      w.bad = 0; w.acc_iter = w.acc_rows = w.acc_con = w.acc_mpr = w.acc_sup = 0; w.broad_valid = 0; w.acc_rebuild = 0; w.peak_efc = w.peak_con = w.peak_hit = 0;
     }
     __syncwarp();
     for (int s = 0; s < nsub; ++s) substep<32>(m, hull, w, lane);
@@ -150,6 +150,10 @@ struct TaskArgs {
   long long* redo_list;             // [N] entries (step tag << 32 | env): the tag tells a fresh entry from an older step's
   unsigned* sched;                  // [kRedoCount] listed, [kRedoNext] claimed, [kMainDone] step-kernel blocks finished, [kNextChunk]
   unsigned redo_tag, main_blocks;
+  // an env whose last step outgrew the step kernel's capacities (prim_*) is "heavy": the step kernel hands it to the redo
+  // kernel at the START of its next step (heavy envs lead the visiting order), so that its latency overlaps the step kernel
+  unsigned char* heavy;             // [N]
+  int prim_efc, prim_con, prim_hit;
 };
 enum { kRedoCount = 0, kRedoNext = 1, kMainDone = 2, kNextChunk = 3, kSchedWords = 4 };
 
@@ -234,7 +238,7 @@ __device__ __forceinline__ void task_load(const TaskArgs& a, Work& w, int env, i
   if (lane == 0) {
     for (int k = 0; k < 3; ++k) w.mocap_pos[k] = a.mocap[(size_t)env * 3 + k];
     w.mocap_quat[0] = a.mocap_quat.x; w.mocap_quat[1] = a.mocap_quat.y; w.mocap_quat[2] = a.mocap_quat.z; w.mocap_quat[3] = a.mocap_quat.w;
-    w.bad = 0; w.acc_iter = w.acc_rows = w.acc_con = w.acc_mpr = w.acc_sup = 0; w.broad_valid = 0; w.acc_rebuild = 0;
+    w.bad = 0; w.acc_iter = w.acc_rows = w.acc_con = w.acc_mpr = w.acc_sup = 0; w.broad_valid = 0; w.acc_rebuild = 0; w.peak_efc = w.peak_con = w.peak_hit = 0;
   }
   __syncwarp();
 }
@@ -270,7 +274,7 @@ __device__ __forceinline__ bool task_env(const Model& m, const real* hull, const
     if (lane == 0) {
       for (int k = 0; k < 3; ++k) w.mocap_pos[k] = a.midpoint[k];
       w.mocap_quat[0] = a.mocap_quat.x; w.mocap_quat[1] = a.mocap_quat.y; w.mocap_quat[2] = a.mocap_quat.z; w.mocap_quat[3] = a.mocap_quat.w;
-      w.bad = 0; w.acc_iter = w.acc_rows = w.acc_con = w.acc_mpr = w.acc_sup = 0; w.broad_valid = 0; w.acc_rebuild = 0;
+      w.bad = 0; w.acc_iter = w.acc_rows = w.acc_con = w.acc_mpr = w.acc_sup = 0; w.broad_valid = 0; w.acc_rebuild = 0; w.peak_efc = w.peak_con = w.peak_hit = 0;
     }
     __syncwarp();
   } else {
@@ -326,6 +330,11 @@ __device__ __forceinline__ bool task_env(const Model& m, const real* hull, const
     // estimated warp instructions above the contact-free baseline: loose broad-phase passes (~9k each), extra Newton
     // iterations (~6k), contacts (~1.5k per contact and substep), portal-refinement support calls (~0.3k)
     a.cost[env] = 9000 * w.acc_rebuild + 6000 * (w.acc_iter - a.frame_skip) + 1500 * w.acc_con + 300 * w.acc_sup;
+    if (mode == 2) {
+      const bool heavy = w.peak_efc > a.prim_efc || w.peak_con > a.prim_con || w.peak_hit > a.prim_hit;
+      a.heavy[env] = heavy ? 1 : 0;
+      if (heavy) a.cost[env] = 1 << 30;  // top bucket: visited (and listed) first
+    }
     if (orow) for (int k = 0; k < kObs; ++k) orow[k] = obs[k];
     if (stepping) {
       bool ok;
@@ -355,6 +364,7 @@ __device__ __forceinline__ bool task_env(const Model& m, const real* hull, const
       a.steps_since_reset[env] = 0;                     // PersistentStateWrapper.reset (:17-20)
       a.steps_since_goal_change[env] = 0;               // LifelongWrapper.reset (:25-28)
       a.num_interventions[env] += 1;
+      a.heavy[env] = 0;
     }
     c.it += w.acc_iter; c.rows += w.acc_rows; c.con += w.acc_con; c.bad += (w.bad & 1) ? 1 : 0; c.over += (w.bad & 14) ? 1 : 0; c.env += 1;
     c.ov_hit += (w.bad & 2) ? 1 : 0; c.ov_con += (w.bad & 4) ? 1 : 0; c.ov_row += (w.bad & 8) ? 1 : 0;
@@ -397,7 +407,17 @@ mjk_task_kernel(const Model* __restrict__ gm, const real* __restrict__ hull, con
     const bool own = base + warp < count;
     const int slot = own ? base + warp : count - 1;
     const int env = env_ids ? env_ids[slot] : slot;
-    task_env(*gm, hull, a, io, w, mode, env, slot, own, lane, c);
+    bool heavy = false;
+    if (mode == 0 && a.redo_list) {
+      heavy = own && a.heavy[env];
+      if (heavy && lane == 0) {
+        const unsigned at = atomicAdd(&a.sched[kRedoCount], 1u);
+        *reinterpret_cast<volatile long long*>(a.redo_list + at) = ((long long)a.redo_tag << 32) | (long long)(unsigned)env;
+        __threadfence();
+      }
+      if (__syncthreads_and(heavy || !own)) continue;  // a chunk of heavy envs only: nothing to step here
+    }
+    task_env(*gm, hull, a, io, w, mode, env, slot, own && !heavy, lane, c);
     __syncthreads();
   }
   task_flush(a, c, mode, lane);
@@ -636,6 +656,8 @@ struct earl_mjk_handle {
   int* d_rank = nullptr;
   unsigned* d_counts = nullptr;
   int bucket_width = 60000;  // flat between 40k and 160k (measured); EARL_MJK_BUCKET_WIDTH overrides
+  bool redo_sms_fixed = false;      // EARL_MJ_REDO_SMS given: no adaptation
+  unsigned* h_redo_seen = nullptr;  // pinned: redo-list length of a recent step (async copy, read without waiting)
   int redo_sms = 4;          // SMs the step kernel leaves to the concurrent redo kernel (EARL_MJ_REDO_SMS; measured 2: 1.49e5, 4: 1.54e5, 6: 1.53e5)
   std::vector<void*> owned;
   template <typename T>
@@ -662,7 +684,18 @@ int launch_task(earl_mjk_handle* h, int mode, const int* env_ids, int count, con
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (mode != 0) a.redo_list = nullptr;
   if (a.redo_list) {
-    if (grid == slots && grid > 8 * h->redo_sms * kBPS) grid -= h->redo_sms * kBPS;  // SMs left to the concurrent redo kernel
+    // SMs left to the concurrent redo kernel: enough for the list of a recent step (2 envs per redo block, about one env
+    // step per step-kernel wave)
+    int r = h->redo_sms;
+    if (!h->redo_sms_fixed && h->h_redo_seen) {
+      const unsigned listed = *reinterpret_cast<volatile unsigned*>(h->h_redo_seen);
+      const unsigned waves = (unsigned)((count + kWPB * slots - 1) / (kWPB * slots));
+      const int want = (int)((listed + 2u * waves - 1u) / (2u * waves));
+      r = want > r ? want : r;
+      r = r > h->eng->sm_count / 4 ? h->eng->sm_count / 4 : r;
+    }
+    if (slots > 8 * r * kBPS && blocks + r * kBPS > slots) grid = grid < slots - r * kBPS ? grid : slots - r * kBPS;
+    a.prim_efc = MAXEFC; a.prim_con = MAXCON; a.prim_hit = MAXHIT;
     a.main_blocks = (unsigned)grid;
     a.redo_tag = (unsigned)(h->total_steps & 0x7fffffff);
   }
@@ -720,7 +753,10 @@ int earl_mjk_create(const earl_mjk_config* cfg, const void* model_blob, size_t m
   if (const char* e = getenv("EARL_MJK_BUCKET_WIDTH")) h->bucket_width = atoi(e) > 0 ? atoi(e) : h->bucket_width;
   if (!(getenv("EARL_MJ_REDO") && atoi(getenv("EARL_MJ_REDO")) == 0))
     if ((rc = h->alloc(&a.redo_list, n))) { earl_mjk_destroy(h); return rc; }
-  if (const char* e = getenv("EARL_MJ_REDO_SMS")) { const int r = atoi(e); if (r >= 1 && r < eng->sm_count / 8) h->redo_sms = r; }
+  if (const char* e = getenv("EARL_MJ_REDO_SMS")) { const int r = atoi(e); if (r >= 1 && r < eng->sm_count / 8) { h->redo_sms = r; h->redo_sms_fixed = true; } }
+  if ((rc = h->alloc(&a.heavy, n))) { earl_mjk_destroy(h); return rc; }
+  if (cudaHostAlloc(reinterpret_cast<void**>(&h->h_redo_seen), sizeof(unsigned), cudaHostAllocDefault) == cudaSuccess) *h->h_redo_seen = 0;
+  else { h->h_redo_seen = nullptr; cudaGetLastError(); }
   *out = h;
   return 0;
 }
@@ -729,6 +765,7 @@ int earl_mjk_destroy(earl_mjk_handle* h) {
   if (!h) return 0;
   if (h->eng) cudaSetDevice(h->eng->device);
   for (void* p : h->owned) cudaFree(p);
+  if (h->h_redo_seen) cudaFreeHost(h->h_redo_seen);
   earl_mjk_engine_destroy(h->eng);
   delete h;
   return 0;
@@ -765,6 +802,7 @@ int earl_mjk_step(earl_mjk_handle* h, const float* actions_dev, double* obs_dev,
   mjk_bucket_kernel<<<(h->a.n + 255) / 256, 256, 0, s>>>(h->a.cost, h->a.n, h->bucket_width, h->d_bucket, h->d_rank, h->d_counts);
   mjk_order_kernel<<<64, 256, 0, s>>>(h->d_bucket, h->d_rank, h->a.n, h->d_counts, h->d_order);
   CU(cudaGetLastError());
+  if (h->h_redo_seen && h->a.redo_list) CU(cudaMemcpyAsync(h->h_redo_seen, h->a.sched + kRedoCount, sizeof(unsigned), cudaMemcpyDeviceToHost, s));
   return 0;
 }
 
