@@ -684,17 +684,17 @@ int launch_task(earl_mjk_handle* h, int mode, const int* env_ids, int count, con
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (mode != 0) a.redo_list = nullptr;
   if (a.redo_list) {
-    // SMs left to the concurrent redo kernel: enough for the list of a recent step (2 envs per redo block, about one env
-    // step per step-kernel wave)
+    // SMs left to the concurrent redo kernel: balanced against the list length L of a recent step -- the step kernel walks
+    // (n - L) envs kWPB = 8 per SM, the redo kernel L envs 2 per SM, at about one env step per wave either way:
+    // (n - L) / (8 (S - r)) = L / (2 r)  =>  r = S * 4 L / (n + 3 L); at least redo_sms, at most half of the GPU
     int r = h->redo_sms;
     if (!h->redo_sms_fixed && h->h_redo_seen) {
-      const unsigned listed = *reinterpret_cast<volatile unsigned*>(h->h_redo_seen);
-      const unsigned waves = (unsigned)((count + kWPB * slots - 1) / (kWPB * slots));
-      const int want = (int)((listed + 2u * waves - 1u) / (2u * waves));
+      const double L = (double)*reinterpret_cast<volatile unsigned*>(h->h_redo_seen), S = (double)h->eng->sm_count;
+      const int want = (int)(S * 4.0 * L / ((double)count + 3.0 * L) + 0.5);
       r = want > r ? want : r;
-      r = r > h->eng->sm_count / 4 ? h->eng->sm_count / 4 : r;
+      r = r > h->eng->sm_count / 2 ? h->eng->sm_count / 2 : r;
     }
-    if (slots > 8 * r * kBPS && blocks + r * kBPS > slots) grid = grid < slots - r * kBPS ? grid : slots - r * kBPS;
+    if (slots >= 2 * r * kBPS && blocks + r * kBPS > slots) grid = grid < slots - r * kBPS ? grid : slots - r * kBPS;
     a.prim_efc = MAXEFC; a.prim_con = MAXCON; a.prim_hit = MAXHIT;
     a.main_blocks = (unsigned)grid;
     a.redo_tag = (unsigned)(h->total_steps & 0x7fffffff);
