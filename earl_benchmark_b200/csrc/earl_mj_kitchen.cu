@@ -294,14 +294,22 @@ __device__ __forceinline__ bool task_env(const Model& m, const real* hull, const
   }
   __syncwarp();
   const int nsub = stepping ? a.frame_skip : 10 * a.frame_skip;
-  for (int s = 0; s < nsub; ++s) substep<32>(m, hull, w, lane);
+  // Capacity overflow (step kernel): nothing is stored, the env is listed for the redo pass AT THE SUBSTEP IT HAPPENS IN, so
+  // that its re-step starts while this chunk is still running; the warp then only keeps the phase barriers company.
+  const bool watch = mode == 0 && a.redo_list != nullptr;
+  int s = 0;
+  for (; s < nsub; ++s) {
+    substep<32>(m, hull, w, lane);  // ends with a warp barrier: w.bad (lane 0, collision / row phases) is visible to all lanes
+    if (watch && (w.bad & 14)) break;
+  }
   __syncwarp();
-  if (mode == 0 && a.redo_list && (w.bad & 14)) {  // capacity overflow: nothing is stored, the redo pass takes the env over
+  if (s < nsub) {
     if (own && lane == 0) {
       const unsigned at = atomicAdd(&a.sched[kRedoCount], 1u);
       *reinterpret_cast<volatile long long*>(a.redo_list + at) = ((long long)a.redo_tag << 32) | (long long)(unsigned)env;
       __threadfence();
     }
+    for (++s; s < nsub; ++s) substep_idle<32>();
     return false;
   }
   // A step that left a non-finite state (or whose factorisation broke down) is NOT stored: the environment stays at its

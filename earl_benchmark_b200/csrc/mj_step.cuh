@@ -102,8 +102,19 @@ MJ_FN void substep(const Model& m, const real* hull, Work& w, int lane) {
 // ------------------------------------------------------------------------------------------------ task layer
 // metaworld SawyerXYZEnv.step (set_xyz_action + do_simulation) followed by the EARL observation / sparse reward
 // (reference earl_benchmark/envs/sawyer_door.py:86-94,168-177).  `action` has 4 entries.
+// A warp that has nothing (more) to compute in this substep keeps its block's phase barriers company: exactly the
+// barriers of substep(), nothing else.
 template <int NL>
-MJ_FN void env_step(const Model& m, const real* hull, Work& w, const real* action, int lane) {
+MJ_HD void substep_idle() {
+  if (MJ_BSYNC_MASK & 1) bsync<NL>();
+  if (MJ_BSYNC_MASK & 2) bsync<NL>();
+  if (MJ_BSYNC_MASK & 4) bsync<NL>();
+  if (MJ_BSYNC_MASK & 8) bsync<NL>();
+}
+
+// mocap target and gripper control of one env step (SawyerXYZEnv.set_xyz_action + the gripper effort)
+template <int NL>
+MJ_FN void env_set_action(const Model& m, Work& w, const real* action, int lane) {
   if (lane == 0) {
     for (int k = 0; k < 3; ++k) {
       const double a = (double)clampr(action[k], -1.0f, 1.0f);
@@ -116,6 +127,11 @@ MJ_FN void env_step(const Model& m, const real* hull, Work& w, const real* actio
     w.ctrl[0] = g; w.ctrl[1] = -g;
   }
   wsync<NL>();
+}
+
+template <int NL>
+MJ_FN void env_step(const Model& m, const real* hull, Work& w, const real* action, int lane) {
+  env_set_action<NL>(m, w, action, lane);
   for (int s = 0; s < m.frame_skip; ++s) substep<NL>(m, hull, w, lane);
 }
 
