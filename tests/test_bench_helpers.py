@@ -1,0 +1,26 @@
+"""CPU-side pieces of bench.py that the driver's runs depend on (no GPU): the CPU-oracle leg and the committed measurement of
+the reference's own Python loop that the bench line quotes."""
+import json
+import os
+import sys
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, REPO)
+import bench  # noqa: E402
+
+
+def test_cpu_port_rate_runs_a_sample_of_at_least_the_requested_length():
+    rate, n_sample, seconds, steps = bench.cpu_port_rate(1 << 14, 4, 2, budget_s=2.0, min_wall_s=0.2)
+    assert rate > 1e5 and n_sample == 1 << 14
+    assert steps >= 4 and seconds >= 0.1           # more steps of the same batch until the sample is worth timing
+
+
+def test_reference_python_loop_measurement_is_committed_and_quoted():
+    """SURVEY 8(d) CPU baseline (i): the unmodified reference's own Python loop, measured where /root/reference exists
+    (oracle/ref_python_rate.py) -- the GPU box cannot run it, so the bench line quotes the committed file."""
+    d = json.load(open(os.path.join(REPO, "profiles", "r02", "ref_python_loop_rate.json")))
+    procs = {r["procs"]: r["env_steps_per_s"] for r in d["runs"]}
+    assert set(procs) == {1, 8} and 5e3 < procs[1] < 1e5 and procs[1] < procs[8] < 8 * procs[1] * 1.1
+    q = bench.ref_python_loop()
+    assert q["unit"] == bench.UNIT and [r["procs"] for r in q["runs"]] == [1, 8]
+    assert abs(q["runs"][0]["value"] - procs[1]) < 1e-6
