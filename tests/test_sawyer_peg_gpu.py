@@ -221,3 +221,32 @@ def test_peg_demonstrations_replayed_on_the_device_by_episode():
     assert succ["reverse"] >= 11 and within3["reverse"] >= 18
     assert within3["forward"] + within3["reverse"] >= 28
     assert 1 - mism / total >= 0.99 > 1 - zeros / total
+
+
+def test_redo_scheduling_does_not_change_the_physics(monkeypatch):
+    """Which kernel re-steps an overflowing env, when it is listed (heavy envs at the start of the step, new overflows at the
+    substep they happen in) and how many SMs the redo kernel gets (adapted to the recent list length, or fixed by
+    EARL_MJ_REDO_SMS) are scheduling decisions: the trajectories are bit-identical under any of them."""
+    n, steps = 2048, 60
+    acts = np.random.RandomState(11).uniform(-1, 1, (steps, n, 4)).astype(np.float32)
+    acts[:, :, 2] -= 0.35
+
+    def run(sms):
+        if sms is None:
+            monkeypatch.delenv("EARL_MJ_REDO_SMS", raising=False)
+        else:
+            monkeypatch.setenv("EARL_MJ_REDO_SMS", str(sms))
+        env = sawyer_peg.SawyerPegV2(reward_type="sparse", num_envs=n, device="cuda:0", seed=3)
+        env.reset()
+        rew = []
+        for t in range(steps):
+            o, r, d, _ = env.step(torch.from_numpy(acts[t]).cuda())
+            rew.append(r.clone())
+        return o.clone(), torch.stack(rew), env.get_state(), env.work_counters()
+
+    o0, r0, s0, w0 = run(None)
+    o1, r1, s1, w1 = run(12)
+    assert w0["redone_states"] > 20 and w0["overflow_states"] == 0 and w1["overflow_states"] == 0
+    assert w0["redone_states"] == w1["redone_states"] and w0["newton_iterations"] == w1["newton_iterations"]
+    assert torch.equal(o0, o1) and torch.equal(r0, r1)
+    assert np.array_equal(s0["qpos"], s1["qpos"]) and np.array_equal(s0["qvel"], s1["qvel"])
