@@ -204,3 +204,41 @@ def test_row_overflow_is_redone_by_the_extra_large_set_not_dropped(monkeypatch):
     differ = np.flatnonzero((st0["qpos"] != st1["qpos"]).any(1) | (r0 != r1).any(0))
     assert 1 <= len(differ) <= w1["redone_states"], (len(differ), w1)
     assert np.isfinite(st1["qpos"]).all() and np.isfinite(r1).all()
+
+
+def test_redo_scheduling_does_not_change_the_kitchen_physics(monkeypatch):
+    """Contact-rich scripted policy (every arm driven into the slide-cabinet handle): a fifth of the env steps outgrow the
+    112-row set.  Heavy-env routing, listing at the overflowing substep and the number of SMs left to the redo kernel are
+    scheduling decisions: observations, rewards and states are bit-identical whether that number adapts or is fixed."""
+    n, steps = 592, 70
+    k = kitchen.REWARD_SITES.index("slide_site")
+
+    def run(sms):
+        if sms is None:
+            monkeypatch.delenv("EARL_MJ_REDO_SMS", raising=False)
+        else:
+            monkeypatch.setenv("EARL_MJ_REDO_SMS", str(sms))
+        env = kitchen.Kitchen(num_envs=n, device="cuda:0", seed=4)
+        env.seed(4)
+        env.reset()
+        gen = torch.Generator(device="cuda:0")
+        gen.manual_seed(8)
+        rew = []
+        for t in range(steps):
+            st = env.get_state()
+            d = torch.from_numpy(st["site_xpos"][:, k] - st["mocap_pos"]).to("cuda:0", torch.float32)
+            u = torch.zeros((n, 9), device="cuda:0")
+            u[:, :3] = torch.clamp(d * 10, -1, 1) * 0.5
+            u += 0.1 * (torch.rand((n, 9), generator=gen, device="cuda:0") * 2 - 1)
+            ob, r, dn, info = env.step(u)
+            rew.append(r.clone())
+        return ob.clone(), torch.stack(rew), env.get_state(), env.work_counters()
+
+    o0, r0, s0, w0 = run(None)
+    o1, r1, s1, w1 = run(6)
+    if w0["redone_states"] == 0:
+        pytest.skip("the scripted reach no longer outgrows the primary capacity set")
+    assert w0["overflow_states"] == 0 and w1["overflow_states"] == 0 and w0["bad_states"] == 0
+    assert w0["redone_states"] == w1["redone_states"] and w0["newton_iterations"] == w1["newton_iterations"]
+    assert torch.equal(o0, o1) and torch.equal(r0, r1)
+    assert np.array_equal(s0["qpos"], s1["qpos"]) and np.array_equal(s0["qvel"], s1["qvel"])
