@@ -37,9 +37,9 @@ def sawyer_peg():
 
 
 def kitchen():
-    """Franka kitchen (ENV/kitchen.py -> adept_envs KitchenV0.MODEl).  The weld keeps MuJoCo's documented regulariser
-    (the 3.35 calibration of the Sawyer welds comes from metaworld demonstrations and does not transfer) and the
-    compiler's default relative pose (kitchen never calls reset_mocap_welds)."""
+    """Franka kitchen (ENV/kitchen.py -> adept_envs KitchenV0.MODEl).  The weld follows the same derived rule as the
+    Sawyer welds (all six rows on the translational body_invweight0, scale 1.0: DESIGN 8.4; round 1's fitted 3.35 is gone)
+    and keeps the compiler's default relative pose (kitchen never calls reset_mocap_welds)."""
     spec = parser.load(os.path.join(REF, "earl_benchmark/envs/kitchen_assets/adept_envs/adept_envs/franka/assets",
                                     "franka_kitchen_jntpos_act_ab.xml"))
     return C.compile_model(spec, weld_tran_scale=1.0, weld_relpose="qpos0",
