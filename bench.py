@@ -163,18 +163,26 @@ def door_cpu_rate(procs, steps_per_proc=20000, task="sawyer_door"):
 
 
 
-def ncu_engine_summary():
-    """A few figures of the committed `ncu --set full` capture of the step kernel (profiles/r02/prof_door_steady_16k_r02.raw.csv:
-    sawyer_door, 16,384 envs, steady regime) -- read from the file, never typed in; None when the file is not there."""
+ENGINE_CAPTURES = {
+    "sawyer_door": ("prof_door_steady_16k_r02.raw.csv", "sawyer_door, 16,384 envs, steady regime, serial-redo build of round 2"),
+    "sawyer_peg": ("prof_peg_steady_16k_final.raw.csv", "sawyer_peg, 16,384 envs, env step 105 of the rollout, final build of round 2"),
+}
+
+
+def ncu_engine_summary(task="sawyer_door"):
+    """A few figures of the committed `ncu --set full` capture of the step kernel on this task (profiles/r02/, ENGINE_CAPTURES)
+    -- read from the file, never typed in; None when the file is not there."""
     import csv
-    path = os.path.join(REPO, "profiles", "r02", "prof_door_steady_16k_r02.raw.csv")
+    fname, what = ENGINE_CAPTURES[task]
+    path = os.path.join(REPO, "profiles", "r02", fname)
     try:
         rows = list(csv.reader(open(path)))
         hdr, val = rows[0], rows[2]
         g = lambda k: float(val[hdr.index(k)].replace(",", ""))  # noqa: E731
-        return {"source": "profiles/r02/prof_door_steady_16k_r02.raw.csv (sawyer_door, 16,384 envs, steady regime; not this run)",
+        return {"source": f"profiles/r02/{fname} ({what}; not this run)",
                 "executed_ipc": g("sm__inst_executed.avg.per_cycle_active"),
                 "achieved_occupancy_pct": g("sm__warps_active.avg.pct_of_peak_sustained_active"),
+                "issue_slots_busy_pct": g("smsp__issue_active.avg.pct_of_peak_sustained_active"),
                 "active_lanes_per_instruction": g("smsp__thread_inst_executed_per_inst_executed.ratio"),
                 "registers_per_thread": g("launch__registers_per_thread"), "kernel_ms": g("gpu__time_duration.sum")}
     except Exception:
@@ -260,7 +268,7 @@ def run_door(dev, rank, world, sm_max_mhz, sm_count, with_cpu, task="sawyer_door
                "kernel": "mj_step_kernel (one warp per env, 16 envs per SM in flight, small capacity set) + concurrent mj_redo_kernel "
                          "(extra-large capacity set, re-steps capacity overflows) + mj_order_kernel (visiting order, <4 us)",
                "redone_states": w1.get("redone_states", 0) - w0.get("redone_states", 0),
-               "ncu": ncu_engine_summary()}
+               "ncu": ncu_engine_summary(task)}
         if with_cpu:
             procs = os.cpu_count() or 1
             rate, flops, wall = door_cpu_rate(procs, task=task)

@@ -24,3 +24,14 @@ def test_reference_python_loop_measurement_is_committed_and_quoted():
     q = bench.ref_python_loop()
     assert q["unit"] == bench.UNIT and [r["procs"] for r in q["runs"]] == [1, 8]
     assert abs(q["runs"][0]["value"] - procs[1]) < 1e-6
+
+
+def test_engine_sections_cite_their_own_committed_ncu_capture():
+    """bench.py's sawyer_door / sawyer_peg sections quote figures READ from the committed ncu captures (profiles/r02/), one per
+    task; a renamed or missing file would silently drop the block."""
+    import bench
+    for task in ("sawyer_door", "sawyer_peg"):
+        s = bench.ncu_engine_summary(task)
+        assert s is not None and bench.ENGINE_CAPTURES[task][0] in s["source"] and task in s["source"]
+        assert s["registers_per_thread"] == 128 and 20 < s["achieved_occupancy_pct"] <= 25.1
+        assert 0 < s["executed_ipc"] < 4 and 16 < s["active_lanes_per_instruction"] <= 32
