@@ -793,7 +793,7 @@ def run_ours(args):
                 "data": "synthetic", "config": config_dict(args, n_total),
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d * world,
                         "d2h_bytes_per_step": d2h * world, "steps": e2e_steps, "reps": e2e_reps,
-                        "api": "PersistentStateWrapper.step(pinned host actions) -> host obs/reward/done/success",
+                        "api": "PersistentStateWrapper.step(pinned host actions) -> host obs/reward/done/success (earl_step_host: the step kernel reads / writes the pinned host buffers over PCIe itself; EARL_TT_HOST_ZEROCOPY=0 = staged copy pipeline)",
                         "pcie_ceiling": ceiling,
                         "frac_of_pcie_ceiling": (e2e_value / ceiling["value"]) if ceiling else None},
                 "gpu_launches": launches,

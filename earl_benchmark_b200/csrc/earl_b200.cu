@@ -70,6 +70,7 @@ struct earl_handle {
   bool pdl = true;        // EARL_TT_PDL=0 disables programmatic dependent launch between consecutive steps
   int host_chunks = 0;    // EARL_TT_HOST_CHUNKS: chunks of the host-buffer pipeline (0 = one per 256k envs, at most 16)
   bool host_tail = true;  // EARL_TT_HOST_TAIL=0: copy reward / done / success per chunk instead of once per step
+  int host_zerocopy = 1;  // EARL_TT_HOST_ZEROCOPY=0: staged copy pipeline instead of the step kernel reading / writing the pinned host buffers itself
   int tma_grid = 0;
   int tma_tile = 256;
   size_t tma_smem = 0;
@@ -353,6 +354,7 @@ int earl_create(const earl_config* cfg, const void* model_blob, size_t model_nby
   if (const char* v = getenv("EARL_TT_PDL")) h->pdl = atoi(v) != 0;
   if (const char* v = getenv("EARL_TT_HOST_CHUNKS")) h->host_chunks = atoi(v);
   if (const char* v = getenv("EARL_TT_HOST_TAIL")) h->host_tail = atoi(v) != 0;
+  if (const char* v = getenv("EARL_TT_HOST_ZEROCOPY")) h->host_zerocopy = atoi(v);
   if (fast && !f64(h) && (h->variant == 8 || h->variant == 6)) {
     rc = h->variant == 8 ? occupancy_grid(earl::tabletop_step_kernel<false, true, 8>, h->sm_count, &h->step_grid)
                          : occupancy_grid(earl::tabletop_step_kernel<false, true, 6>, h->sm_count, &h->step_grid);
@@ -470,10 +472,59 @@ int earl_rollout(earl_handle* h, const float* actions_dev, int32_t action_ring, 
   return note_stream(h, s);
 }
 
+}  // extern "C"
+namespace {
+// device alias of a pinned, mapped host buffer (cudaHostAlloc / cudaHostRegister under unified addressing); null otherwise
+template <class T>
+T* mapped_alias(T* host) {
+  cudaPointerAttributes at{};
+  if (cudaPointerGetAttributes(&at, host) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  return at.type == cudaMemoryTypeHost ? static_cast<T*>(at.devicePointer) : nullptr;
+}
+
+// Zero-copy host step: the one-tile-per-CTA kernel reads the actions from, and writes observations / reward / done / success
+// to, the caller's pinned host buffers directly -- full-line coalesced float4 traffic over PCIe in both directions at once,
+// no staging copies, no chunk pipeline, one launch.  Only for the FAST configuration and mapped, 16-byte aligned buffers.
+bool step_host_zerocopy(earl_handle* h, const float* actions_host, float* obs_host, float* reward_host, uint8_t* done_host,
+                        uint8_t* success_host, int* rc_out) {
+  if (!h->host_zerocopy || !fast_path(h) || f64(h)) return false;
+  const float* a = mapped_alias(actions_host);
+  float* o = mapped_alias(obs_host);
+  float* r = mapped_alias(reward_host);
+  uint8_t* d = mapped_alias(done_host);
+  uint8_t* su = success_host ? mapped_alias(success_host) : nullptr;
+  if (!a || !o || !r || !d || (success_host && !su) || ((uintptr_t)o & 15u) || ((uintptr_t)a & 15u)) return false;
+  if (!h->host_stream) return false;
+  cudaStream_t so = h->host_stream;
+  auto run = [&]() -> int {
+    if (h->order_pending) {
+      CU(cudaStreamWaitEvent(so, h->order_ev, 0));
+      if (h->in_stream) CU(cudaStreamWaitEvent(h->in_stream, h->order_ev, 0));
+      h->order_pending = false;
+    }
+    const int variant = h->variant;
+    h->variant = 5;
+    const int rc = launch_step_range(h, 0, h->p.n, a, o, r, d, su, so);
+    h->variant = variant;
+    if (rc) return rc;
+    h->total_steps += 1;
+    CU(cudaStreamSynchronize(so));
+    return 0;
+  };
+  *rc_out = run();
+  return true;
+}
+}  // namespace
+extern "C" {
+
 int earl_step_host(earl_handle* h, const float* actions_host, float* obs_host, float* reward_host, uint8_t* done_host,
                    uint8_t* success_host) {
   if (int rc = check_handle(h)) return rc;
   if (!actions_host || !obs_host || !reward_host || !done_host) return fail(EARL_ERR_INVALID, "null host buffer");
+  {
+    int rc = 0;
+    if (step_host_zerocopy(h, actions_host, obs_host, reward_host, done_host, success_host, &rc)) return rc;
+  }
   const size_t n = (size_t)h->p.n;
   if (!h->d_act) {
     int rc = h->alloc(&h->d_act, n * earl::kTTAct, false);

@@ -310,10 +310,15 @@ __global__ void __launch_bounds__(kTTBlock, MINB) tabletop_step_kernel(const Tab
 // gcd(3, 8) = 1).  This is the design that reached 0.98 of the HBM copy peak on the three-object task (csrc/earl_tt3.cu);
 // it replaces the cp.async.bulk pipeline (0.93-0.95) and the persistent LSU kernel (0.87-0.88) above ~3M envs, where
 // nothing is L2-resident.
-__global__ void __launch_bounds__(kTTBlock) tabletop_step_tile_kernel(const __grid_constant__ TabletopParams p) {
+__global__ void __launch_bounds__(kTTBlock, 8) tabletop_step_tile_kernel(const __grid_constant__ TabletopParams p) {
   __shared__ float4 s_obs[kTTBlock * 3];
   __shared__ float4 s_act4[kTTBlock * kTTAct / 4];
+  __shared__ float4 s_rew4[kTTBlock / 4];
+  __shared__ uint4 s_done16[kTTBlock / 16], s_succ16[kTTBlock / 16];
   float* s_act = reinterpret_cast<float*>(s_act4);
+  float* s_rew = reinterpret_cast<float*>(s_rew4);
+  uint8_t* s_done = reinterpret_cast<uint8_t*>(s_done16);
+  uint8_t* s_succ = reinterpret_cast<uint8_t*>(s_succ16);
   const int t = threadIdx.x;
   const int base = p.first + blockIdx.x * kTTBlock;
   const int i = base + t;
@@ -345,9 +350,9 @@ __global__ void __launch_bounds__(kTTBlock) tabletop_step_tile_kernel(const __gr
     const bool succ = tt_success(pos32, g0, wide, p.success_sq);
     steps = steps == 0xffffffffu ? steps : steps + 1u;   // PersistentStateWrapper.step (persistent_state_wrapper.py:25-29)
     tt_store_state<false>(p, i, s, pos32, steps);
-    __stcs(p.reward + i, succ ? 1.f : 0.f);
-    p.done[i] = (unsigned long long)steps >= p.horizon ? 1 : 0;
-    if (p.success) p.success[i] = succ ? 1 : 0;
+    s_rew[t] = succ ? 1.f : 0.f;
+    s_done[t] = (unsigned long long)steps >= p.horizon ? 1 : 0;
+    s_succ[t] = succ ? 1 : 0;
     const float att = (s.flags & kAttached) ? 0.f : -1.f;
     s_obs[3 * t] = pos32;                                  // tabletop_manipulation.py:55-60
     s_obs[3 * t + 1] = make_float4(att, att, g0.x, g0.y);
@@ -359,6 +364,21 @@ __global__ void __launch_bounds__(kTTBlock) tabletop_step_tile_kernel(const __gr
   for (int k = 0; k < 3; ++k) {
     const int idx = t + kTTBlock * k;
     if (idx < rows * 3) __stcs(dst + idx, s_obs[idx]);
+  }
+  // reward (4 B), done and success (1 B per env) leave as 16-byte vectors too: a whole tile is 1 KB + 256 B + 256 B of
+  // contiguous full lines instead of 32-byte warp stores -- what a PCIe link wants when the outputs are pinned host memory
+  // (earl_step_host, zero-copy path), and fewer store instructions on HBM.  Ragged tile or unaligned buffers: one env each.
+  const bool vec = rows == kTTBlock &&
+                   !((reinterpret_cast<uintptr_t>(p.reward) | reinterpret_cast<uintptr_t>(p.done) | reinterpret_cast<uintptr_t>(p.success)) & 15u);
+  if (vec) {
+    if (t < kTTBlock / 4) __stcs(reinterpret_cast<float4*>(p.reward + base) + t, s_rew4[t]);
+    else if (t < kTTBlock / 4 + kTTBlock / 16) __stcs(reinterpret_cast<uint4*>(p.done + base) + (t - kTTBlock / 4), s_done16[t - kTTBlock / 4]);
+    else if (t < kTTBlock / 4 + kTTBlock / 8 && p.success)
+      __stcs(reinterpret_cast<uint4*>(p.success + base) + (t - kTTBlock / 4 - kTTBlock / 16), s_succ16[t - kTTBlock / 4 - kTTBlock / 16]);
+  } else if (i < p.n) {
+    __stcs(p.reward + i, s_rew[t]);
+    p.done[i] = s_done[t];
+    if (p.success) p.success[i] = s_succ[t];
   }
 }
 

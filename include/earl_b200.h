@@ -151,9 +151,12 @@ EARL_API int earl_step(earl_handle* h, const float* actions_dev, float* obs_dev,
 EARL_API int earl_rollout(earl_handle* h, const float* actions_dev, int32_t action_ring, int32_t num_steps, float* obs_dev,
                  float* reward_dev, uint8_t* done_dev, uint8_t* success_dev, int32_t out_ring, void* stream);
 
-/* Same step with HOST buffers: host->device copy of the actions, the kernel, device->host copies of
- * obs/reward/done(/success), then a synchronise.  Pinned host memory gives full PCIe speed; pageable
- * memory works.  This is the call a CPU-side RL loop makes. */
+/* Same step with HOST buffers, then a synchronise.  This is the call a CPU-side RL loop makes.
+ * Pinned (mapped) 16-byte aligned buffers on the sparse fp32-state configuration: ONE launch of the
+ * one-tile-per-CTA step kernel that reads the actions from and writes obs/reward/done(/success) to the
+ * host buffers itself, full 128-byte lines over PCIe in both directions at once (no staging copies;
+ * EARL_TT_HOST_ZEROCOPY=0 turns it off).  Otherwise: chunked pipeline of host->device copy, kernel,
+ * device->host copies; pageable memory works there. */
 EARL_API int earl_step_host(earl_handle* h, const float* actions_host, float* obs_host, float* reward_host,
                    uint8_t* done_host, uint8_t* success_host);
 

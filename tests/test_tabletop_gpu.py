@@ -625,3 +625,29 @@ def test_lifelong_goal_stream_covers_the_horizon():
     env.reset()
     base = env.env.env if hasattr(env.env, "env") else env.env
     assert base._goal_stream.shape[0] >= 127
+
+
+@pytest.mark.parametrize("n", [2051, 300000])
+def test_zero_copy_host_step_equals_the_copy_pipeline_and_the_device_path(monkeypatch, n):
+    """EARL_TT_HOST_ZEROCOPY=1: the one-tile-per-CTA step kernel reads the pinned host actions and writes the pinned host
+    outputs itself (no staging copies).  Same observations, rewards, done / success flags and state as the chunked copy
+    pipeline and as the device-resident step, bit for bit, on a ragged and on a multi-chunk batch."""
+    steps = 12
+    acts = actions(n, steps, seed=31, grip_bias=0.3)
+    monkeypatch.setenv("EARL_TT_HOST_ZEROCOPY", "1")
+    z = make(n, 7)
+    monkeypatch.setenv("EARL_TT_HOST_ZEROCOPY", "0")
+    c, d = make(n, 7), make(n, 7)
+    for e in (z, c, d):
+        e.reset()
+    for t in range(steps):
+        zo, zr, zd, zi = z.step(acts[t])
+        co, cr, cd, ci = c.step(acts[t])
+        do, dr, dd, di = d.step(torch.from_numpy(acts[t]).to(DEV))
+        assert isinstance(zo, np.ndarray)
+        assert np.array_equal(zo, co) and np.array_equal(zr, cr) and np.array_equal(zd, cd) and np.array_equal(zi["success"], ci["success"]), t
+        assert np.array_equal(zo, np_(do)) and np.array_equal(zr, np_(dr)) and np.array_equal(zd, np_(dd)), t
+    assert zd.all()                                                      # the horizon (7) was crossed inside the run
+    sz, sd = z.env.get_state(), d.env.get_state()
+    for k in sz:
+        assert np.array_equal(np.asarray(sz[k]), np.asarray(sd[k])), k
