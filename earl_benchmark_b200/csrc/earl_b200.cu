@@ -70,6 +70,7 @@ struct earl_handle {
   bool pdl = true;        // EARL_TT_PDL=0 disables programmatic dependent launch between consecutive steps
   int host_chunks = 0;    // EARL_TT_HOST_CHUNKS: chunks of the host-buffer pipeline (0 = one per 256k envs, at most 16)
   bool host_tail = true;  // EARL_TT_HOST_TAIL=0: copy reward / done / success per chunk instead of once per step
+  bool tile_vec = false;  // set around the zero-copy launch: tile kernel with 16-byte vector stores for reward / done / success
   int host_zerocopy = 1;  // EARL_TT_HOST_ZEROCOPY=0: staged copy pipeline instead of the step kernel reading / writing the pinned host buffers itself
   int tma_grid = 0;
   int tma_tile = 256;
@@ -211,7 +212,8 @@ int launch_step_range(earl_handle* h, int first, int count, const float* actions
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at;
     cfg.numAttrs = h->pdl ? 1 : 0;
-    CU(cudaLaunchKernelEx(&cfg, earl::tabletop_step_tile_kernel, p));
+    if (h->tile_vec) CU(cudaLaunchKernelEx(&cfg, earl::tabletop_step_tile_kernel<true>, p));
+    else CU(cudaLaunchKernelEx(&cfg, earl::tabletop_step_tile_kernel<false>, p));
     h->launches += 1;
     return 0;
   }
@@ -504,8 +506,10 @@ bool step_host_zerocopy(earl_handle* h, const float* actions_host, float* obs_ho
     }
     const int variant = h->variant;
     h->variant = 5;
+    h->tile_vec = true;
     const int rc = launch_step_range(h, 0, h->p.n, a, o, r, d, su, so);
     h->variant = variant;
+    h->tile_vec = false;
     if (rc) return rc;
     h->total_steps += 1;
     CU(cudaStreamSynchronize(so));
