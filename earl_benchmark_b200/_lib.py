@@ -76,6 +76,7 @@ SIGNATURES = [
     ("earl_step", C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP, _VP]),
     ("earl_rollout", C.c_int, [_VP, _VP, _I32, _I32, _VP, _VP, _VP, _VP, _I32, _VP]),
     ("earl_step_host", C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP]),
+    ("earl_set_host_zerocopy", C.c_int, [_VP, _I32]),
     ("earl_get_obs", C.c_int, [_VP, _VP, _VP]),
     ("earl_compute_reward", C.c_int, [_VP, _VP, _I64, _VP, _VP, _VP]),
     ("earl_counters", C.c_int, [_VP, C.POINTER(_I64), _VP, _VP, _VP, _VP]),

@@ -585,6 +585,12 @@ int earl_step_host(earl_handle* h, const float* actions_host, float* obs_host, f
   return 0;
 }
 
+int earl_set_host_zerocopy(earl_handle* h, int32_t enable) {
+  if (int rc = check_handle(h)) return rc;
+  h->host_zerocopy = enable ? 1 : 0;
+  return 0;
+}
+
 int earl_get_obs(earl_handle* h, float* obs_dev, void* stream) {
   if (int rc = check_handle(h)) return rc;
   if (!obs_dev || ((uintptr_t)obs_dev & 15u)) return fail(EARL_ERR_INVALID, "obs must be non-null and 16-byte aligned");

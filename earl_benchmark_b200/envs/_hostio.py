@@ -40,3 +40,30 @@ class HostBuffers:
     @staticmethod
     def as_numpy(ho, hr, hd, hs):
         return ho.numpy(), hr.numpy(), hd.numpy().view(np.bool_), {"success": hs.numpy().view(np.bool_)}
+
+
+def ranks_on_this_host():
+    """How many processes of this job drive a GPU from this host (torchrun's LOCAL_WORLD_SIZE / WORLD_SIZE, or the initialised
+    process group): they share the host's PCIe root complex and memory bandwidth."""
+    import os
+    for key in ("LOCAL_WORLD_SIZE", "WORLD_SIZE"):
+        v = os.environ.get(key)
+        if v and v.isdigit():
+            return max(1, int(v))
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            return dist.get_world_size()
+    except Exception:
+        pass
+    return 1
+
+
+def host_zerocopy_default():
+    """Policy behind earl_set_host_zerocopy (include/earl_b200.h): None = EARL_TT_HOST_ZEROCOPY decides (read by the library),
+    else 1 when this process has the host to itself and 0 when several ranks share it (measured: DESIGN.md section 4)."""
+    import os
+    if os.environ.get("EARL_TT_HOST_ZEROCOPY") is not None:
+        return None
+    return 1 if ranks_on_this_host() == 1 else 0
+

@@ -18,6 +18,7 @@ import numpy as np
 import torch
 
 from .. import _lib, rng
+from . import _hostio
 from ._hostio import HostBuffers
 from ..spaces import Box
 
@@ -178,6 +179,9 @@ class TabletopManipulation:
         h = C.c_void_p()
         _lib.check(L.earl_create(C.byref(cfg), C.byref(blob), C.sizeof(blob), C.byref(h)))
         self._handle = h
+        zc = _hostio.host_zerocopy_default()
+        if zc is not None:
+            _lib.check(L.earl_set_host_zerocopy(h, zc))
         # goal stream: draw e of (global) env j = stream[e * total_envs + j]
         stream = rng.PyRandom(self._seed).tabletop_goal_rows(self._goal_stream_rows * self._total_envs,
                                                              self._task_to_row)

@@ -160,6 +160,13 @@ EARL_API int earl_rollout(earl_handle* h, const float* actions_dev, int32_t acti
 EARL_API int earl_step_host(earl_handle* h, const float* actions_host, float* obs_host, float* reward_host,
                    uint8_t* done_host, uint8_t* success_host);
 
+/* Chooses how earl_step_host moves data when the buffers allow both: 1 = the step kernel reads / writes the pinned host
+ * buffers itself (best when this process has the host's PCIe / memory bandwidth to itself: +4 % at 1M envs, +30 % at 64k),
+ * 0 = staged copy pipeline (measured better when several ranks share one host: 2 GPUs 0.99 vs 0.96 of the concurrent
+ * ceiling).  Default 1 unless EARL_TT_HOST_ZEROCOPY says otherwise; the Python host side sets 0 when the job has more than
+ * one rank on the node.  Results are identical either way. */
+EARL_API int earl_set_host_zerocopy(earl_handle* h, int32_t enable);
+
 /* env._get_obs() (tabletop_manipulation.py:55-60) for all envs. */
 EARL_API int earl_get_obs(earl_handle* h, float* obs_dev, void* stream);
 

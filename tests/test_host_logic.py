@@ -219,3 +219,19 @@ def test_three_object_env_host_side_contract():
     assert w.env._episode_horizon == 123
     with pytest.raises(ValueError):
         LifelongWrapper(t3.TabletopManipulation(num_envs=2), 400)
+
+
+def test_host_zerocopy_policy_follows_the_ranks_on_this_host(monkeypatch):
+    """earl_set_host_zerocopy's Python side: alone on the host -> the step kernel drives the pinned buffers itself; several
+    ranks on the node (torchrun) -> staged copy pipeline; EARL_TT_HOST_ZEROCOPY set -> the library's own reading decides."""
+    from earl_benchmark_b200.envs import _hostio
+    for k in ("LOCAL_WORLD_SIZE", "WORLD_SIZE", "EARL_TT_HOST_ZEROCOPY"):
+        monkeypatch.delenv(k, raising=False)
+    assert _hostio.ranks_on_this_host() == 1 and _hostio.host_zerocopy_default() == 1
+    monkeypatch.setenv("WORLD_SIZE", "8")
+    assert _hostio.ranks_on_this_host() == 8 and _hostio.host_zerocopy_default() == 0
+    monkeypatch.setenv("LOCAL_WORLD_SIZE", "1")                          # 8 nodes x 1 GPU: nobody shares this host
+    assert _hostio.host_zerocopy_default() == 1
+    monkeypatch.setenv("LOCAL_WORLD_SIZE", "2")
+    monkeypatch.setenv("EARL_TT_HOST_ZEROCOPY", "1")
+    assert _hostio.host_zerocopy_default() is None
