@@ -163,6 +163,16 @@ def door_cpu_rate(procs, steps_per_proc=20000, task="sawyer_door"):
 
 
 
+def host_path_note():
+    """Which of earl_step_host's two data paths this process uses (earl_set_host_zerocopy, envs/_hostio.py)."""
+    from earl_benchmark_b200.envs import _hostio
+    zc = _hostio.host_zerocopy_default()
+    if zc is None:
+        zc = int(os.environ.get("EARL_TT_HOST_ZEROCOPY", "1") != "0")
+    return ("the step kernel reads / writes the pinned host buffers over PCIe itself, one launch per step" if zc else
+            "staged pipeline of host->device copy, kernel, device->host copies (several ranks share this host)")
+
+
 ENGINE_CAPTURES = {
     "sawyer_door": ("prof_door_steady_16k_r02.raw.csv", "sawyer_door, 16,384 envs, steady regime, serial-redo build of round 2"),
     "sawyer_peg": ("prof_peg_steady_16k_final.raw.csv", "sawyer_peg, 16,384 envs, env step 105 of the rollout, final build of round 2"),
@@ -793,7 +803,7 @@ def run_ours(args):
                 "data": "synthetic", "config": config_dict(args, n_total),
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d * world,
                         "d2h_bytes_per_step": d2h * world, "steps": e2e_steps, "reps": e2e_reps,
-                        "api": "PersistentStateWrapper.step(pinned host actions) -> host obs/reward/done/success (earl_step_host: the step kernel reads / writes the pinned host buffers over PCIe itself; EARL_TT_HOST_ZEROCOPY=0 = staged copy pipeline)",
+                        "api": "PersistentStateWrapper.step(pinned host actions) -> host obs/reward/done/success (earl_step_host: " + host_path_note() + ")",
                         "pcie_ceiling": ceiling,
                         "frac_of_pcie_ceiling": (e2e_value / ceiling["value"]) if ceiling else None},
                 "gpu_launches": launches,

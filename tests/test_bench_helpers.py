@@ -35,3 +35,14 @@ def test_engine_sections_cite_their_own_committed_ncu_capture():
         assert s is not None and bench.ENGINE_CAPTURES[task][0] in s["source"] and task in s["source"]
         assert s["registers_per_thread"] == 128 and 20 < s["achieved_occupancy_pct"] <= 25.1
         assert 0 < s["executed_ipc"] < 4 and 16 < s["active_lanes_per_instruction"] <= 32
+
+
+def test_bench_names_the_host_data_path_it_measured(monkeypatch):
+    import bench
+    for k in ("LOCAL_WORLD_SIZE", "WORLD_SIZE", "EARL_TT_HOST_ZEROCOPY"):
+        monkeypatch.delenv(k, raising=False)
+    assert "one launch per step" in bench.host_path_note()
+    monkeypatch.setenv("WORLD_SIZE", "4")
+    assert "staged pipeline" in bench.host_path_note()
+    monkeypatch.setenv("EARL_TT_HOST_ZEROCOPY", "1")
+    assert "one launch per step" in bench.host_path_note()
