@@ -30,9 +30,16 @@ def _worker(rank, world, port, n_total, rows, out_dir):
     stats = torch.tensor([ret, float(hi - lo) * 0.5, float(hi - lo) * 0.75, float(hi - lo)], dtype=torch.float64)
     res = all_reduce_eval_stats(stats)
     slow = max_over_ranks(10.0 + rank)
+    # ranks sharing one host keep the staged copy pipeline of the host step (earl_set_host_zerocopy, envs/_hostio.py)
+    from earl_benchmark_b200.envs import _hostio
+    os.environ.pop("EARL_TT_HOST_ZEROCOPY", None)
+    policy = _hostio.host_zerocopy_default()
+    os.environ.pop("WORLD_SIZE")                       # no launcher variables: the initialised process group answers
+    os.environ.pop("LOCAL_WORLD_SIZE", None)
+    ranks = _hostio.ranks_on_this_host()
     if rank == 0:
         np.save(os.path.join(out_dir, "res.npy"), np.array([res["mean_return"], res["success_rate"], res["success_any_rate"],
-                                                             res["num_envs"], slow]))
+                                                             res["num_envs"], slow, policy, ranks]))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -46,6 +53,7 @@ def test_world_size_2_gloo(tmp_path):
     res = np.load(tmp_path / "res.npy")
     assert res[3] == n_total and abs(res[0] - np.arange(n_total).sum() / n_total) < 1e-12
     assert abs(res[1] - 0.5) < 1e-12 and abs(res[2] - 0.75) < 1e-12 and res[4] == 11.0
+    assert res[5] == 0 and res[6] == world             # two ranks on this host: staged pipeline for the host step
 
 
 def test_single_process_degenerate_path():
