@@ -176,6 +176,7 @@ def host_path_note():
 ENGINE_CAPTURES = {
     "sawyer_door": ("prof_door_steady_16k_r02.raw.csv", "sawyer_door, 16,384 envs, steady regime, serial-redo build of round 2"),
     "sawyer_peg": ("prof_peg_steady_16k_final.raw.csv", "sawyer_peg, 16,384 envs, env step 105 of the rollout, final build of round 2"),
+    "kitchen": ("prof_kitchen_steady_4736_r02.raw.csv", "kitchen, 4,736 envs, env step 32 of the rollout, two barrier domains"),
 }
 
 
@@ -354,7 +355,8 @@ def run_kitchen(dev, rank, world, sm_max_mhz, sm_count, with_cpu):
                         "overflow_states": w1["overflow_states"] - w0["overflow_states"],
                         "redone_states": w1["redone_states"] - w0["redone_states"]},
                "kernel": "mjk_task_kernel (one warp per env, 8 envs per SM in flight, 112-row workspaces, model tables in global memory, cost-sorted visiting order, dynamic chunks) "
-                         "+ mjk_redo_kernel (544-row set, concurrent on four reserved SMs plus every SM the step kernel vacates: the ~0.1 % of env steps that outgrew 112 rows / 24 contacts)"}
+                         "+ mjk_redo_kernel (544-row set, concurrent on four reserved SMs plus every SM the step kernel vacates: the ~0.1 % of env steps that outgrew 112 rows / 24 contacts)",
+               "ncu": ncu_engine_summary("kitchen")}
         if with_cpu:
             procs = os.cpu_count() or 1
             rate, flops, wall = door_cpu_rate(procs, steps_per_proc=1500, task="kitchen")
@@ -366,8 +368,8 @@ def run_kitchen(dev, rank, world, sm_max_mhz, sm_count, with_cpu):
             out["roofline"] = {"bound": "fp32", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
                                "algorithmic_flops_per_env_step": flops,
                                "peak_source": f"{sm_count} SMs x 128 lanes x 2 x {sm_max_mhz or 1965.0:.0f} MHz (nominal FP32 FMA issue)",
-                               "note": "first device version of this capacity set: 6 warps per SM, 2,974 candidate pairs tested per "
-                                       "substep; latency bound"}
+                               "note": "8 warps per SM (27 KB workspace and 246 registers per env both bind there), cached broad phase, "
+                                       "cost-sorted dynamic chunks; bound by per-warp dependent latency and the phase barriers, not by FMA issue"}
     del env
     return out
 

@@ -35,6 +35,8 @@ def test_engine_sections_cite_their_own_committed_ncu_capture():
         assert s is not None and bench.ENGINE_CAPTURES[task][0] in s["source"] and task in s["source"]
         assert s["registers_per_thread"] == 128 and 20 < s["achieved_occupancy_pct"] <= 25.1
         assert 0 < s["executed_ipc"] < 4 and 16 < s["active_lanes_per_instruction"] <= 32
+    k = bench.ncu_engine_summary("kitchen")
+    assert k is not None and "kitchen" in k["source"] and k["registers_per_thread"] == 246 and 12 < k["achieved_occupancy_pct"] <= 12.6
 
 
 def test_bench_names_the_host_data_path_it_measured(monkeypatch):
